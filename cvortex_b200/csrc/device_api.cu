@@ -1,0 +1,398 @@
+// device_api.cu -- the thin C ABI over the sm_100a kernels (include/cvtx_b200.h).
+//
+// Takes the place of the reference's OpenCL host layer
+//   src/ocl_P3D.cpp:150-725, src/ocl_P2D.cpp:107-631, src/ocl_F3D.cpp:72-646
+// (pack to cl_float3 -> one NDRange per 256 sources chained by events ->
+// blocking read -> scale) and of the per-device state it pulls from
+//   src/opencl_acc.cpp:203-239, src/OclPlatformState.cpp:87-213.
+// One call = pack kernel + ONE pair kernel (+ a reduce kernel when the source
+// set was split for load balance), all asynchronous on the caller's stream.
+// No CPU path lives here: errors are returned, never papered over.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+#include "../../include/cvtx_b200.h"
+#include "m2m_kernel.cuh"
+#include "runtime.h"
+
+using namespace cvtx;
+
+static_assert((int)CVTX_B200_P3D_VEL == OP_P3D_VEL && (int)CVTX_B200_F3D_DVORT == OP_F3D_DVORT, "op ids");
+static_assert((int)CVTX_B200_SINGULAR == REG_SINGULAR && (int)CVTX_B200_GAUSSIAN == REG_GAUSSIAN, "reg ids");
+
+// ---- shared runtime pieces (declared in runtime.h) ----------------------------
+namespace {
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_force_T{0}, g_force_chunks{0};
+std::mutex g_devices_mu;
+std::vector<Device *> g_devices;
+int g_device_count = -2;                                       // -2 = not probed yet
+}  // namespace
+
+int cvtx::fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+cudaError_t cvtx::Buffer::reserve(size_t bytes) {
+	if (bytes <= cap) return cudaSuccess;
+	release();
+	const size_t want = bytes + bytes / 4 + 4096;              // grow-only with headroom
+	cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocPortable) : cudaMalloc(&p, want);
+	if (e == cudaSuccess) cap = want; else p = nullptr;
+	return e;
+}
+
+void cvtx::Buffer::release() {
+	if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+	p = nullptr; cap = 0;
+}
+
+cvtx::HostStage &cvtx::host_stage() {
+	static HostStage hs;
+	hs.src.pinned = hs.tgt.pinned = hs.out.pinned = true;
+	return hs;
+}
+
+namespace {
+
+int probe_devices() {
+	std::lock_guard<std::mutex> lk(g_devices_mu);
+	if (g_device_count != -2) return g_device_count;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+		cudaGetLastError();
+		// no driver / no device is "zero accelerators", anything else is an error
+		g_device_count = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? 0 : -1;
+		return g_device_count;
+	}
+	for (int i = 0; i < n; ++i) {
+		Device *d = new Device();
+		if (cudaGetDeviceProperties(&d->prop, i) != cudaSuccess) std::memset(&d->prop, 0, sizeof(d->prop));
+		g_devices.push_back(d);
+	}
+	g_device_count = n;
+	return n;
+}
+
+int ensure_ready(Device *d) {                   // caller holds d->mu and has done cudaSetDevice
+	if (d->ready) return CVTX_B200_OK;
+	CUDA_TRY(cudaEventCreateWithFlags(&d->arena_idle, cudaEventDisableTiming));
+	CUDA_TRY(cudaEventCreate(&d->k_start));
+	CUDA_TRY(cudaEventCreate(&d->k_stop));
+	CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+	d->ready = true;
+	return CVTX_B200_OK;
+}
+
+// ---- launch planning ----------------------------------------------------------
+struct Plan { int T, B, gx, gy, tiles_per_chunk; };
+
+// Pick targets-per-thread and the number of source chunks so that the grid is
+// many waves of equal work units (see the header of m2m_kernel.cuh).
+Plan make_plan(int n_src, int n_tgt, int n_out, int sm_count) {
+	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
+	static const int cand_T[3] = {4, 2, 1}, cand_B[3] = {256, 256, 128}, cand_occ[3] = {2, 3, 8};
+	Plan p = {};
+	const int cmax = n_src_tiles >= 2 ? n_src_tiles / 2 : 1;  // a chunk is at least two tiles
+	int pick = 2;
+	for (int v = 0; v < 3; ++v) {
+		const long tiles_t = ((long)n_tgt + cand_B[v] * cand_T[v] - 1) / (cand_B[v] * cand_T[v]);
+		if (tiles_t * cmax >= 2L * sm_count * cand_occ[v]) { pick = v; break; }
+	}
+	const int fT = g_force_T.load();
+	if (fT == 4) pick = 0; else if (fT == 2) pick = 1; else if (fT == 1) pick = 2;
+	p.T = cand_T[pick]; p.B = cand_B[pick];
+	const long tiles_t = ((long)n_tgt + p.B * p.T - 1) / (p.B * p.T);
+	const long want_units = 24L * sm_count * cand_occ[pick];
+	long c = (want_units + tiles_t - 1) / tiles_t;
+	const long mem_cap = (1L << 30) / ((long)n_tgt * n_out * 8 + 1);   // keep FP64 partials under 1 GiB
+	if (c > mem_cap) c = mem_cap;
+	if (c > cmax) c = cmax;
+	if (c < 1) c = 1;
+	const int fC = g_force_chunks.load();
+	if (fC > 0) c = fC < n_src_tiles ? fC : n_src_tiles;
+	if (n_src_tiles == 0) c = 1;
+	p.tiles_per_chunk = n_src_tiles ? (int)((n_src_tiles + c - 1) / c) : 0;
+	p.gy = n_src_tiles ? (n_src_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk : 1;
+	p.gx = (int)tiles_t;
+	return p;
+}
+
+struct Launcher {
+	M2MArgs args; Plan plan; cudaStream_t st; cudaError_t err;
+	template <class P> void run() {
+		const dim3 grid(plan.gx, plan.gy);
+		if (plan.T == 4) m2m_kernel<P, 4, 256, 2><<<grid, 256, 0, st>>>(args);
+		else if (plan.T == 2) m2m_kernel<P, 2, 256, 3><<<grid, 256, 0, st>>>(args);
+		else m2m_kernel<P, 1, 128, 8><<<grid, 128, 0, st>>>(args);
+		err = cudaGetLastError();
+	}
+};
+
+struct Info {
+	int lane, sfu, tcols, nout;
+	template <class P> void run() { lane = P::LANE_OPS; sfu = P::SFU_OPS; tcols = P::TCOLS; nout = P::NOUT; }
+};
+
+struct ConstsOf {
+	float sigma, nu; PairConsts k;
+	template <class P> void run() { k = P::make_consts(sigma, nu); }
+};
+
+}  // namespace
+
+cvtx::Device *cvtx::get_device(int device) {
+	const int n = probe_devices();
+	if (device < 0 || device >= n) return nullptr;
+	return g_devices[device];
+}
+
+// =============================================================================
+extern "C" {
+
+int cvtx_b200_device_count(void) { return probe_devices(); }
+
+const char *cvtx_b200_device_name(int device) {
+	Device *d = get_device(device);
+	return d ? d->prop.name : nullptr;
+}
+
+int cvtx_b200_device_sm_count(int device) {
+	Device *d = get_device(device);
+	return d ? d->prop.multiProcessorCount : -1;
+}
+
+int cvtx_b200_device_clock_khz(int device) {
+	if (!get_device(device)) return -1;
+	int khz = 0;
+	if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) != cudaSuccess) return -1;
+	return khz;
+}
+
+void cvtx_b200_release(void) {
+	{
+		std::lock_guard<std::mutex> lk(g_devices_mu);
+		for (size_t i = 0; i < g_devices.size(); ++i) {
+			Device *d = g_devices[i];
+			std::lock_guard<std::mutex> dl(d->mu);
+			if (!d->ready) continue;
+			cudaSetDevice((int)i);
+			cudaDeviceSynchronize();
+			Buffer *all[] = {&d->packedA, &d->packedB, &d->partial, &d->d_src, &d->d_tgt, &d->d_out};
+			for (Buffer *b : all) b->release();
+			cudaEventDestroy(d->arena_idle); cudaEventDestroy(d->k_start); cudaEventDestroy(d->k_stop);
+			cudaStreamDestroy(d->stream);
+			d->ready = false; d->timed = false;
+		}
+	}
+	HostStage &hs = host_stage();
+	std::lock_guard<std::mutex> hl(hs.mu);
+	hs.src.release(); hs.tgt.release(); hs.out.release();
+}
+
+int cvtx_b200_op_info(int op, int reg, int *src_cols_, int *tgt_cols, int *out_cols, int *lane_ops, int *sfu_ops) {
+	Info q = {};
+	if (!dispatch_op(op, reg, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "no kernel for this (op, regularisation)");
+	if (src_cols_) *src_cols_ = src_cols(op);
+	if (tgt_cols) *tgt_cols = q.tcols;
+	if (out_cols) *out_cols = q.nout;
+	if (lane_ops) *lane_ops = q.lane;
+	if (sfu_ops) *sfu_ops = q.sfu;
+	return CVTX_B200_OK;
+}
+
+int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tpt, int *grid_x, int *grid_y) {
+	Device *d = get_device(device);
+	Info q = {};
+	if (!d || n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "bad device or counts");
+	if (!dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "bad op");
+	const Plan p = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount);
+	if (block) *block = p.B;
+	if (tpt) *tpt = p.T;
+	if (grid_x) *grid_x = p.gx;
+	if (grid_y) *grid_y = p.gy;
+	return CVTX_B200_OK;
+}
+
+unsigned long long cvtx_b200_kernel_launches(void) { return g_launches.load(); }
+
+void cvtx_b200_tune(int force_T, int force_chunks) { g_force_T = force_T; g_force_chunks = force_chunks; }
+
+const char *cvtx_b200_last_error(void) { return g_err.c_str(); }
+
+float cvtx_b200_last_pair_kernel_ms(int device) {
+	Device *d = get_device(device);
+	if (!d) return -1.f;
+	std::lock_guard<std::mutex> lk(d->mu);
+	if (!d->timed) return -1.f;
+	float ms = -1.f;
+	if (cudaSetDevice(device) != cudaSuccess) return -1.f;
+	if (cudaEventSynchronize(d->k_stop) != cudaSuccess) return -1.f;
+	if (cudaEventElapsedTime(&ms, d->k_start, d->k_stop) != cudaSuccess) return -1.f;
+	return ms;
+}
+
+int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, int n_src,
+                  const float *tgt, int n_tgt, float *out, float sigma, float nu)
+{
+	g_err.clear();
+	Device *d = get_device(device);
+	if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
+	if (n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "negative count");
+	if (op_is_filament(op)) reg = REG_SINGULAR;
+	Info q = {};
+	if (!dispatch_op(op, reg, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "no kernel for this (op, regularisation)");
+	if (n_tgt == 0) return CVTX_B200_OK;
+	if (!tgt || !out || (n_src > 0 && !src)) return fail(CVTX_B200_ERR_ARGUMENT, "null pointer");
+
+	cudaStream_t st = (cudaStream_t)stream_;
+	std::lock_guard<std::mutex> lk(d->mu);
+	CUDA_TRY(cudaSetDevice(device));
+	if (int rc = ensure_ready(d)) return rc;
+	if (n_src == 0) {                                  // no sources: the sums are empty
+		CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_tgt * q.nout, st));
+		return CVTX_B200_OK;
+	}
+
+	const Plan plan = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount);
+	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
+	const int n_pad = n_src_tiles * kSrcTile;
+	const bool two = src_kind(op) != SRC_P2D;
+
+	// the arena may still be in use by an earlier call on another stream
+	CUDA_TRY(cudaStreamWaitEvent(st, d->arena_idle, 0));
+	const size_t need_packed = (size_t)n_pad * sizeof(float4);
+	const size_t need_partial = plan.gy > 1 ? sizeof(double) * (size_t)plan.gy * n_tgt * q.nout : 0;
+	if (need_packed > d->packedA.cap || (two && need_packed > d->packedB.cap) || need_partial > d->partial.cap) {
+		CUDA_TRY(cudaDeviceSynchronize());             // growing frees memory earlier launches may still read
+		CUDA_TRY(d->packedA.reserve(need_packed));
+		if (two) CUDA_TRY(d->packedB.reserve(need_packed));
+		CUDA_TRY(d->partial.reserve(need_partial));
+	}
+
+	pack_sources_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src_kind(op), src_cols(op), src, n_src, n_pad,
+	                                                          (float4 *)d->packedA.p, two ? (float4 *)d->packedB.p : nullptr);
+	CUDA_TRY(cudaGetLastError());
+
+	ConstsOf ck = {sigma, nu, {}};
+	dispatch_op(op, reg, ck);
+	Launcher L = {};
+	L.args.srcA = (const float4 *)d->packedA.p;
+	L.args.srcB = two ? (const float4 *)d->packedB.p : nullptr;
+	L.args.n_src_tiles = n_src_tiles;
+	L.args.tiles_per_chunk = plan.tiles_per_chunk;
+	L.args.tgt = tgt;
+	L.args.n_tgt = n_tgt;
+	L.args.out = out;
+	L.args.partial = (double *)d->partial.p;
+	L.args.k = ck.k;
+	L.plan = plan;
+	L.st = st;
+	CUDA_TRY(cudaEventRecord(d->k_start, st));
+	dispatch_op(op, reg, L);
+	CUDA_TRY(L.err);
+	CUDA_TRY(cudaEventRecord(d->k_stop, st));
+	d->timed = true;
+	unsigned long long launched = 2;
+	if (plan.gy > 1) {
+		const long n_vals = (long)n_tgt * q.nout;
+		reduce_partials_kernel<<<(unsigned)((n_vals + 255) / 256), 256, 0, st>>>((const double *)d->partial.p, out, n_vals, plan.gy);
+		CUDA_TRY(cudaGetLastError());
+		++launched;
+	}
+	CUDA_TRY(cudaEventRecord(d->arena_idle, st));
+	g_launches += launched;
+	return CVTX_B200_OK;
+}
+
+int cvtx_b200_m2m_host(int op, int reg, int device, const float *src, int n_src, const float *tgt, int n_tgt,
+                       float *out, float sigma, float nu, size_t *h2d_bytes, size_t *d2h_bytes)
+{
+	g_err.clear();
+	if (h2d_bytes) *h2d_bytes = 0;
+	if (d2h_bytes) *d2h_bytes = 0;
+	if (!get_device(device)) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
+	if (n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "negative count");
+	if (op_is_filament(op)) reg = REG_SINGULAR;
+	Info q = {};
+	if (!dispatch_op(op, reg, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "no kernel for this (op, regularisation)");
+	if (n_tgt == 0) return CVTX_B200_OK;
+	if (!tgt || !out || (n_src > 0 && !src)) return fail(CVTX_B200_ERR_ARGUMENT, "null pointer");
+	const size_t sb = sizeof(float) * (size_t)n_src * src_cols(op);
+	const size_t tb = sizeof(float) * (size_t)n_tgt * q.tcols;
+	HostStage &hs = host_stage();
+	std::lock_guard<std::mutex> lk(hs.mu);
+	CUDA_TRY(cudaSetDevice(device));
+	CUDA_TRY(hs.src.reserve(sb));
+	CUDA_TRY(hs.tgt.reserve(tb));
+	if (sb) std::memcpy(hs.src.p, src, sb);
+	std::memcpy(hs.tgt.p, tgt, tb);
+	return run_staged(op, reg, std::vector<int>(1, device), n_src, n_tgt, out, sigma, nu, h2d_bytes, d2h_bytes);
+}
+
+}  // extern "C"
+
+// =============================================================================
+// Staged multi-device runner: one host thread drives every device
+// asynchronously (H2D of the replicated sources and of the device's target
+// shard, pack + pair kernels, D2H of the shard's result), then waits for all.
+// Targets are embarrassingly parallel -- each output is an independent sum over
+// all sources (reference src/P3D.cpp:335-339) -- so the results need no
+// collective; each device writes its own slice.
+int cvtx::run_staged(int op, int reg, const std::vector<int> &devices, int n_src, int n_tgt,
+                     float *out, float sigma, float nu, size_t *h2d_bytes, size_t *d2h_bytes)
+{
+	Info q = {};
+	if (op_is_filament(op)) reg = REG_SINGULAR;
+	if (!dispatch_op(op, reg, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "no kernel for this (op, regularisation)");
+	if (devices.empty()) return fail(CVTX_B200_ERR_ARGUMENT, "no device given");
+	HostStage &hs = host_stage();
+	const int G = (int)devices.size();
+	const size_t srow = sizeof(float) * src_cols(op), trow = sizeof(float) * q.tcols, orow = sizeof(float) * q.nout;
+	const size_t sb = srow * (size_t)n_src;
+	CUDA_TRY(cudaSetDevice(devices[0]));
+	CUDA_TRY(hs.out.reserve(orow * (size_t)n_tgt));
+	size_t up = 0, down = 0;
+	for (int g = 0; g < G; ++g) {
+		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
+		if (hi == lo) continue;
+		Device *d = get_device(devices[g]);
+		if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
+		cudaStream_t st;
+		{
+			std::lock_guard<std::mutex> lk(d->mu);
+			CUDA_TRY(cudaSetDevice(devices[g]));
+			if (int rc = ensure_ready(d)) return rc;
+			st = d->stream;
+			CUDA_TRY(d->d_src.reserve(sb));
+			CUDA_TRY(d->d_tgt.reserve(trow * (size_t)(hi - lo)));
+			CUDA_TRY(d->d_out.reserve(orow * (size_t)(hi - lo)));
+		}
+		if (sb) CUDA_TRY(cudaMemcpyAsync(d->d_src.p, hs.src.p, sb, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(d->d_tgt.p, (const char *)hs.tgt.p + trow * lo, trow * (size_t)(hi - lo),
+		                         cudaMemcpyHostToDevice, st));
+		if (int rc = cvtx_b200_m2m(op, reg, devices[g], st, (const float *)d->d_src.p, n_src,
+		                           (const float *)d->d_tgt.p, (int)(hi - lo), (float *)d->d_out.p, sigma, nu))
+			return rc;
+		CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo),
+		                         cudaMemcpyDeviceToHost, st));
+		up += sb + trow * (size_t)(hi - lo);
+		down += orow * (size_t)(hi - lo);
+	}
+	for (int g = 0; g < G; ++g) {
+		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
+		if (hi == lo) continue;
+		Device *d = get_device(devices[g]);
+		CUDA_TRY(cudaSetDevice(devices[g]));
+		CUDA_TRY(cudaStreamSynchronize(d->stream));
+		std::memcpy((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
+	}
+	if (h2d_bytes) *h2d_bytes = up;
+	if (d2h_bytes) *d2h_bytes = down;
+	return CVTX_B200_OK;
+}

@@ -1,0 +1,286 @@
+// host_api.cu -- the cvtx_* all-pairs entry points and accelerator control of
+// the public ABI (include/cvortex/libcvtx.h), on top of the staged
+// multi-device runner of device_api.cu.
+//
+// Replaces, in the reference:
+//   * the dispatch blocks of src/P3D.cpp:343-366,387-410,432-456,476-498,
+//     src/P2D.cpp:141-162,252-276, src/F3D.cpp:162-202 ("small, or no kernel
+//     name, or the GPU call failed -> OpenMP loop, else OpenCL");
+//   * src/accelerators.cpp:39-118 + src/opencl_acc.cpp:55-258 (init/finalise,
+//     device list, enable/disable, names).
+// Dispatch rule here: if at least one accelerator is enabled and the
+// cvtx_VortFunc names one of the four built-in kernels, the call runs on the
+// GPU(s) at ANY size and a failure aborts with a message; the host loops of
+// host_scalar.cpp run only when the caller disabled every accelerator or
+// supplied a user-defined regularisation.  There is no silent substitution
+// in either direction.
+//
+// A call does: gather the array-of-pointers input into the pinned staging area
+// (parallel 28/16-byte row copies) -> H2D -> pack + pair kernels -> D2H ->
+// result_array.  With several accelerators enabled the targets are split into
+// contiguous shards, one per device, sources replicated.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "export.h"
+#include "host_scalar.h"
+#include "op_table.h"
+#include "runtime.h"
+
+using namespace cvtx;
+
+namespace {
+
+std::mutex g_mu;
+bool g_init = false;
+std::vector<char> g_enabled;
+std::string g_info;
+std::atomic<int> g_last_dispatch{-1};       // 1 = GPU, 0 = host loops, -1 = none yet
+std::atomic<int> g_last_devices{0};
+
+// Below this many pairs one device finishes before a second could be fed
+// (about 2 ms of kernel time), so sharding is skipped.
+constexpr double kShardMinPairs = 2.0e9;
+
+std::vector<int> enabled_devices() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	std::vector<int> v;
+	for (size_t i = 0; i < g_enabled.size(); ++i) if (g_enabled[i]) v.push_back((int)i);
+	return v;
+}
+
+void build_info(int n_dev) {
+	int rt = 0, drv = 0;
+	cudaRuntimeGetVersion(&rt);
+	cudaDriverGetVersion(&drv);
+	char buf[256];
+	g_info = "cvortex version: 0.3.8 (B200 CUDA backend)\n";
+#if defined(__CUDACC_VER_MAJOR__)
+	std::snprintf(buf, sizeof(buf), "compiler: nvcc %d.%d / GCC %d.%d.%d\n", __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__,
+	              __GNUC__, __GNUC_MINOR__, __GNUC_PATCHLEVEL__);
+	g_info += buf;
+#endif
+	g_info += "using OpenMP: TRUE\nusing OpenCL: FALSE\n";
+	std::snprintf(buf, sizeof(buf), "using CUDA: TRUE (runtime %d, driver %d, sm_100a kernels)\naccelerators: %d\n", rt, drv, n_dev);
+	g_info += buf;
+	for (int i = 0; i < n_dev; ++i) {
+		std::snprintf(buf, sizeof(buf), "  [%d] %s, %d SMs\n", i, cvtx_b200_device_name(i), cvtx_b200_device_sm_count(i));
+		g_info += buf;
+	}
+}
+
+[[noreturn]] void gpu_failure(const char *entry, int rc) {
+	std::fprintf(stderr, "cvortex: %s failed on the GPU path (status %d): %s\n"
+	                     "cvortex: refusing to substitute a CPU result; aborting.\n",
+	             entry, rc, cvtx_b200_last_error());
+	std::abort();
+}
+
+// Copy n rows of `row_bytes` through an array of pointers into contiguous memory.
+void gather_rows(void *dst, const void *const *ptrs, long n, size_t row_bytes) {
+	char *out = (char *)dst;
+#pragma omp parallel for schedule(static) if (n > 32768)
+	for (long i = 0; i < n; ++i) std::memcpy(out + (size_t)i * row_bytes, ptrs[i], row_bytes);
+}
+void copy_rows(void *dst, const void *src, long n, size_t row_bytes) {
+	const size_t total = (size_t)n * row_bytes, piece = 1 << 20;
+	const long pieces = (long)((total + piece - 1) / piece);
+#pragma omp parallel for schedule(static) if (pieces > 8)
+	for (long i = 0; i < pieces; ++i) {
+		const size_t lo = (size_t)i * piece, len = lo + piece <= total ? piece : total - lo;
+		std::memcpy((char *)dst + lo, (const char *)src + lo, len);
+	}
+}
+
+// The GPU route of every M2M entry point.  Returns false when the call is not
+// the GPU's to take (nothing enabled / user-defined regularisation), in which
+// case the caller runs the host loops; aborts on a GPU failure.
+bool gpu_m2m(const char *entry, int op, const cvtx_VortFunc *kernel,
+             const void *const *src_ptrs, int n_src,
+             const void *tgt_flat, const void *const *tgt_ptrs, int n_tgt,
+             void *result, float sigma, float nu)
+{
+	int reg = REG_SINGULAR;
+	if (!op_is_filament(op)) {
+		reg = reg_from_name(kernel->cl_kernel_name_ext);
+		if (reg < 0 || !op_supported(op, reg)) return false;
+	}
+	std::vector<int> devs = enabled_devices();
+	if (devs.empty()) return false;
+	g_last_dispatch = 1;
+	if (n_tgt <= 0) return true;
+	if ((double)n_src * (double)n_tgt < kShardMinPairs) devs.resize(1);
+	g_last_devices = (int)devs.size();
+
+	int tcols = 0, scols = 0;
+	cvtx_b200_op_info(op, reg, &scols, &tcols, nullptr, nullptr, nullptr);
+	const size_t srow = sizeof(float) * scols, trow = sizeof(float) * tcols;
+	HostStage &hs = host_stage();
+	std::lock_guard<std::mutex> lk(hs.mu);
+	cudaError_t e = cudaSetDevice(devs[0]);
+	if (e == cudaSuccess) e = hs.src.reserve(srow * (size_t)(n_src > 0 ? n_src : 0));
+	if (e == cudaSuccess) e = hs.tgt.reserve(trow * (size_t)n_tgt);
+	if (e != cudaSuccess) {
+		fail(CVTX_B200_ERR_CUDA, std::string("pinned staging: ") + cudaGetErrorString(e));
+		gpu_failure(entry, CVTX_B200_ERR_CUDA);
+	}
+	if (n_src > 0) gather_rows(hs.src.p, src_ptrs, n_src, srow);
+	if (tgt_ptrs) gather_rows(hs.tgt.p, tgt_ptrs, n_tgt, trow);
+	else copy_rows(hs.tgt.p, tgt_flat, n_tgt, trow);
+	const int rc = run_staged(op, reg, devs, n_src > 0 ? n_src : 0, n_tgt, (float *)result, sigma, nu, nullptr, nullptr);
+	if (rc != CVTX_B200_OK) gpu_failure(entry, rc);
+	return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- diagnostics (declared in cvtx_b200.h) -------------------------------------
+CVTX_API int cvtx_b200_last_dispatch(void) { return g_last_dispatch.load(); }
+CVTX_API int cvtx_b200_last_devices_used(void) { return g_last_devices.load(); }
+
+// ---- library / accelerator control ---------------------------------------------
+CVTX_API void cvtx_initialise() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (g_init) return;                                  // idempotent, like reference src/opencl_acc.cpp:55-67
+	int n = cvtx_b200_device_count();
+	if (n < 0) {
+		std::fprintf(stderr, "cvortex: CUDA initialisation failed: %s\n", cvtx_b200_last_error());
+		n = 0;
+	}
+	g_enabled.assign((size_t)n, 0);
+	// Default: accelerator 0 only, as the reference does (src/opencl_acc.cpp:192-201).
+	// CVTX_B200_ENABLE=all turns every device on for callers that cannot be
+	// changed to call cvtx_accelerator_enable() themselves.
+	const char *env = std::getenv("CVTX_B200_ENABLE");
+	if (n > 0) g_enabled[0] = 1;
+	if (env && !std::strcmp(env, "all")) g_enabled.assign((size_t)n, 1);
+	build_info(n);
+	g_init = true;
+}
+
+CVTX_API void cvtx_finalise() {
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		if (!g_init) return;
+		g_enabled.clear();
+		g_info.clear();
+		g_init = false;
+	}
+	cvtx_b200_release();
+}
+
+CVTX_API const char *cvtx_information() { return g_info.c_str(); }
+
+CVTX_API int cvtx_num_accelerators() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	return (int)g_enabled.size();
+}
+
+CVTX_API int cvtx_num_enabled_accelerators() {
+	std::lock_guard<std::mutex> lk(g_mu);
+	int c = 0;
+	for (char e : g_enabled) c += e ? 1 : 0;
+	return c;
+}
+
+CVTX_API const char *cvtx_accelerator_name(int accelerator_id) {
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		if (accelerator_id < 0 || accelerator_id >= (int)g_enabled.size()) return nullptr;
+	}
+	return cvtx_b200_device_name(accelerator_id);
+}
+
+CVTX_API int cvtx_accelerator_enabled(int accelerator_id) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (accelerator_id < 0 || accelerator_id >= (int)g_enabled.size()) return 0;
+	return g_enabled[accelerator_id] ? 1 : 0;
+}
+
+CVTX_API void cvtx_accelerator_enable(int accelerator_id) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (accelerator_id >= 0 && accelerator_id < (int)g_enabled.size()) g_enabled[accelerator_id] = 1;
+}
+
+CVTX_API void cvtx_accelerator_disable(int accelerator_id) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (accelerator_id >= 0 && accelerator_id < (int)g_enabled.size()) g_enabled[accelerator_id] = 0;
+}
+
+// ---- the hot path --------------------------------------------------------------
+#define PTRS(p) ((const void *const *)(p))
+
+CVTX_API void cvtx_P3D_M2M_vel(const cvtx_P3D **array_start, const int num_particles, const bsv_V3f *mes_start,
+                               const int num_mes, bsv_V3f *result_array, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	if (gpu_m2m("cvtx_P3D_M2M_vel", OP_P3D_VEL, kernel, PTRS(array_start), num_particles, mes_start, nullptr, num_mes,
+	            result_array, regularisation_radius, 0.f)) return;
+	g_last_dispatch = 0;
+	host_m2m_p3d_vel(array_start, num_particles, mes_start, num_mes, result_array, kernel, regularisation_radius);
+}
+
+CVTX_API void cvtx_P3D_M2M_dvort(const cvtx_P3D **array_start, const int num_particles, const cvtx_P3D **induced_start,
+                                 const int num_induced, bsv_V3f *result_array, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	if (gpu_m2m("cvtx_P3D_M2M_dvort", OP_P3D_DVORT, kernel, PTRS(array_start), num_particles, nullptr, PTRS(induced_start),
+	            num_induced, result_array, regularisation_radius, 0.f)) return;
+	g_last_dispatch = 0;
+	host_m2m_p3d_dvort(array_start, num_particles, induced_start, num_induced, result_array, kernel, regularisation_radius);
+}
+
+CVTX_API void cvtx_P3D_M2M_visc_dvort(const cvtx_P3D **array_start, const int num_particles, const cvtx_P3D **induced_start,
+                                      const int num_induced, bsv_V3f *result_array, const cvtx_VortFunc *kernel,
+                                      float regularisation_radius, float kinematic_visc) {
+	if (gpu_m2m("cvtx_P3D_M2M_visc_dvort", OP_P3D_VISC, kernel, PTRS(array_start), num_particles, nullptr, PTRS(induced_start),
+	            num_induced, result_array, regularisation_radius, kinematic_visc)) return;
+	g_last_dispatch = 0;
+	host_m2m_p3d_visc(array_start, num_particles, induced_start, num_induced, result_array, kernel, regularisation_radius, kinematic_visc);
+}
+
+CVTX_API void cvtx_P3D_M2M_vort(const cvtx_P3D **array_start, const int num_particles, const bsv_V3f *mes_start,
+                                const int num_mes, bsv_V3f *result_array, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	if (gpu_m2m("cvtx_P3D_M2M_vort", OP_P3D_VORT, kernel, PTRS(array_start), num_particles, mes_start, nullptr, num_mes,
+	            result_array, regularisation_radius, 0.f)) return;
+	g_last_dispatch = 0;
+	host_m2m_p3d_vort(array_start, num_particles, mes_start, num_mes, result_array, kernel, regularisation_radius);
+}
+
+CVTX_API void cvtx_P2D_M2M_vel(const cvtx_P2D **array_start, const int num_particles, const bsv_V2f *mes_start,
+                               const int num_mes, bsv_V2f *result_array, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	if (gpu_m2m("cvtx_P2D_M2M_vel", OP_P2D_VEL, kernel, PTRS(array_start), num_particles, mes_start, nullptr, num_mes,
+	            result_array, regularisation_radius, 0.f)) return;
+	g_last_dispatch = 0;
+	host_m2m_p2d_vel(array_start, num_particles, mes_start, num_mes, result_array, kernel, regularisation_radius);
+}
+
+CVTX_API void cvtx_P2D_M2M_visc_dvort(const cvtx_P2D **array_start, const int num_particles, const cvtx_P2D **induced_start,
+                                      const int num_induced, float *result_array, const cvtx_VortFunc *kernel,
+                                      float regularisation_radius, float kinematic_visc) {
+	if (gpu_m2m("cvtx_P2D_M2M_visc_dvort", OP_P2D_VISC, kernel, PTRS(array_start), num_particles, nullptr, PTRS(induced_start),
+	            num_induced, result_array, regularisation_radius, kinematic_visc)) return;
+	g_last_dispatch = 0;
+	host_m2m_p2d_visc(array_start, num_particles, induced_start, num_induced, result_array, kernel, regularisation_radius, kinematic_visc);
+}
+
+CVTX_API void cvtx_F3D_M2M_vel(const cvtx_F3D **array_start, const int num_filaments, const bsv_V3f *mes_start,
+                               const int num_mes, bsv_V3f *result_array) {
+	if (gpu_m2m("cvtx_F3D_M2M_vel", OP_F3D_VEL, nullptr, PTRS(array_start), num_filaments, mes_start, nullptr, num_mes,
+	            result_array, 0.f, 0.f)) return;
+	g_last_dispatch = 0;
+	host_m2m_f3d_vel(array_start, num_filaments, mes_start, num_mes, result_array);
+}
+
+CVTX_API void cvtx_F3D_M2M_dvort(const cvtx_F3D **array_start, const int num_filaments, const cvtx_P3D **induced_start,
+                                 const int num_induced, bsv_V3f *result_array) {
+	if (gpu_m2m("cvtx_F3D_M2M_dvort", OP_F3D_DVORT, nullptr, PTRS(array_start), num_filaments, nullptr, PTRS(induced_start),
+	            num_induced, result_array, 0.f, 0.f)) return;
+	g_last_dispatch = 0;
+	host_m2m_f3d_dvort(array_start, num_filaments, induced_start, num_induced, result_array);
+}
+
+}  // extern "C"

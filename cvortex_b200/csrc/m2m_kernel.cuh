@@ -1,0 +1,205 @@
+// m2m_kernel.cuh -- the all-pairs kernel: every M2M op of the hot path is this
+// one template, instantiated with a pair policy from pair_math.cuh.
+//
+// It replaces the reference's OpenCL scheme (src/nbody.cl:38-73 + the host
+// loop src/ocl_P3D.cpp:259-291): there one work-item evaluates ONE pair, a
+// 256-wide shared-memory tree adds them up, work-item 0 read-modify-writes the
+// target's result, and the host launches one NDRange per 256 sources.  Here
+//
+//   grid  = (target tiles, source chunks); ONE launch per call
+//   block = B threads, each owning T targets held in registers for the
+//           whole kernel (positions + per-target attributes)
+//   the block streams its source chunk through shared memory in tiles of S
+//   packed records, double-buffered with 1-D TMA bulk copies
+//   (cp.async.bulk + mbarrier transaction counts) issued by one thread, so the
+//   math warps spend no issue slots on loads or address arithmetic;
+//   every thread reads the same source record at the same time -> LDS.128
+//   broadcasts, 2 per source per warp, amortised over T targets;
+//   running sums are FP32 per chain (a tile, or Policy::CHAIN sources) and
+//   are flushed into FP64 accumulators, matching the reference CPU path's
+//   double accumulation (src/P3D.cpp:237-249) at ~0.1 % extra instructions;
+//   the epilogue applies Policy::finish() in FP64 and either writes the
+//   final floats (one chunk) or FP64 partials that reduce_partials_kernel
+//   adds in a fixed order (deterministic, no atomics).
+//
+// The source-chunk dimension exists for load balance only: 1M targets give 977
+// target tiles of 1024, i.e. 3.3 waves on 296 resident blocks (18 % tail
+// loss); splitting the sources C ways turns that into 3.3*C waves of work
+// units that the hardware block scheduler hands out dynamically.  blockIdx.x
+// (fastest) walks the target tiles so that co-resident blocks read the same
+// source chunk from L2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "op_table.h"
+
+namespace cvtx {
+
+constexpr int kSrcTile = 256;   // S: packed sources per shared-memory tile (also the padding quantum)
+
+struct M2MArgs {
+	const float4 *srcA;        // packed source records, padded to a multiple of kSrcTile
+	const float4 *srcB;        // second record (unused when Policy::NSRC4 == 1)
+	int n_src_tiles;           // total tiles of kSrcTile sources
+	int tiles_per_chunk;       // tiles handled by one blockIdx.y
+	const float *tgt;          // raw target rows, Policy::TCOLS floats each
+	int n_tgt;
+	float *out;                // final result, Policy::NOUT floats per target (gridDim.y == 1)
+	double *partial;           // [gridDim.y][n_tgt][NOUT] FP64 partials (gridDim.y > 1)
+	PairConsts k;
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred p;\n\t"
+	    "WAIT_%=:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@p bra DONE_%=;\n\t"
+	    "bra WAIT_%=;\n\t"
+	    "DONE_%=:\n\t"
+	    "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class P, int T, int B, int MINB>
+__global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
+{
+	constexpr int S = kSrcTile;
+	constexpr int CHAIN = P::CHAIN ? P::CHAIN : S;
+	constexpr int UNROLL = CHAIN < 8 ? CHAIN : 8;
+	static_assert(S % CHAIN == 0, "a tile must hold whole chains");
+	constexpr uint32_t kTileBytes = S * sizeof(float4);
+
+	__shared__ __align__(128) float4 tileA[2][S];
+	__shared__ __align__(128) float4 tileB[2][P::NSRC4 == 2 ? S : 1];
+	__shared__ __align__(8) uint64_t full[2];
+
+	const int tid = threadIdx.x;
+	const int tile0 = blockIdx.y * args.tiles_per_chunk;
+	const int ntile = min(args.tiles_per_chunk, args.n_src_tiles - tile0);
+	const float4 *gA = args.srcA + (size_t)tile0 * S;
+	const float4 *gB = args.srcB + (size_t)tile0 * S;
+
+	if (tid == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
+	if (tid == 0 && ntile > 0) {
+		mbar_expect_tx(&full[0], kTileBytes * P::NSRC4);
+		bulk_g2s(tileA[0], gA, kTileBytes, &full[0]);
+		if (P::NSRC4 == 2) bulk_g2s(tileB[0], gB, kTileBytes, &full[0]);
+	}
+
+	// ---- this thread's T targets, strided by B so a warp touches contiguous rows
+	const long base = (long)blockIdx.x * (B * T) + tid;
+	float tg[T][P::NTGT];
+	double dacc[T][P::NACC];
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		long i = base + (long)t * B;
+		i = i < args.n_tgt ? i : (long)args.n_tgt - 1;          // clamp: tail threads redo the last target, never store
+		P::load_target(args.tgt + i * P::TCOLS, tg[t]);
+#pragma unroll
+		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
+	}
+
+	for (int it = 0; it < ntile; ++it) {
+		const int buf = it & 1;
+		if (tid == 0 && it + 1 < ntile) {                          // prefetch the next tile into the other buffer
+			mbar_expect_tx(&full[buf ^ 1], kTileBytes * P::NSRC4);
+			bulk_g2s(tileA[buf ^ 1], gA + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
+			if (P::NSRC4 == 2) bulk_g2s(tileB[buf ^ 1], gB + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
+		}
+		mbar_wait(&full[buf], (it >> 1) & 1);
+
+		const float4 *sA = tileA[buf];
+		const float4 *sB = tileB[P::NSRC4 == 2 ? buf : 0];
+#pragma unroll 1
+		for (int j0 = 0; j0 < S; j0 += CHAIN) {
+			float acc[T][P::NACC];
+#pragma unroll
+			for (int t = 0; t < T; ++t)
+#pragma unroll
+				for (int c = 0; c < P::NACC; ++c) acc[t][c] = 0.0f;
+#pragma unroll UNROLL
+			for (int j = 0; j < CHAIN; ++j) {
+				const float4 a = sA[j0 + j];
+				float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (P::NSRC4 == 2) b = sB[j0 + j];
+#pragma unroll
+				for (int t = 0; t < T; ++t) P::pair(tg[t], a, b, acc[t], args.k);
+			}
+#pragma unroll
+			for (int t = 0; t < T; ++t)
+#pragma unroll
+				for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t][c];
+		}
+		__syncthreads();      // everyone is done with tile[buf] before it is refilled two iterations on
+	}
+
+	// ---- epilogue: FP64 finish, then final floats or FP64 partials
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		const long i = base + (long)t * B;
+		if (i < args.n_tgt) {
+			double res[P::NOUT];
+			P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
+			if (gridDim.y == 1) {
+#pragma unroll
+				for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)res[c];
+			} else {
+				double *dst = args.partial + ((size_t)blockIdx.y * args.n_tgt + i) * P::NOUT;
+#pragma unroll
+				for (int c = 0; c < P::NOUT; ++c) dst[c] = res[c];
+			}
+		}
+	}
+}
+
+// out[i] = (float) sum_c partial[c][i], chunks added in index order.
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, float *__restrict__ out,
+                                       long n_vals, int n_chunks)
+{
+	const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_vals) return;
+	double s = 0.0;
+	for (int c = 0; c < n_chunks; ++c) s += partial[(size_t)c * n_vals + i];
+	out[i] = (float)s;
+}
+
+// Raw rows -> packed float4 records, zero-padded to n_pad (a multiple of kSrcTile).
+__global__ void pack_sources_kernel(int kind, int cols, const float *__restrict__ rows, int n, int n_pad,
+                                    float4 *__restrict__ A, float4 *__restrict__ Bq)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pad) return;
+	float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+	if (i < n) {
+		float row[7];
+		for (int c = 0; c < cols; ++c) row[c] = rows[(size_t)i * cols + c];
+		pack_source(kind, row, a, b);
+	}
+	A[i] = a;
+	if (Bq) Bq[i] = b;
+}
+
+}  // namespace cvtx

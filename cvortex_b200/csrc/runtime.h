@@ -1,0 +1,64 @@
+// runtime.h -- internal to libcvortex.so: per-device state, the library-wide
+// pinned staging area and the staged multi-device runner shared by
+// device_api.cu (thin C ABI) and host_api.cu (the cvtx_* entry points).
+//
+// Replaces the reference's global `ocl_state` (src/opencl_acc.cpp:42-49) and
+// the per-call clCreateBuffer / clEnqueueWriteBuffer traffic of its host
+// wrappers (src/ocl_P3D.cpp:187-222, :260-275): buffers here are grow-only and
+// live for the life of the library.
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/cvtx_b200.h"
+
+namespace cvtx {
+
+struct Buffer {
+	void *p = nullptr; size_t cap = 0; bool pinned = false;
+	cudaError_t reserve(size_t bytes);
+	void release();
+};
+
+struct Device {
+	std::mutex mu;
+	bool ready = false;
+	cudaDeviceProp prop;
+	// arena of cvtx_b200_m2m
+	Buffer packedA, packedB, partial;
+	cudaEvent_t arena_idle = nullptr, k_start = nullptr, k_stop = nullptr;
+	bool timed = false;
+	// raw rows of the staged (host-array) path
+	cudaStream_t stream = nullptr;
+	Buffer d_src, d_tgt, d_out;
+};
+
+// Library-wide pinned (portable) staging: sources, targets and results of ONE
+// all-pairs call at a time.  Hold `mu` from the first write into src/tgt until
+// run_staged() has returned.
+struct HostStage {
+	std::mutex mu;
+	Buffer src, tgt, out;
+};
+HostStage &host_stage();
+
+int fail(int code, const std::string &msg);
+Device *get_device(int device);
+
+// Run (op, reg) with n_src source rows in host_stage().src and n_tgt target
+// rows in host_stage().tgt.  Targets are split into contiguous shards over
+// `devices` (every device gets the full source set); each shard's result lands
+// in host_stage().out and is copied to `out`.  Synchronous.  Caller holds
+// host_stage().mu.
+int run_staged(int op, int reg, const std::vector<int> &devices, int n_src, int n_tgt,
+               float *out, float sigma, float nu, size_t *h2d_bytes, size_t *d2h_bytes);
+
+}  // namespace cvtx
+
+#define CUDA_TRY(expr)                                                                                    \
+	do {                                                                                                  \
+		cudaError_t e_ = (expr);                                                                          \
+		if (e_ != cudaSuccess)                                                                            \
+			return cvtx::fail(CVTX_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+	} while (0)

@@ -1,0 +1,135 @@
+#ifndef CVTX_B200_H
+#define CVTX_B200_H
+/*
+ * cvtx_b200.h -- the thin C ABI of the B200 all-pairs backend.
+ *
+ * This is the seam the reference has between its front ends and its OpenCL
+ * host layer: `int opencl_brute_force_<OBJ>_M2M_<fn>(...)`, 0 = done, -1 =
+ * "could not, caller decides" (reference src/ocl_P3D.h:33-117, src/ocl_P2D.h,
+ * src/ocl_F3D.h:32-77), plus the device bookkeeping of src/opencl_acc.h:43-95.
+ * The public drop-in surface stays the reference's own `cvtx_*` ABI
+ * (include/cvortex/libcvtx.h in this repo, same 52 symbols); libcvortex.so
+ * exports both.  Everything here is `extern "C"`, plain pointers and sizes.
+ *
+ * Two levels:
+ *   cvtx_b200_m2m()       device pointers in, device pointer out, asynchronous
+ *                         on the caller's stream -- for callers that keep their
+ *                         particles on the GPU (one process per GPU under
+ *                         torch.distributed uses this), and what the kernel-only
+ *                         benchmark times.
+ *   cvtx_b200_m2m_host()  flat host arrays in/out on one device, synchronous:
+ *                         pinned staging + H2D + cvtx_b200_m2m + D2H.
+ * The pointer-array entry points (`cvtx_P3D_M2M_vel(const cvtx_P3D **...)`) sit on
+ * top of these in host_api.cpp: gather, shard targets over the enabled
+ * devices, call, scatter.
+ *
+ * Row formats are the reference's structs verbatim:
+ *   P3D particle = 7 floats  x y z wx wy wz vol             (libcvtx.h:53-57)
+ *   P2D particle = 4 floats  x y vorticity area             (libcvtx.h:66-70)
+ *   F3D filament = 7 floats  ax ay az bx by bz strength     (libcvtx.h:60-63)
+ *   bsv_V3f / bsv_V2f points and results = 3 / 2 packed floats
+ *
+ * There is no CPU fallback anywhere behind this header: a call either runs
+ * the CUDA kernels or returns an error code with cvtx_b200_last_error() set.
+ */
+#include <stddef.h>
+
+#ifndef CVTX_B200_API
+# if defined(__GNUC__)
+#  define CVTX_B200_API __attribute__((visibility("default")))
+# else
+#  define CVTX_B200_API
+# endif
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Ops: which reference entry point a call implements. */
+enum cvtx_b200_op {
+	CVTX_B200_P3D_VEL = 0,        /* cvtx_P3D_M2M_vel         src (n,7)  tgt (m,3)  out (m,3) */
+	CVTX_B200_P3D_DVORT = 1,      /* cvtx_P3D_M2M_dvort       src (n,7)  tgt (m,7)  out (m,3) */
+	CVTX_B200_P3D_VISC_DVORT = 2, /* cvtx_P3D_M2M_visc_dvort  src (n,7)  tgt (m,7)  out (m,3) */
+	CVTX_B200_P3D_VORT = 3,       /* cvtx_P3D_M2M_vort        src (n,7)  tgt (m,3)  out (m,3) */
+	CVTX_B200_P2D_VEL = 4,        /* cvtx_P2D_M2M_vel         src (n,4)  tgt (m,2)  out (m,2) */
+	CVTX_B200_P2D_VISC_DVORT = 5, /* cvtx_P2D_M2M_visc_dvort  src (n,4)  tgt (m,4)  out (m,1) */
+	CVTX_B200_F3D_VEL = 6,        /* cvtx_F3D_M2M_vel         src (n,7)  tgt (m,3)  out (m,3) */
+	CVTX_B200_F3D_DVORT = 7       /* cvtx_F3D_M2M_dvort       src (n,7)  tgt (m,7)  out (m,3) */
+};
+
+/* Regularisations: the four values of cvtx_VortFunc::cl_kernel_name_ext the
+ * reference accelerates (src/VortFunc.cpp:210,223,236,249).  Ignored by the
+ * filament ops.  visc ops accept WINCKELMANS and GAUSSIAN only. */
+enum cvtx_b200_reg {
+	CVTX_B200_SINGULAR = 0,
+	CVTX_B200_WINCKELMANS = 1,
+	CVTX_B200_PLANETARY = 2,
+	CVTX_B200_GAUSSIAN = 3
+};
+
+enum cvtx_b200_status {
+	CVTX_B200_OK = 0,
+	CVTX_B200_ERR_UNSUPPORTED = -1,   /* (op, reg) has no kernel */
+	CVTX_B200_ERR_ARGUMENT = -2,      /* bad device / negative count / null pointer */
+	CVTX_B200_ERR_CUDA = -3           /* a CUDA call failed; see cvtx_b200_last_error() */
+};
+
+/* ---- devices (replaces reference src/opencl_acc.cpp:55-130, OclDeviceState) ---- */
+CVTX_B200_API int cvtx_b200_device_count(void);                       /* CUDA devices visible; <0 = CUDA error */
+CVTX_B200_API const char *cvtx_b200_device_name(int device);          /* library-owned string, NULL for a bad index */
+CVTX_B200_API int cvtx_b200_device_sm_count(int device);
+CVTX_B200_API int cvtx_b200_device_clock_khz(int device);             /* cudaDevAttrClockRate */
+CVTX_B200_API void cvtx_b200_release(void);                           /* free every per-device arena / pinned buffer */
+
+/* ---- the hot path ------------------------------------------------------------ */
+/* Asynchronous on `stream` (a cudaStream_t, NULL = the legacy default stream)
+ * of `device`.  All pointers are device pointers on that device; n_src rows of
+ * sources act on n_tgt rows of targets; out receives n_tgt rows and is
+ * overwritten (zeros when n_src == 0).  Scratch comes from a per-device
+ * arena owned by the library; successive calls on one device are ordered
+ * against each other even across different streams. */
+CVTX_B200_API int cvtx_b200_m2m(int op, int reg, int device, void *stream,
+                  const float *src_dev, int n_src,
+                  const float *tgt_dev, int n_tgt,
+                  float *out_dev, float sigma, float nu);
+
+/* Synchronous, host arrays, one device.  Bytes moved are reported through the
+ * optional out-parameters (NULL to ignore). */
+CVTX_B200_API int cvtx_b200_m2m_host(int op, int reg, int device,
+                       const float *src, int n_src,
+                       const float *tgt, int n_tgt,
+                       float *out, float sigma, float nu,
+                       size_t *h2d_bytes, size_t *d2h_bytes);
+
+/* ---- introspection ------------------------------------------------------------ */
+/* Shape and roofline metadata of (op, reg): floats per source / target / output
+ * row, and the algorithmic FP32 lane-ops and MUFU ops per pair of the kernel's
+ * formulation. */
+CVTX_B200_API int cvtx_b200_op_info(int op, int reg, int *src_cols, int *tgt_cols, int *out_cols,
+                      int *lane_ops_per_pair, int *sfu_ops_per_pair);
+/* Geometry the planner would use: threads per block, targets per thread,
+ * grid.x (target tiles), grid.y (source chunks). */
+CVTX_B200_API int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tgt_per_thread,
+                   int *grid_x, int *grid_y);
+/* Kernels launched by this library since load (pack + pair + reduce). */
+CVTX_B200_API unsigned long long cvtx_b200_kernel_launches(void);
+/* Time the all-pairs kernel alone: cudaEvents recorded on `stream` immediately
+ * around the pair-kernel launch of the most recent cvtx_b200_m2m() call on
+ * `device`.  Blocks until that kernel finishes.  <0 if nothing was recorded. */
+CVTX_B200_API float cvtx_b200_last_pair_kernel_ms(int device);
+/* Experiments only: force targets-per-thread (1, 2, 4; 0 = planner) and the
+ * number of source chunks (0 = planner). */
+CVTX_B200_API void cvtx_b200_tune(int force_tgt_per_thread, int force_chunks);
+/* Which route the most recent cvtx_*_M2M_* call of the public ABI took:
+ * 1 = the CUDA kernels, 0 = the host loops (every accelerator disabled, or a
+ * user-defined cvtx_VortFunc), -1 = no call yet; and on how many devices. */
+CVTX_B200_API int cvtx_b200_last_dispatch(void);
+CVTX_B200_API int cvtx_b200_last_devices_used(void);
+/* Thread-local description of the last failure in this thread ("" if none). */
+CVTX_B200_API const char *cvtx_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVTX_B200_H */

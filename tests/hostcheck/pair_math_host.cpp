@@ -1,0 +1,67 @@
+// pair_math_host.cpp -- TEST-ONLY host build of the device pair arithmetic.
+//
+// Compiles cvortex_b200/csrc/pair_math.cuh + op_table.h with g++ (MUFU ops
+// replaced by libm) and runs the *same summation structure* the CUDA kernel
+// uses -- sources packed into float4 records and zero-padded to whole tiles,
+// FP32 partial sums per chain (Policy::CHAIN sources, or a 256-source tile) flushed into FP64, Policy::finish() --
+// so the algebraic rewrites (bilinear hoisting, division-free Winckelmans,
+// packed filament records, coincident-pair rule) can be validated against the
+// oracle on a machine without a GPU.  It is not part of the product and is
+// never a fallback for it: it lives under tests/ and is built by
+// tests/conftest.py into tests/_build/.
+#include <vector>
+#include <cstring>
+#include "../../cvortex_b200/csrc/op_table.h"
+
+using namespace cvtx;
+
+namespace {
+struct Runner {
+	const float *src; int n; const float *tgt; int m; float *out; int op; float sigma, nu;
+	template <class P> void run() {
+		const int S = 256;
+		const int kind = src_kind(op), cols = src_cols(op);
+		const long npad = ((long)n + S - 1) / S * S;
+		std::vector<f4> A(npad), B(npad);
+		std::memset(A.data(), 0, sizeof(f4) * npad);
+		std::memset(B.data(), 0, sizeof(f4) * npad);
+		for (long j = 0; j < n; ++j) pack_source(kind, src + cols * j, A[j], B[j]);
+		const PairConsts k = P::make_consts(sigma, nu);
+#pragma omp parallel for schedule(static)
+		for (long i = 0; i < m; ++i) {
+			const float *row = tgt + (long)P::TCOLS * i;
+			float tg[P::NTGT];
+			P::load_target(row, tg);
+			double dacc[P::NACC];
+			for (int c = 0; c < P::NACC; ++c) dacc[c] = 0.0;
+			const int chain = P::CHAIN ? P::CHAIN : S;
+			for (long t0 = 0; t0 < npad; t0 += chain) {
+				float acc[P::NACC];
+				for (int c = 0; c < P::NACC; ++c) acc[c] = 0.0f;
+				for (long j = t0; j < t0 + chain; ++j) P::pair(tg, A[j], B[j], acc, k);
+				for (int c = 0; c < P::NACC; ++c) dacc[c] += (double)acc[c];
+			}
+			double res[P::NOUT];
+			P::finish(row, dacc, res, k);
+			for (int c = 0; c < P::NOUT; ++c) out[(long)P::NOUT * i + c] = (float)res[c];
+		}
+	}
+};
+struct Meta {
+	int *v;
+	template <class P> void run() { v[0] = P::LANE_OPS; v[1] = P::SFU_OPS; v[2] = P::TCOLS; v[3] = P::NOUT; v[4] = P::NACC; v[5] = P::NSRC4; }
+};
+}  // namespace
+
+extern "C" int hostcheck_m2m(int op, int reg, const float *src, int n, const float *tgt, int m,
+                             float *out, float sigma, float nu)
+{
+	Runner r = {src, n, tgt, m, out, op, sigma, nu};
+	return dispatch_op(op, reg, r) ? 0 : -1;
+}
+
+extern "C" int hostcheck_meta(int op, int reg, int *six)
+{
+	Meta q = {six};
+	return dispatch_op(op, reg, q) ? 0 : -1;
+}

@@ -1,0 +1,120 @@
+"""GPU tests of the thin device-level C ABI (include/cvtx_b200.h) and of size-independent
+properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+from util import SHAPES, make_case, particles3d, points, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+def test_m2m_host_matches_oracle_and_counts_bytes(gpu, oracle):
+    _, dev = gpu
+    rng = np.random.default_rng(1)
+    for op, reg in (("P3D_M2M_vel", "winckelmans"), ("P3D_M2M_dvort", "gaussian"), ("P2D_M2M_vel", "gaussian"),
+                    ("P2D_M2M_visc_dvort", "winckelmans"), ("F3D_M2M_vel", "singular")):
+        src, tgt = make_case(op, rng, 3001, 999, self_targets=False)
+        before = dev.kernel_launches()
+        out, up, down = dev.m2m_host(op, reg, 0, src, tgt, 0.05, 0.2)
+        assert dev.kernel_launches() - before >= 2          # pack + pair (+ reduce)
+        assert up == src.nbytes + tgt.nbytes and down == out.nbytes
+        want = oracle.m2m(op, src, tgt, reg, 0.05, 0.2)
+        assert rel_l2(out.reshape(want.shape), want) <= TOL
+        assert dev.last_pair_kernel_ms(0) > 0
+
+
+def test_m2m_on_torch_tensors_and_streams(gpu, oracle, torch_cuda):
+    torch = torch_cuda
+    _, dev = gpu
+    rng = np.random.default_rng(2)
+    P, X = particles3d(rng, 4096 + 77), points(rng, 2048 + 5, 3)
+    src, tgt = torch.from_numpy(P).cuda(), torch.from_numpy(X).cuda()
+    out = torch.full((X.shape[0], 3), float("nan"), device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        dev.m2m("P3D_M2M_vel", "winckelmans", 0, side.cuda_stream, src, P.shape[0], tgt, X.shape[0], out, 0.02)
+    side.synchronize()
+    assert rel_l2(out.cpu().numpy(), oracle.m2m("P3D_M2M_vel", P, X, "winckelmans", 0.02)) <= TOL
+    # back-to-back calls on different streams share the arena safely
+    out2 = torch.empty_like(out)
+    dev.m2m("P3D_M2M_vel", "gaussian", 0, torch.cuda.current_stream().cuda_stream, src, P.shape[0], tgt, X.shape[0], out2, 0.02)
+    with torch.cuda.stream(side):
+        dev.m2m("P3D_M2M_vel", "winckelmans", 0, side.cuda_stream, src, P.shape[0], tgt, X.shape[0], out, 0.02)
+    torch.cuda.synchronize()
+    assert rel_l2(out2.cpu().numpy(), oracle.m2m("P3D_M2M_vel", P, X, "gaussian", 0.02)) <= TOL
+    assert rel_l2(out.cpu().numpy(), oracle.m2m("P3D_M2M_vel", P, X, "winckelmans", 0.02)) <= TOL
+
+
+def test_errors_are_reported_not_hidden(gpu):
+    from cvortex_b200.device import BackendError
+    _, dev = gpu
+    with pytest.raises(BackendError):
+        dev.m2m_host("P3D_M2M_visc_dvort", "singular", 0, np.zeros((4, 7), np.float32), np.zeros((4, 7), np.float32))
+    with pytest.raises(BackendError):
+        dev.m2m_host("P3D_M2M_vel", "winckelmans", 99, np.zeros((4, 7), np.float32), np.zeros((4, 3), np.float32))
+
+
+# ---- BASELINE.json sizes: properties that need no O(N*M) CPU work ----------------
+def _device_run(dev, torch, op, reg, src_t, tgt_t, sigma, nu=1.0):
+    ocols = SHAPES[op][2]
+    out = torch.empty((tgt_t.shape[0], ocols), device="cuda")
+    dev.m2m(op, reg, 0, torch.cuda.current_stream().cuda_stream, src_t, src_t.shape[0], tgt_t, tgt_t.shape[0], out, sigma, nu)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("op,reg", [("P3D_M2M_vel", "winckelmans"), ("P3D_M2M_vel", "gaussian"), ("P3D_M2M_dvort", "gaussian")])
+def test_full_size_1m_sampled_parity_and_linearity(gpu, oracle, torch_cuda, op, reg):
+    """Config 2 of BASELINE.json (1M x 1M): the oracle checks a strided sample of targets against
+    ALL 1M sources; linearity (splitting the sources in two halves adds up) checks every target."""
+    torch = torch_cuda
+    _, dev = gpu
+    n = 1_000_000
+    rng = np.random.default_rng(20261017)
+    P = particles3d(rng, n, vol=0.01)
+    tgt_np = P if SHAPES[op][3] else points(rng, n, 3)
+    src, tgt = torch.from_numpy(P).cuda(), torch.from_numpy(tgt_np).cuda()
+    full = _device_run(dev, torch, op, reg, src, tgt, 0.02)
+    assert torch.isfinite(full).all()
+    # sampled parity against the oracle (all sources x 256 strided targets)
+    idx = np.arange(0, n, n // 256)[:256]
+    want = oracle.m2m(op, P, np.ascontiguousarray(tgt_np[idx]), reg, 0.02)
+    got = full[torch.from_numpy(idx).cuda()].cpu().numpy()
+    e = rel_l2(got, want)
+    print(f"{op}/{reg} 1M sampled gpu-vs-ref {e:.2e}")
+    assert e <= TOL
+    # linearity over a source split, on every target
+    half = n // 2 + 12345
+    a = _device_run(dev, torch, op, reg, src[:half].contiguous(), tgt, 0.02)
+    b = _device_run(dev, torch, op, reg, src[half:].contiguous(), tgt, 0.02)
+    num = torch.linalg.norm((a + b - full).double())
+    den = torch.linalg.norm(full.double())
+    assert float(num / den) <= 2e-6
+
+
+def test_full_size_4m_visc_strength_scaling(gpu, torch_cuda):
+    """Config 3 (4M particles, visc_dvort Winckelmans) on a 64k-target shard: doubling every
+    vorticity doubles the result exactly (power-of-two scaling commutes with rounding)."""
+    torch = torch_cuda
+    _, dev = gpu
+    n, m = 4_000_000, 65_536
+    rng = np.random.default_rng(4)
+    P = particles3d(rng, n, vol=0.01)
+    src = torch.from_numpy(P).cuda()
+    tgt = src[:m].contiguous()
+    a = _device_run(dev, torch, "P3D_M2M_visc_dvort", "winckelmans", src, tgt, 0.02)
+    src2 = src.clone()
+    src2[:, 3:6] *= 2
+    b = _device_run(dev, torch, "P3D_M2M_visc_dvort", "winckelmans", src2, src2[:m].contiguous(), 0.02)
+    assert torch.isfinite(a).all()
+    assert torch.equal(b, 2 * a)

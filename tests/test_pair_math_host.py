@@ -1,0 +1,46 @@
+"""The device pair arithmetic (cvortex_b200/csrc/pair_math.cuh), compiled for the host by
+tests/hostcheck, against the oracle: validates the algebraic rewrites and the summation
+structure of the CUDA kernel on a box without a GPU.  MUFU ops are libm here, so the errors
+are a lower bound of what the GPU tests see."""
+import numpy as np
+import pytest
+
+from util import SHAPES, make_case, op_cases, rel_l2
+
+OPS = {"P3D_M2M_vel": 0, "P3D_M2M_dvort": 1, "P3D_M2M_visc_dvort": 2, "P3D_M2M_vort": 3,
+       "P2D_M2M_vel": 4, "P2D_M2M_visc_dvort": 5, "F3D_M2M_vel": 6, "F3D_M2M_dvort": 7}
+REG = {"singular": 0, "winckelmans": 1, "planetary": 2, "gaussian": 3}
+
+
+def run(hostcheck, op, reg, src, tgt, sigma, nu):
+    out = np.zeros((tgt.shape[0], SHAPES[op][2]), np.float32)
+    assert hostcheck.hostcheck_m2m(OPS[op], REG[reg], src, src.shape[0], tgt, tgt.shape[0], out, sigma, nu) == 0
+    return out[:, 0] if SHAPES[op][2] == 1 else out
+
+
+@pytest.mark.parametrize("op,reg", op_cases() + [("P3D_M2M_vort", r) for r in ("winckelmans", "planetary", "gaussian")])
+@pytest.mark.parametrize("box,sigma", [(10.0, 0.3), (10.0, 0.02), (1.53e-4, 0.3)])
+def test_rewritten_pair_math_matches_oracle(hostcheck, oracle, op, reg, box, sigma):
+    rng = np.random.default_rng(1)
+    base = "P3D_M2M_vel" if op == "P3D_M2M_vort" else op
+    src, tgt = make_case(base, rng, 1500, 500, box=box, self_targets=True)
+    got = run(hostcheck, op, reg, src, tgt, sigma, 0.1)
+    f32 = oracle.m2m(op, src, tgt, reg, sigma, 0.1)
+    f64 = oracle.m2m(op, src, tgt, reg, sigma, 0.1, f64=True)
+    e_par, e_gpu, e_ref = rel_l2(got, f32), rel_l2(got, f64), rel_l2(f32, f64)
+    if op == "P3D_M2M_vort" and np.linalg.norm(f64) == 0:
+        assert np.all(got == 0)
+        return
+    slack = 3.0 if op.startswith("F3D") else 1.5       # see tests/test_gpu_parity.py::assert_parity
+    assert e_par <= 1e-5 or e_gpu <= slack * e_ref + 1e-6, (e_par, e_gpu, e_ref)
+
+
+def test_lane_op_metadata_is_consistent(hostcheck):
+    import ctypes as C
+    v = (C.c_int * 6)()
+    expect = {(0, 1): (21, 1), (0, 0): (17, 1), (0, 3): (28, 3), (1, 1): (31, 1), (1, 3): (38, 3), (2, 1): (19, 1),
+              (2, 3): (15, 1), (4, 3): (9, 2), (4, 1): (11, 1), (5, 3): (9, 1), (5, 1): (16, 2), (6, 0): (37, 3), (7, 0): (43, 3)}
+    for (op, reg), (lane, sfu) in expect.items():
+        assert hostcheck.hostcheck_meta(op, reg, v) == 0
+        assert (v[0], v[1]) == (lane, sfu), (op, reg, v[0], v[1])
+    assert hostcheck.hostcheck_meta(2, 0, v) == -1      # visc needs an eta: no singular variant
