@@ -109,15 +109,21 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		if (P::NSRC4 == 2) bulk_g2s(tileB[0], gB, kTileBytes, &full[0]);
 	}
 
-	// ---- this thread's T targets, strided by B so a warp touches contiguous rows
+	// ---- this thread's T targets, strided by B so a warp touches contiguous rows.
+	// Two targets share one Vec<2> (packed FP32x2 lanes) when T is even.
+	constexpr int W = (T % 2 == 0) ? 2 : 1;
+	constexpr int NV = T / W;
 	const long base = (long)blockIdx.x * (B * T) + tid;
-	float tg[T][P::NTGT];
+	Vec<W> tg[NV][P::NTGT];
 	double dacc[T][P::NACC];
 #pragma unroll
 	for (int t = 0; t < T; ++t) {
 		long i = base + (long)t * B;
 		i = i < args.n_tgt ? i : (long)args.n_tgt - 1;          // clamp: tail threads redo the last target, never store
-		P::load_target(args.tgt + i * P::TCOLS, tg[t]);
+		float one[P::NTGT];
+		P::load_target(args.tgt + i * P::TCOLS, one);
+#pragma unroll
+		for (int c = 0; c < P::NTGT; ++c) tg[t / W][c].set(t % W, one[c]);
 #pragma unroll
 		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
 	}
@@ -135,23 +141,23 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		const float4 *sB = tileB[P::NSRC4 == 2 ? buf : 0];
 #pragma unroll 1
 		for (int j0 = 0; j0 < S; j0 += CHAIN) {
-			float acc[T][P::NACC];
+			Vec<W> acc[NV][P::NACC];
 #pragma unroll
-			for (int t = 0; t < T; ++t)
+			for (int v = 0; v < NV; ++v)
 #pragma unroll
-				for (int c = 0; c < P::NACC; ++c) acc[t][c] = 0.0f;
+				for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
 #pragma unroll UNROLL
 			for (int j = 0; j < CHAIN; ++j) {
 				const float4 a = sA[j0 + j];
 				float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
 				if (P::NSRC4 == 2) b = sB[j0 + j];
 #pragma unroll
-				for (int t = 0; t < T; ++t) P::pair(tg[t], a, b, acc[t], args.k);
+				for (int v = 0; v < NV; ++v) P::template pair<W>(tg[v], a, b, acc[v], args.k);
 			}
 #pragma unroll
 			for (int t = 0; t < T; ++t)
 #pragma unroll
-				for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t][c];
+				for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
 		}
 		__syncthreads();      // everyone is done with tile[buf] before it is refilled two iterations on
 	}

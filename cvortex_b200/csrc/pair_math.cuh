@@ -25,6 +25,17 @@
 // reference (src/VortFunc.cpp:164-173), because erff() differs from it by up
 // to 1e-3 relative on near pairs.
 //
+// LANES.  Every formula is written once over Vec<W>, W targets side by side:
+// W = 1 is plain FP32; W = 2 maps onto Blackwell's packed FP32x2 instructions
+// (PTX add/mul/fma.f32x2 -> SASS FADD2 / FMUL2 / FFMA2).  One FFMA2 does two
+// FMAs for one issue slot, and its scalar operands broadcast for free
+// (`R25.F32`), which is exactly the shape of this loop: two targets of a
+// thread against the same source record.  The FP32 pipe still retires 128
+// lane-ops per SM per clock, but the kernel stops being ISSUE-bound: the
+// scalar form of Winckelmans vel needs 21 FP32 + 1 MUFU + 0.6 other issue
+// slots per pair (FP32 pipe <= 93 % busy at best); packed it needs 11.8.
+// MUFU, compares and selects stay per lane.
+//
 // Coincident-pair rule (reference: contribution is exactly zero when the two
 // positions compare equal, src/P3D.cpp:58,94,127, src/P2D.cpp:57,178): here a
 // pair is dropped when r^2 == 0.  For formulas that are regular at r = 0 and
@@ -33,7 +44,7 @@
 // Each policy exposes
 //   NSRC4   float4 records per packed source (1 or 2)
 //   TCOLS   floats per raw target row in global memory
-//   NTGT    target floats kept in registers during the pair loop
+//   NTGT    target values kept in registers during the pair loop
 //   NACC    FP32 running sums per target
 //   NOUT    output floats per target
 //   CHAIN   sources per FP32 running-sum chain before it is flushed into the
@@ -45,10 +56,10 @@
 //   LANE_OPS, SFU_OPS   algorithmic FP32 lane-ops / MUFU ops per pair of THIS
 //                       formulation (FMA = 1 lane-op; compares/selects not
 //                       counted) -- the roofline denominators, see DESIGN.md
-//   load_target(), pair(), finish()
+//   load_target(row, tg[]), pair<W>(tg, a, b, acc, k), finish(row, acc, out, k)
 // and is usable from host code too (tests/hostcheck compiles this header with
 // g++ to validate the algebra against the oracle without a GPU; MUFU ops are
-// then replaced by libm).
+// then replaced by libm and FP32x2 by two scalar lanes).
 #pragma once
 #include <math.h>
 
@@ -71,7 +82,7 @@ struct PairConsts {
 	double s0, s1;
 };
 
-// ---- MUFU wrappers --------------------------------------------------------
+// ---- MUFU wrappers (scalar) --------------------------------------------------
 CVTX_HD float mufu_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
 	float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
@@ -94,6 +105,83 @@ CVTX_HD float mufu_ex2(float x) {
 #endif
 }
 
+// ---- Vec<W>: W FP32 lanes -----------------------------------------------------
+template <int W> struct Vec;
+
+template <> struct Vec<1> {
+	float x;
+	static constexpr int LANES = 1;
+	CVTX_HD float lane(int) const { return x; }
+	CVTX_HD void set(int, float s) { x = s; }
+};
+
+#if !defined(__CUDACC__)
+struct f2 { float x, y; };
+#else
+typedef float2 f2;
+#endif
+
+template <> struct Vec<2> {
+	f2 v;
+	static constexpr int LANES = 2;
+	CVTX_HD float lane(int i) const { return i ? v.y : v.x; }
+	CVTX_HD void set(int i, float s) { if (i) v.y = s; else v.x = s; }
+};
+
+template <int W> CVTX_HD Vec<W> bc(float s) {
+	Vec<W> r;
+	for (int i = 0; i < W; ++i) r.set(i, s);
+	return r;
+}
+
+// fused a*b + c, a*b, a + b, a - b, -a  (FFMA2 / FMUL2 / FADD2 when W = 2;
+// negations fold into the instructions' operand modifiers)
+CVTX_HD Vec<1> vfma(Vec<1> a, Vec<1> b, Vec<1> c) { Vec<1> r; r.x = fmaf(a.x, b.x, c.x); return r; }
+CVTX_HD Vec<1> vmul(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = a.x * b.x; return r; }
+CVTX_HD Vec<1> vadd(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = a.x + b.x; return r; }
+CVTX_HD Vec<1> vsub(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = a.x - b.x; return r; }
+CVTX_HD Vec<1> vneg(Vec<1> a) { Vec<1> r; r.x = -a.x; return r; }
+CVTX_HD Vec<2> vneg(Vec<2> a) { Vec<2> r; r.v.x = -a.v.x; r.v.y = -a.v.y; return r; }
+#if defined(__CUDA_ARCH__)
+CVTX_HD Vec<2> vfma(Vec<2> a, Vec<2> b, Vec<2> c) { Vec<2> r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+CVTX_HD Vec<2> vmul(Vec<2> a, Vec<2> b) { Vec<2> r; r.v = __fmul2_rn(a.v, b.v); return r; }
+CVTX_HD Vec<2> vadd(Vec<2> a, Vec<2> b) { Vec<2> r; r.v = __fadd2_rn(a.v, b.v); return r; }
+CVTX_HD Vec<2> vsub(Vec<2> a, Vec<2> b) { Vec<2> r; r.v = __fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y)); return r; }
+#else
+CVTX_HD Vec<2> vfma(Vec<2> a, Vec<2> b, Vec<2> c) { Vec<2> r; r.v.x = fmaf(a.v.x, b.v.x, c.v.x); r.v.y = fmaf(a.v.y, b.v.y, c.v.y); return r; }
+CVTX_HD Vec<2> vmul(Vec<2> a, Vec<2> b) { Vec<2> r; r.v.x = a.v.x * b.v.x; r.v.y = a.v.y * b.v.y; return r; }
+CVTX_HD Vec<2> vadd(Vec<2> a, Vec<2> b) { Vec<2> r; r.v.x = a.v.x + b.v.x; r.v.y = a.v.y + b.v.y; return r; }
+CVTX_HD Vec<2> vsub(Vec<2> a, Vec<2> b) { Vec<2> r; r.v.x = a.v.x - b.v.x; r.v.y = a.v.y - b.v.y; return r; }
+#endif
+
+// scalar-operand forms (the scalar broadcasts inside the instruction)
+template <int W> CVTX_HD Vec<W> vfma(Vec<W> a, float b, Vec<W> c) { return vfma(a, bc<W>(b), c); }
+template <int W> CVTX_HD Vec<W> vfma(Vec<W> a, Vec<W> b, float c) { return vfma(a, b, bc<W>(c)); }
+template <int W> CVTX_HD Vec<W> vfma(Vec<W> a, float b, float c) { return vfma(a, bc<W>(b), bc<W>(c)); }
+template <int W> CVTX_HD Vec<W> vmul(Vec<W> a, float b) { return vmul(a, bc<W>(b)); }
+template <int W> CVTX_HD Vec<W> vsub(Vec<W> a, float b) { return vsub(a, bc<W>(b)); }
+template <int W> CVTX_HD Vec<W> vsub(float a, Vec<W> b) { return vsub(bc<W>(a), b); }
+// a*b - c
+template <int W> CVTX_HD Vec<W> vfms(Vec<W> a, Vec<W> b, Vec<W> c) { return vfma(a, b, vneg(c)); }
+template <int W> CVTX_HD Vec<W> vfms(Vec<W> a, float b, Vec<W> c) { return vfma(a, bc<W>(b), vneg(c)); }
+
+// per-lane operations (MUFU, compares, selects have no packed form)
+template <int W> CVTX_HD Vec<W> vrsqrt(Vec<W> a) { Vec<W> r; for (int i = 0; i < W; ++i) r.set(i, mufu_rsqrt(a.lane(i))); return r; }
+template <int W> CVTX_HD Vec<W> vrcp(Vec<W> a) { Vec<W> r; for (int i = 0; i < W; ++i) r.set(i, mufu_rcp(a.lane(i))); return r; }
+template <int W> CVTX_HD Vec<W> vex2(Vec<W> a) { Vec<W> r; for (int i = 0; i < W; ++i) r.set(i, mufu_ex2(a.lane(i))); return r; }
+// c > 0 ? v : 0      (the coincident-pair rule)
+template <int W> CVTX_HD Vec<W> keep_if_pos(Vec<W> c, Vec<W> v) {
+	Vec<W> r;
+	for (int i = 0; i < W; ++i) r.set(i, c.lane(i) > 0.0f ? v.lane(i) : 0.0f);
+	return r;
+}
+// c < thr ? a : b
+template <int W> CVTX_HD Vec<W> pick_if_less(Vec<W> c, float thr, Vec<W> a, Vec<W> b) {
+	Vec<W> r;
+	for (int i = 0; i < W; ++i) r.set(i, c.lane(i) < thr ? a.lane(i) : b.lane(i));
+	return r;
+}
+
 static constexpr double kPi = 3.14159265359;              // CVTX_PI_F, reference src/P3D.cpp:47 (as a float literal there)
 static constexpr double kSqrt2OverPi = 0.7978845608028654;  // reference src/VortFunc.cpp:49
 static constexpr double kRecipSqrt2 = 0.7071067811865475;   // reference src/VortFunc.cpp:50
@@ -103,13 +191,13 @@ static constexpr double kLog2e = 1.4426950408889634;
 // Returns s with  g_gauss3D(rho) = 1 - e * s,  e = exp(-rho^2/2):
 //   erf(z) ~ 1 - poly(t) e,  t = 1/(1 + p z),  z = rho/sqrt2
 //   g = erf(z) - rho sqrt(2/pi) e = 1 - e (poly(t) + rho sqrt(2/pi))
-CVTX_HD float gauss_tail(float r, float k_t, float k_c) {
-	const float t = mufu_rcp(fmaf(r, k_t, 1.0f));
-	float p = fmaf(t, 1.061405429f, -1.453152027f);
-	p = fmaf(t, p, 1.421413741f);
-	p = fmaf(t, p, -0.284496736f);
-	p = fmaf(t, p, 0.254829592f);
-	return fmaf(r, k_c, p * t);
+template <int W> CVTX_HD Vec<W> gauss_tail(Vec<W> r, float k_t, float k_c) {
+	const Vec<W> t = vrcp(vfma(r, k_t, 1.0f));
+	Vec<W> p = vfma(t, 1.061405429f, -1.453152027f);
+	p = vfma(t, p, 1.421413741f);
+	p = vfma(t, p, -0.284496736f);
+	p = vfma(t, p, 0.254829592f);
+	return vfma(r, k_c, vmul(p, t));
 }
 
 // ---------------------------------------------------------------------------
@@ -125,18 +213,18 @@ template <> struct Reg3D<REG_WINCKELMANS> {
 	// c0 = 1/sigma^2, c1 = -3/sigma^4, c2 = -10.5/sigma^2.
 	// A = sigma^3 g/r^3 = g/rho^3.  Bn = -(3 rho^2 + 10.5)(rho^2+1)^-7/2 / sigma^2.
 	static constexpr int A_OPS = 6, AB_OPS = 9, SFU = 1;
-	CVTX_HD static float A(float r2, const PairConsts &k) {
-		const float a = fmaf(r2, k.c0, 1.0f), b = fmaf(r2, k.c0, 2.5f);
-		const float ra = mufu_rsqrt(a), ra2 = ra * ra, ra4 = ra2 * ra2;
-		return b * (ra4 * ra);
+	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.5f);
+		const Vec<W> ra = vrsqrt(a), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2);
+		return vmul(b, vmul(ra4, ra));
 	}
-	CVTX_HD static void AB(float r2, const PairConsts &k, float &A_, float &B_) {
-		const float a = fmaf(r2, k.c0, 1.0f), b = fmaf(r2, k.c0, 2.5f), b2 = fmaf(r2, k.c1, k.c2);
-		const float ra = mufu_rsqrt(a), ra2 = ra * ra, ra4 = ra2 * ra2, ra5 = ra4 * ra;
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B_) {
+		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.5f), b2 = vfma(r2, k.c1, k.c2);
+		const Vec<W> ra = vrsqrt(a), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2), ra5 = vmul(ra4, ra);
 		// the self pair must give exactly 0: c = w_t x w_t formed with FMAs is
 		// only zero to rounding, and A(0) = 2.5 would amplify that residue
-		A_ = r2 > 0.0f ? b * ra5 : 0.0f;
-		B_ = b2 * (ra5 * ra2);
+		A_ = keep_if_pos(r2, vmul(b, ra5));
+		B_ = vmul(b2, vmul(ra5, ra2));
 	}
 	static void consts(PairConsts &k, double s) {
 		k.c0 = (float)(1.0 / (s * s)); k.c1 = (float)(-3.0 / (s * s * s * s)); k.c2 = (float)(-10.5 / (s * s));
@@ -147,15 +235,14 @@ template <> struct Reg3D<REG_WINCKELMANS> {
 template <> struct Reg3D<REG_SINGULAR> {
 	// A = 1/r^3, Bn = -3/r^5; both dropped at r = 0.
 	static constexpr int A_OPS = 2, AB_OPS = 4, SFU = 1;
-	CVTX_HD static float A(float r2, const PairConsts &) {
-		const float ri = mufu_rsqrt(r2);
-		return r2 > 0.0f ? ri * ri * ri : 0.0f;
+	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &) {
+		const Vec<W> ri = vrsqrt(r2);
+		return keep_if_pos(r2, vmul(vmul(ri, ri), ri));
 	}
-	CVTX_HD static void AB(float r2, const PairConsts &, float &A_, float &B_) {
-		const float ri = mufu_rsqrt(r2), ri2 = ri * ri, ri3 = ri2 * ri;
-		const bool ok = r2 > 0.0f;
-		A_ = ok ? ri3 : 0.0f;
-		B_ = ok ? ri3 * (ri2 * -3.0f) : 0.0f;
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &, Vec<W> &A_, Vec<W> &B_) {
+		const Vec<W> ri = vrsqrt(r2), ri2 = vmul(ri, ri), ri3 = vmul(ri2, ri);
+		A_ = keep_if_pos(r2, ri3);
+		B_ = keep_if_pos(r2, vmul(ri3, vmul(ri2, -3.0f)));
 	}
 	static void consts(PairConsts &, double) {}
 	static double scaleA(double) { return 1.0; }
@@ -165,15 +252,14 @@ template <> struct Reg3D<REG_PLANETARY> {
 	// rho < 1: g = rho^3, zeta = 3  ->  A = 1/sigma^3, Bn = 0;  else singular.
 	// c0 = sigma^2, c1 = 1/sigma^3.
 	static constexpr int A_OPS = 2, AB_OPS = 4, SFU = 1;
-	CVTX_HD static float A(float r2, const PairConsts &k) {
-		const float ri = mufu_rsqrt(r2);
-		return r2 < k.c0 ? k.c1 : ri * ri * ri;
+	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> ri = vrsqrt(r2);
+		return pick_if_less(r2, k.c0, bc<W>(k.c1), vmul(vmul(ri, ri), ri));
 	}
-	CVTX_HD static void AB(float r2, const PairConsts &k, float &A_, float &B_) {
-		const float ri = mufu_rsqrt(r2), ri2 = ri * ri, ri3 = ri2 * ri;
-		const bool in = r2 < k.c0;
-		A_ = in ? (r2 > 0.0f ? k.c1 : 0.0f) : ri3;        // exact 0 for the self pair, as above
-		B_ = in ? 0.0f : ri3 * (ri2 * -3.0f);
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B_) {
+		const Vec<W> ri = vrsqrt(r2), ri2 = vmul(ri, ri), ri3 = vmul(ri2, ri);
+		A_ = pick_if_less(r2, k.c0, keep_if_pos(r2, bc<W>(k.c1)), ri3);        // exact 0 for the self pair, as above
+		B_ = pick_if_less(r2, k.c0, bc<W>(0.0f), vmul(ri3, vmul(ri2, -3.0f)));
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(s * s); k.c1 = (float)(1.0 / (s * s * s)); }
 	static double scaleA(double) { return 1.0; }
@@ -183,23 +269,22 @@ template <> struct Reg3D<REG_GAUSSIAN> {
 	// c0 = p/(sqrt2 sigma), c1 = -log2(e)/(2 sigma^2), c2 = sqrt(2/pi)/sigma,
 	// c3 = sqrt(2/pi)/sigma^3.   A = g/r^3,  Bn = (c3 e - 3A)/r^2.
 	static constexpr int A_OPS = 13, AB_OPS = 16, SFU = 3;
-	CVTX_HD static float A(float r2, const PairConsts &k) {
-		const float ri = mufu_rsqrt(r2), r = r2 * ri;
-		const float e = mufu_ex2(r2 * k.c1);
-		const float s = gauss_tail(r, k.c0, k.c2);
-		const float g = fmaf(-e, s, 1.0f);
-		return r2 > 0.0f ? g * (ri * ri * ri) : 0.0f;
+	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> ri = vrsqrt(r2), r = vmul(r2, ri);
+		const Vec<W> e = vex2(vmul(r2, k.c1));
+		const Vec<W> s = gauss_tail(r, k.c0, k.c2);
+		const Vec<W> g = vfma(vneg(e), s, 1.0f);
+		return keep_if_pos(r2, vmul(g, vmul(vmul(ri, ri), ri)));
 	}
-	CVTX_HD static void AB(float r2, const PairConsts &k, float &A_, float &B_) {
-		const float ri = mufu_rsqrt(r2), r = r2 * ri, ri2 = ri * ri;
-		const float e = mufu_ex2(r2 * k.c1);
-		const float s = gauss_tail(r, k.c0, k.c2);
-		const float g = fmaf(-e, s, 1.0f);
-		const float a = g * (ri2 * ri);
-		const float h = fmaf(-3.0f, a, k.c3 * e);
-		const bool ok = r2 > 0.0f;
-		A_ = ok ? a : 0.0f;
-		B_ = ok ? h * ri2 : 0.0f;
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B_) {
+		const Vec<W> ri = vrsqrt(r2), r = vmul(r2, ri), ri2 = vmul(ri, ri);
+		const Vec<W> e = vex2(vmul(r2, k.c1));
+		const Vec<W> s = gauss_tail(r, k.c0, k.c2);
+		const Vec<W> g = vfma(vneg(e), s, 1.0f);
+		const Vec<W> a = vmul(g, vmul(ri2, ri));
+		const Vec<W> h = vfma(a, -3.0f, vmul(e, k.c3));
+		A_ = keep_if_pos(r2, a);
+		B_ = keep_if_pos(r2, vmul(h, ri2));
 	}
 	static void consts(PairConsts &k, double s) {
 		k.c0 = (float)(0.3275911 * kRecipSqrt2 / s);
@@ -210,6 +295,15 @@ template <> struct Reg3D<REG_GAUSSIAN> {
 	static double scaleA(double) { return 1.0; }
 };
 
+// rad = target - source position, r^2 (6 lane-ops); shared by the 3D particle ops
+template <int W> struct Rad3 { Vec<W> x, y, z, r2; };
+template <int W> CVTX_HD Rad3<W> rad3(const Vec<W> *tg, const f4 a) {
+	Rad3<W> d;
+	d.x = vsub(tg[0], a.x); d.y = vsub(tg[1], a.y); d.z = vsub(tg[2], a.z);
+	d.r2 = vfma(d.z, d.z, vfma(d.y, d.y, vmul(d.x, d.x)));
+	return d;
+}
+
 // ===========================================================================
 // cvtx_P3D_M2M_vel      u_t = -(1/4pi) sum_s [g(rho)/r^3] (rad x w_s)
 // reference: src/P3D.cpp:51-72 (pair), :230-251 (sum), :343-366 (entry)
@@ -219,16 +313,15 @@ template <int REG> struct P3DVel {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0;
 	static constexpr int LANE_OPS = 15 + Reg3D<REG>::A_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4 b, float *acc, const PairConsts &k) {
-		const float dx = tg[0] - a.x, dy = tg[1] - a.y, dz = tg[2] - a.z;
-		const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-		const float K = Reg3D<REG>::A(r2, k);
-		const float cx = fmaf(dy, b.z, -(dz * b.y));
-		const float cy = fmaf(dz, b.x, -(dx * b.z));
-		const float cz = fmaf(dx, b.y, -(dy * b.x));
-		acc[0] = fmaf(K, cx, acc[0]);
-		acc[1] = fmaf(K, cy, acc[1]);
-		acc[2] = fmaf(K, cz, acc[2]);
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		const Vec<W> K = Reg3D<REG>::A(d.r2, k);
+		const Vec<W> cx = vfms(d.y, b.z, vmul(d.z, b.y));
+		const Vec<W> cy = vfms(d.z, b.x, vmul(d.x, b.z));
+		const Vec<W> cz = vfms(d.x, b.y, vmul(d.y, b.x));
+		acc[0] = vfma(K, cx, acc[0]);
+		acc[1] = vfma(K, cy, acc[1]);
+		acc[2] = vfma(K, cz, acc[2]);
 	}
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
 		out[0] = acc[0] * k.s0; out[1] = acc[1] * k.s0; out[2] = acc[2] * k.s0;
@@ -255,19 +348,18 @@ template <int REG> struct P3DDvort {
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4 b, float *acc, const PairConsts &k) {
-		const float dx = tg[0] - a.x, dy = tg[1] - a.y, dz = tg[2] - a.z;
-		const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-		float A, Bn;
-		Reg3D<REG>::AB(r2, k, A, Bn);
-		const float cx = fmaf(tg[4], b.z, -(tg[5] * b.y));
-		const float cy = fmaf(tg[5], b.x, -(tg[3] * b.z));
-		const float cz = fmaf(tg[3], b.y, -(tg[4] * b.x));
-		const float trip = fmaf(dz, cz, fmaf(dy, cy, dx * cx));
-		const float s = Bn * trip;
-		acc[0] = fmaf(s, dx, fmaf(A, cx, acc[0]));
-		acc[1] = fmaf(s, dy, fmaf(A, cy, acc[1]));
-		acc[2] = fmaf(s, dz, fmaf(A, cz, acc[2]));
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		Vec<W> A, Bn;
+		Reg3D<REG>::AB(d.r2, k, A, Bn);
+		const Vec<W> cx = vfms(tg[4], b.z, vmul(tg[5], b.y));
+		const Vec<W> cy = vfms(tg[5], b.x, vmul(tg[3], b.z));
+		const Vec<W> cz = vfms(tg[3], b.y, vmul(tg[4], b.x));
+		const Vec<W> trip = vfma(d.z, cz, vfma(d.y, cy, vmul(d.x, cx)));
+		const Vec<W> s = vmul(Bn, trip);
+		acc[0] = vfma(s, d.x, vfma(A, cx, acc[0]));
+		acc[1] = vfma(s, d.y, vfma(A, cy, acc[1]));
+		acc[2] = vfma(s, d.z, vfma(A, cz, acc[2]));
 	}
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
 		out[0] = acc[0] * k.s0; out[1] = acc[1] * k.s0; out[2] = acc[2] * k.s0;
@@ -292,17 +384,17 @@ template <int REG> struct P3DDvort {
 template <int REG> struct Eta3D;
 template <> struct Eta3D<REG_WINCKELMANS> {   // eta = 52.5 (rho^2+1)^-9/2
 	static constexpr int OPS = 5, SFU = 1;
-	CVTX_HD static float eta(float r2, const PairConsts &k) {
-		const float ra = mufu_rsqrt(fmaf(r2, k.c0, 1.0f));
-		const float ra2 = ra * ra, ra4 = ra2 * ra2, ra8 = ra4 * ra4;
-		return ra8 * ra;
+	template <int W> CVTX_HD static Vec<W> eta(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> ra = vrsqrt(vfma(r2, k.c0, 1.0f));
+		const Vec<W> ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2), ra8 = vmul(ra4, ra4);
+		return vmul(ra8, ra);
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(1.0 / (s * s)); }
 	static double scale() { return 52.5; }
 };
 template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 	static constexpr int OPS = 1, SFU = 1;
-	CVTX_HD static float eta(float r2, const PairConsts &k) { return mufu_ex2(r2 * k.c0); }
+	template <int W> CVTX_HD static Vec<W> eta(Vec<W> r2, const PairConsts &k) { return vex2(vmul(r2, k.c0)); }
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(-0.5 * kLog2e / (s * s)); }
 	static double scale() { return kSqrt2OverPi; }
 };
@@ -313,15 +405,13 @@ template <int REG> struct P3DVisc {
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
 	}
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4 b, float *acc, const PairConsts &k) {
-		const float dx = tg[0] - a.x, dy = tg[1] - a.y, dz = tg[2] - a.z;
-		const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-		float eta = Eta3D<REG>::eta(r2, k);
-		eta = r2 > 0.0f ? eta : 0.0f;                 // coincident pair contributes nothing
-		acc[0] = fmaf(eta, b.x - tg[3], acc[0]);
-		acc[1] = fmaf(eta, b.y - tg[4], acc[1]);
-		acc[2] = fmaf(eta, b.z - tg[5], acc[2]);
-		acc[3] = fmaf(eta, a.w - tg[6], acc[3]);
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		const Vec<W> eta = keep_if_pos(d.r2, Eta3D<REG>::eta(d.r2, k));   // coincident pair contributes nothing
+		acc[0] = vfma(eta, vsub(b.x, tg[3]), acc[0]);
+		acc[1] = vfma(eta, vsub(b.y, tg[4]), acc[1]);
+		acc[2] = vfma(eta, vsub(b.z, tg[5]), acc[2]);
+		acc[3] = vfma(eta, vsub(a.w, tg[6]), acc[3]);
 	}
 	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &k) {
 		const double vt = row[6];
@@ -345,29 +435,31 @@ template <int REG> struct P3DVisc {
 template <int REG> struct Zeta3D;
 template <> struct Zeta3D<REG_SINGULAR> {
 	static constexpr int OPS = 0, SFU = 0;
-	CVTX_HD static float zeta(float, const PairConsts &) { return 0.0f; }
+	template <int W> CVTX_HD static Vec<W> zeta(Vec<W>, const PairConsts &) { return bc<W>(0.0f); }
 	static void consts(PairConsts &, double) {}
 	static double scale() { return 0.0; }
 };
 template <> struct Zeta3D<REG_WINCKELMANS> {  // zeta = 7.5 (rho^2+1)^-7/2
 	static constexpr int OPS = 5, SFU = 1;
-	CVTX_HD static float zeta(float r2, const PairConsts &k) {
-		const float ra = mufu_rsqrt(fmaf(r2, k.c0, 1.0f));
-		const float ra2 = ra * ra, ra4 = ra2 * ra2;
-		return (ra4 * ra2) * ra;
+	template <int W> CVTX_HD static Vec<W> zeta(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> ra = vrsqrt(vfma(r2, k.c0, 1.0f));
+		const Vec<W> ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2);
+		return vmul(vmul(ra4, ra2), ra);
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(1.0 / (s * s)); }
 	static double scale() { return 7.5; }
 };
 template <> struct Zeta3D<REG_PLANETARY> {    // zeta = rho < 1 ? 3 : 0
 	static constexpr int OPS = 0, SFU = 0;
-	CVTX_HD static float zeta(float r2, const PairConsts &k) { return r2 < k.c0 ? 1.0f : 0.0f; }
+	template <int W> CVTX_HD static Vec<W> zeta(Vec<W> r2, const PairConsts &k) {
+		return pick_if_less(r2, k.c0, bc<W>(1.0f), bc<W>(0.0f));
+	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(s * s); }
 	static double scale() { return 3.0; }
 };
 template <> struct Zeta3D<REG_GAUSSIAN> {     // zeta = sqrt(2/pi) exp(-rho^2/2)
 	static constexpr int OPS = 1, SFU = 1;
-	CVTX_HD static float zeta(float r2, const PairConsts &k) { return mufu_ex2(r2 * k.c0); }
+	template <int W> CVTX_HD static Vec<W> zeta(Vec<W> r2, const PairConsts &k) { return vex2(vmul(r2, k.c0)); }
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(-0.5 * kLog2e / (s * s)); }
 	static double scale() { return kSqrt2OverPi; }
 };
@@ -376,15 +468,17 @@ template <int REG> struct P3DVort {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0;
 	static constexpr int LANE_OPS = 9 + Zeta3D<REG>::OPS, SFU_OPS = Zeta3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4 b, float *acc, const PairConsts &k) {
-		const float dx = a.x - tg[0], dy = a.y - tg[1], dz = a.z - tg[2];
-		const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-		float z = Zeta3D<REG>::zeta(r2, k);
-		const bool in = fabsf(dx) < k.c3 && fabsf(dy) < k.c3 && fabsf(dz) < k.c3;   // c3 = 5 sigma
-		z = in ? z : 0.0f;
-		acc[0] = fmaf(z, b.x, acc[0]);
-		acc[1] = fmaf(z, b.y, acc[1]);
-		acc[2] = fmaf(z, b.z, acc[2]);
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		const Vec<W> zeta = Zeta3D<REG>::zeta(d.r2, k);
+		Vec<W> z;
+		for (int i = 0; i < W; ++i) {                          // c3 = 5 sigma: the reference's box cutoff
+			const bool in = fabsf(d.x.lane(i)) < k.c3 && fabsf(d.y.lane(i)) < k.c3 && fabsf(d.z.lane(i)) < k.c3;
+			z.set(i, in ? zeta.lane(i) : 0.0f);
+		}
+		acc[0] = vfma(z, b.x, acc[0]);
+		acc[1] = vfma(z, b.y, acc[1]);
+		acc[2] = vfma(z, b.z, acc[2]);
 	}
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
 		out[0] = acc[0] * k.s0; out[1] = acc[1] * k.s0; out[2] = acc[2] * k.s0;
@@ -407,31 +501,33 @@ template <int REG> struct P3DVort {
 template <int REG> struct Reg2D;
 template <> struct Reg2D<REG_SINGULAR> {      // K = 1/r^2
 	static constexpr int OPS = 0, SFU = 1;
-	CVTX_HD static float K(float r2, const PairConsts &) { const float ir = mufu_rcp(r2); return r2 > 0.0f ? ir : 0.0f; }
+	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &) { return keep_if_pos(r2, vrcp(r2)); }
 	static void consts(PairConsts &, double) {}
 	static double scale(double) { return 1.0; }
 };
 template <> struct Reg2D<REG_WINCKELMANS> {   // K = sigma^2 g/r^2 = (rho^2+2)/(rho^2+1)^2
 	static constexpr int OPS = 4, SFU = 1;
-	CVTX_HD static float K(float r2, const PairConsts &k) {
-		const float a = fmaf(r2, k.c0, 1.0f), b = fmaf(r2, k.c0, 2.0f);
-		const float ia = mufu_rcp(a);
-		return b * (ia * ia);
+	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.0f);
+		const Vec<W> ia = vrcp(a);
+		return vmul(b, vmul(ia, ia));
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(1.0 / (s * s)); }
 	static double scale(double s) { return 1.0 / (s * s); }
 };
 template <> struct Reg2D<REG_PLANETARY> {     // K = rho < 1 ? 1/sigma^2 : 1/r^2
 	static constexpr int OPS = 0, SFU = 1;
-	CVTX_HD static float K(float r2, const PairConsts &k) { const float ir = mufu_rcp(r2); return r2 < k.c0 ? k.c1 : ir; }
+	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
+		return pick_if_less(r2, k.c0, bc<W>(k.c1), vrcp(r2));
+	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(s * s); k.c1 = (float)(1.0 / (s * s)); }
 	static double scale(double) { return 1.0; }
 };
 template <> struct Reg2D<REG_GAUSSIAN> {      // K = (1 - exp(-rho^2/2))/r^2
 	static constexpr int OPS = 2, SFU = 2;
-	CVTX_HD static float K(float r2, const PairConsts &k) {
-		const float e = mufu_ex2(r2 * k.c0), ir = mufu_rcp(r2);
-		return r2 > 0.0f ? fmaf(-e, ir, ir) : 0.0f;
+	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> e = vex2(vmul(r2, k.c0)), ir = vrcp(r2);
+		return keep_if_pos(r2, vfma(vneg(e), ir, ir));
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(-0.5 * kLog2e / (s * s)); }
 	static double scale(double) { return 1.0; }
@@ -441,12 +537,12 @@ template <int REG> struct P2DVel {
 	static constexpr int NSRC4 = 1, TCOLS = 2, NTGT = 2, NACC = 2, NOUT = 2, CHAIN = 0;
 	static constexpr int LANE_OPS = 7 + Reg2D<REG>::OPS, SFU_OPS = Reg2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; }
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4, float *acc, const PairConsts &k) {
-		const float dx = tg[0] - a.x, dy = tg[1] - a.y;
-		const float r2 = fmaf(dy, dy, dx * dx);
-		const float kg = Reg2D<REG>::K(r2, k) * a.z;
-		acc[0] = fmaf(kg, dy, acc[0]);
-		acc[1] = fmaf(kg, dx, acc[1]);
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
+		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
+		const Vec<W> r2 = vfma(dy, dy, vmul(dx, dx));
+		const Vec<W> kg = vmul(Reg2D<REG>::K(r2, k), a.z);
+		acc[0] = vfma(kg, dy, acc[0]);
+		acc[1] = vfma(kg, dx, acc[1]);
 	}
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
 		out[0] = acc[0] * k.s0; out[1] = -(acc[1] * k.s0);
@@ -465,23 +561,18 @@ template <int REG> struct P2DVel {
 // ===========================================================================
 template <int REG> struct Eta2D;
 template <> struct Eta2D<REG_WINCKELMANS> {   // eta = 24 exp(4/a^3)/a^4, a = rho^2+1 (as coded, src/VortFunc.cpp:124-131)
-	static constexpr int OPS = 8, SFU = 2;
-	CVTX_HD static float eta(float r2, const PairConsts &k) {
-		const float a = fmaf(r2, k.c0, 1.0f);
-		float ia = mufu_rcp(a);
-		// one Newton step: MUFU.RCP's ~1 ulp error is raised to the 4th power below, and the
-		// PSE sum over a smooth field cancels to second order (measured on B200: 1.4e-5 from
-		// FP64 without the step, against 8.6e-6 for the reference, on the 50x50 lattice test)
-		ia = fmaf(ia, fmaf(-a, ia, 1.0f), ia);
-		const float ia2 = ia * ia, ia3 = ia2 * ia;
-		return mufu_ex2(ia3 * 5.770780163555854f) * (ia2 * ia2);       // 4 log2(e)
+	static constexpr int OPS = 6, SFU = 2;
+	template <int W> CVTX_HD static Vec<W> eta(Vec<W> r2, const PairConsts &k) {
+		const Vec<W> ia = vrcp(vfma(r2, k.c0, 1.0f));
+		const Vec<W> ia2 = vmul(ia, ia), ia3 = vmul(ia2, ia);
+		return vmul(vex2(vmul(ia3, 5.770780163555854f)), vmul(ia2, ia2));       // 4 log2(e)
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(1.0 / (s * s)); }
 	static double scale() { return 24.0; }
 };
 template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFunc.cpp:196-199
 	static constexpr int OPS = 1, SFU = 1;
-	CVTX_HD static float eta(float r2, const PairConsts &k) { return mufu_ex2(r2 * k.c0); }
+	template <int W> CVTX_HD static Vec<W> eta(Vec<W> r2, const PairConsts &k) { return vex2(vmul(r2, k.c0)); }
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(-0.5 * kLog2e / (s * s)); }
 	static double scale() { return 1.0; }
 };
@@ -490,13 +581,12 @@ template <int REG> struct P2DVisc {
 	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 2, NOUT = 1, CHAIN = 8;
 	static constexpr int LANE_OPS = 8 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4, float *acc, const PairConsts &k) {
-		const float dx = tg[0] - a.x, dy = tg[1] - a.y;
-		const float r2 = fmaf(dy, dy, dx * dx);
-		float eta = Eta2D<REG>::eta(r2, k);
-		eta = r2 > 0.0f ? eta : 0.0f;
-		acc[0] = fmaf(eta, a.z - tg[2], acc[0]);      // sum eta (G_s - G_t)
-		acc[1] = fmaf(eta, a.w - tg[3], acc[1]);      // sum eta (A_s - A_t)
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
+		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
+		const Vec<W> r2 = vfma(dy, dy, vmul(dx, dx));
+		const Vec<W> eta = keep_if_pos(r2, Eta2D<REG>::eta(r2, k));
+		acc[0] = vfma(eta, vsub(a.z, tg[2]), acc[0]);      // sum eta (G_s - G_t)
+		acc[1] = vfma(eta, vsub(a.w, tg[3]), acc[1]);      // sum eta (A_s - A_t)
 	}
 	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &k) {
 		out[0] = k.s0 * ((double)row[3] * acc[0] - (double)row[2] * acc[1]);
@@ -518,32 +608,42 @@ template <int REG> struct P2DVisc {
 // source a = {ax, ay, az, G/4pi}   b = {bx, by, bz, 3 G/(4 pi |b-a|)}
 // r0 is formed per pair as r1 - r2, like the reference: the subtraction is exact
 // (|r1| ~ |r2|), so r0 stays consistent with the rounded r1, r2 and the
-// cancelling difference r1.r0/|r1| - r2.r0/|r2| keeps the reference's accuracy
-// (a per-source r0 = b - a measured 2.4x worse against FP64).
+// cancelling difference r1.r0/|r1| - r2.r0/|r2| keeps the reference's accuracy.
 // ===========================================================================
+template <int W> struct Fil { Vec<W> px, py, pz, qx, qy, qz, ox, oy, oz, n1, n2, d1, d2; };
+template <int W> CVTX_HD Fil<W> filament_geometry(const Vec<W> *tg, const f4 a, const f4 b) {   // 21 lane-ops
+	Fil<W> f;
+	f.px = vsub(tg[0], a.x); f.py = vsub(tg[1], a.y); f.pz = vsub(tg[2], a.z);        // r1
+	f.qx = vsub(tg[0], b.x); f.qy = vsub(tg[1], b.y); f.qz = vsub(tg[2], b.z);        // r2
+	f.ox = vsub(f.px, f.qx); f.oy = vsub(f.py, f.qy); f.oz = vsub(f.pz, f.qz);        // r0 = r1 - r2 (exact)
+	f.n1 = vfma(f.pz, f.pz, vfma(f.py, f.py, vmul(f.px, f.px)));
+	f.n2 = vfma(f.qz, f.qz, vfma(f.qy, f.qy, vmul(f.qx, f.qx)));
+	f.d1 = vfma(f.pz, f.oz, vfma(f.py, f.oy, vmul(f.px, f.ox)));
+	f.d2 = vfma(f.qz, f.oz, vfma(f.qy, f.oy, vmul(f.qx, f.ox)));
+	return f;
+}
+
 struct F3DVel {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0;
 	static constexpr int LANE_OPS = 37, SFU_OPS = 3;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4 b, float *acc, const PairConsts &) {
-		const float px = tg[0] - a.x, py = tg[1] - a.y, pz = tg[2] - a.z;        // r1
-		const float qx = tg[0] - b.x, qy = tg[1] - b.y, qz = tg[2] - b.z;        // r2
-		const float ox = px - qx, oy = py - qy, oz = pz - qz;                    // r0 = r1 - r2
-		const float cx = fmaf(py, qz, -(pz * qy));
-		const float cy = fmaf(pz, qx, -(px * qz));
-		const float cz = fmaf(px, qy, -(py * qx));
-		const float c2 = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
-		const float n1 = fmaf(pz, pz, fmaf(py, py, px * px));
-		const float n2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
-		const float d1 = fmaf(pz, oz, fmaf(py, oy, px * ox));
-		const float d2 = fmaf(qz, oz, fmaf(qy, oy, qx * ox));
-		const float t1 = a.w * mufu_rcp(c2);
-		const float t2 = fmaf(d1, mufu_rsqrt(n1), -(d2 * mufu_rsqrt(n2)));
-		const bool ok = (fabsf(t1) <= 3.40282346e38f) && (fabsf(t2) <= 3.40282346e38f);
-		const float kk = ok ? t1 * t2 : 0.0f;
-		acc[0] = fmaf(kk, cx, acc[0]);
-		acc[1] = fmaf(kk, cy, acc[1]);
-		acc[2] = fmaf(kk, cz, acc[2]);
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
+		const Fil<W> f = filament_geometry(tg, a, b);
+		const Vec<W> cx = vfms(f.py, f.qz, vmul(f.pz, f.qy));
+		const Vec<W> cy = vfms(f.pz, f.qx, vmul(f.px, f.qz));
+		const Vec<W> cz = vfms(f.px, f.qy, vmul(f.py, f.qx));
+		const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
+		const Vec<W> t1 = vmul(vrcp(c2), a.w);
+		const Vec<W> t2 = vfms(f.d1, vrsqrt(f.n1), vmul(f.d2, vrsqrt(f.n2)));
+		const Vec<W> kk0 = vmul(t1, t2);
+		Vec<W> kk;
+		for (int i = 0; i < W; ++i) {
+			const bool ok = (fabsf(t1.lane(i)) <= 3.40282346e38f) && (fabsf(t2.lane(i)) <= 3.40282346e38f);
+			kk.set(i, ok ? kk0.lane(i) : 0.0f);
+		}
+		acc[0] = vfma(kk, cx, acc[0]);
+		acc[1] = vfma(kk, cy, acc[1]);
+		acc[2] = vfma(kk, cz, acc[2]);
 	}
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &) {
 		out[0] = acc[0]; out[1] = acc[1]; out[2] = acc[2];
@@ -563,29 +663,27 @@ struct F3DDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0;
 	static constexpr int LANE_OPS = 43, SFU_OPS = 3;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	CVTX_HD static void pair(const float *tg, const f4 a, const f4 b, float *acc, const PairConsts &) {
-		const float px = tg[0] - a.x, py = tg[1] - a.y, pz = tg[2] - a.z;        // r1
-		const float qx = tg[0] - b.x, qy = tg[1] - b.y, qz = tg[2] - b.z;        // r2
-		const float ox = px - qx, oy = py - qy, oz = pz - qz;                    // r0 = r1 - r2 (exact)
-		const float xx = fmaf(py, oz, -(pz * oy));                               // X = r1 x r0
-		const float xy = fmaf(pz, ox, -(px * oz));
-		const float xz = fmaf(px, oy, -(py * ox));
-		const float x2 = fmaf(xz, xz, fmaf(xy, xy, xx * xx));
-		const float n1 = fmaf(pz, pz, fmaf(py, py, px * px));
-		const float n2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
-		const float d1 = fmaf(pz, oz, fmaf(py, oy, px * ox));
-		const float d2 = fmaf(qz, oz, fmaf(qy, oy, qx * ox));
-		const float rs1 = mufu_rsqrt(n1), rs2 = mufu_rsqrt(n2), rsx = mufu_rsqrt(x2);
-		const float t212 = fmaf(d1, rs1, -(d2 * rs2));
-		const float sA = -(a.w * t212) * (rsx * rsx);
-		const float t222 = (x2 * rsx) * (rs1 - rs2);
-		const float Bv = b.w * t222;
-		const bool ok = (sA == sA) && (Bv == Bv);
-		const float sa = ok ? sA : 0.0f, bv = ok ? Bv : 0.0f;
-		acc[0] = fmaf(sa, ox, acc[0]);
-		acc[1] = fmaf(sa, oy, acc[1]);
-		acc[2] = fmaf(sa, oz, acc[2]);
-		acc[3] += bv;
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
+		const Fil<W> f = filament_geometry(tg, a, b);
+		const Vec<W> xx = vfms(f.py, f.oz, vmul(f.pz, f.oy));                    // X = r1 x r0
+		const Vec<W> xy = vfms(f.pz, f.ox, vmul(f.px, f.oz));
+		const Vec<W> xz = vfms(f.px, f.oy, vmul(f.py, f.ox));
+		const Vec<W> x2 = vfma(xz, xz, vfma(xy, xy, vmul(xx, xx)));
+		const Vec<W> rs1 = vrsqrt(f.n1), rs2 = vrsqrt(f.n2), rsx = vrsqrt(x2);
+		const Vec<W> t212 = vfms(f.d1, rs1, vmul(f.d2, rs2));
+		const Vec<W> sA = vmul(vneg(vmul(t212, a.w)), vmul(rsx, rsx));
+		const Vec<W> t222 = vmul(vmul(x2, rsx), vsub(rs1, rs2));
+		const Vec<W> Bv = vmul(t222, b.w);
+		Vec<W> sa, bv;
+		for (int i = 0; i < W; ++i) {
+			const bool ok = (sA.lane(i) == sA.lane(i)) && (Bv.lane(i) == Bv.lane(i));
+			sa.set(i, ok ? sA.lane(i) : 0.0f);
+			bv.set(i, ok ? Bv.lane(i) : 0.0f);
+		}
+		acc[0] = vfma(sa, f.ox, acc[0]);
+		acc[1] = vfma(sa, f.oy, acc[1]);
+		acc[2] = vfma(sa, f.oz, acc[2]);
+		acc[3] = vadd(acc[3], bv);
 	}
 	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &) {
 		const double wx = row[3], wy = row[4], wz = row[5];

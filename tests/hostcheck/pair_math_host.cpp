@@ -16,7 +16,8 @@
 using namespace cvtx;
 
 namespace {
-struct Runner {
+// W = lanes per Vec: 1 = scalar FP32, 2 = the packed FP32x2 form the kernel uses for even T
+template <int W> struct Runner {
 	const float *src; int n; const float *tgt; int m; float *out; int op; float sigma, nu;
 	template <class P> void run() {
 		const int S = 256;
@@ -28,22 +29,30 @@ struct Runner {
 		for (long j = 0; j < n; ++j) pack_source(kind, src + cols * j, A[j], B[j]);
 		const PairConsts k = P::make_consts(sigma, nu);
 #pragma omp parallel for schedule(static)
-		for (long i = 0; i < m; ++i) {
-			const float *row = tgt + (long)P::TCOLS * i;
-			float tg[P::NTGT];
-			P::load_target(row, tg);
-			double dacc[P::NACC];
-			for (int c = 0; c < P::NACC; ++c) dacc[c] = 0.0;
+		for (long i0 = 0; i0 < m; i0 += W) {
+			Vec<W> tg[P::NTGT];
+			const float *rows[W];
+			for (int l = 0; l < W; ++l) {
+				const long i = i0 + l < m ? i0 + l : m - 1;        // odd tail: repeat the last target
+				rows[l] = tgt + (long)P::TCOLS * i;
+				float one[P::NTGT];
+				P::load_target(rows[l], one);
+				for (int c = 0; c < P::NTGT; ++c) tg[c].set(l, one[c]);
+			}
+			double dacc[W][P::NACC];
+			for (int l = 0; l < W; ++l) for (int c = 0; c < P::NACC; ++c) dacc[l][c] = 0.0;
 			const int chain = P::CHAIN ? P::CHAIN : S;
 			for (long t0 = 0; t0 < npad; t0 += chain) {
-				float acc[P::NACC];
-				for (int c = 0; c < P::NACC; ++c) acc[c] = 0.0f;
-				for (long j = t0; j < t0 + chain; ++j) P::pair(tg, A[j], B[j], acc, k);
-				for (int c = 0; c < P::NACC; ++c) dacc[c] += (double)acc[c];
+				Vec<W> acc[P::NACC];
+				for (int c = 0; c < P::NACC; ++c) acc[c] = bc<W>(0.0f);
+				for (long j = t0; j < t0 + chain; ++j) P::template pair<W>(tg, A[j], B[j], acc, k);
+				for (int l = 0; l < W; ++l) for (int c = 0; c < P::NACC; ++c) dacc[l][c] += (double)acc[c].lane(l);
 			}
-			double res[P::NOUT];
-			P::finish(row, dacc, res, k);
-			for (int c = 0; c < P::NOUT; ++c) out[(long)P::NOUT * i + c] = (float)res[c];
+			for (int l = 0; l < W && i0 + l < m; ++l) {
+				double res[P::NOUT];
+				P::finish(rows[l], dacc[l], res, k);
+				for (int c = 0; c < P::NOUT; ++c) out[(long)P::NOUT * (i0 + l) + c] = (float)res[c];
+			}
 		}
 	}
 };
@@ -56,7 +65,14 @@ struct Meta {
 extern "C" int hostcheck_m2m(int op, int reg, const float *src, int n, const float *tgt, int m,
                              float *out, float sigma, float nu)
 {
-	Runner r = {src, n, tgt, m, out, op, sigma, nu};
+	Runner<2> r = {src, n, tgt, m, out, op, sigma, nu};
+	return dispatch_op(op, reg, r) ? 0 : -1;
+}
+
+extern "C" int hostcheck_m2m_scalar(int op, int reg, const float *src, int n, const float *tgt, int m,
+                                    float *out, float sigma, float nu)
+{
+	Runner<1> r = {src, n, tgt, m, out, op, sigma, nu};
 	return dispatch_op(op, reg, r) ? 0 : -1;
 }
 

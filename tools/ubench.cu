@@ -36,6 +36,46 @@ __global__ void __launch_bounds__(256) ffma_peak(float *out, int iters, float a,
 }
 
 template <int ILP>
+__global__ void __launch_bounds__(256) ffma2_peak(float *out, int iters, float a, float b) {
+	float2 x[ILP];
+#pragma unroll
+	for (int i = 0; i < ILP; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int r = 0; r < 16; ++r)
+#pragma unroll
+			for (int i = 0; i < ILP; ++i) x[i] = __ffma2_rn(x[i], make_float2(a, a), make_float2(b, b));
+	}
+	float s = 0;
+#pragma unroll
+	for (int i = 0; i < ILP; ++i) s += x[i].x + x[i].y;
+	if (s == 123.456f) out[0] = s;
+}
+
+// OP: 0 = FADD2, 1 = FMUL2, 2 = FADD (scalar), 3 = FMUL (scalar)
+template <int OP>
+__global__ void __launch_bounds__(256) packed_op_peak(float *out, int iters, float a) {
+	float2 x[8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int r = 0; r < 16; ++r)
+#pragma unroll
+			for (int i = 0; i < 8; ++i) {
+				if (OP == 0) x[i] = __fadd2_rn(x[i], make_float2(a, a));
+				else if (OP == 1) x[i] = __fmul2_rn(x[i], make_float2(a, a));
+				else if (OP == 2) { x[i].x = x[i].x + a; x[i].y = x[i].y + a; }
+				else { x[i].x = x[i].x * a; x[i].y = x[i].y * a; }
+			}
+	}
+	float s = 0;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+	if (s == 123.456f) out[0] = s;
+}
+
+template <int ILP>
 __global__ void __launch_bounds__(256) mufu_peak(float *out, int iters) {
 	float x[ILP];
 #pragma unroll
@@ -134,6 +174,22 @@ int main(int argc, char **argv) {
 		CK(cudaEventRecord(e0)); ffma_peak<4><<<blocks, 256>>>(dummy, iters, 1.0001f, 0.5f); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
 		ops = (double)blocks * 256 * iters * 16 * 4;
 		if (pass) printf("FFMA peak (ILP 4, 8 blk/SM): %.2f T lane-op/s = %.1f%% of nominal\n", ops / (time_ms(e0, e1) * 1e-3) * 1e-12, 100 * ops / (time_ms(e0, e1) * 1e-3) / peak_lane);
+		CK(cudaEventRecord(e0)); ffma2_peak<8><<<blocks, 256>>>(dummy, iters, 1.0001f, 0.5f); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+		ops = (double)blocks * 256 * iters * 16 * 8 * 2;
+		if (pass) printf("FFMA2 (packed f32x2) peak (ILP 8): %.2f T lane-op/s = %.1f%% of nominal, at half the issue slots\n", ops / (time_ms(e0, e1) * 1e-3) * 1e-12, 100 * ops / (time_ms(e0, e1) * 1e-3) / peak_lane);
+		{
+			const char *names[4] = {"FADD2", "FMUL2", "FADD", "FMUL"};
+			for (int op = 0; op < 4; ++op) {
+				CK(cudaEventRecord(e0));
+				if (op == 0) packed_op_peak<0><<<blocks, 256>>>(dummy, iters, 1.0001f);
+				else if (op == 1) packed_op_peak<1><<<blocks, 256>>>(dummy, iters, 1.0001f);
+				else if (op == 2) packed_op_peak<2><<<blocks, 256>>>(dummy, iters, 1.0001f);
+				else packed_op_peak<3><<<blocks, 256>>>(dummy, iters, 1.0001f);
+				CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+				ops = (double)blocks * 256 * iters * 16 * 8 * 2;
+				if (pass) printf("%s peak: %.2f T lane-op/s = %.1f%% of nominal\n", names[op], ops / (time_ms(e0, e1) * 1e-3) * 1e-12, 100 * ops / (time_ms(e0, e1) * 1e-3) / peak_lane);
+			}
+		}
 		CK(cudaEventRecord(e0)); mufu_peak<8><<<blocks, 256>>>(dummy, iters / 4); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
 		ops = (double)blocks * 256 * (iters / 4) * 16 * 8;
 		if (pass) printf("MUFU.RSQ peak: %.2f T op/s = %.1f%% of nominal (SMs x 16 x clock)\n", ops / (time_ms(e0, e1) * 1e-3) * 1e-12, 100 * ops / (time_ms(e0, e1) * 1e-3) / (peak_lane / 8));
@@ -174,6 +230,9 @@ int main(int argc, char **argv) {
 	run_variant<W, 4, 256, 2>(b, "vel-W chunks=4", 4);
 	run_variant<W, 4, 256, 2>(b, "vel-W chunks=8", 8);
 	run_variant<W, 4, 256, 2>(b, "vel-W chunks=16", 16);
+	run_variant<W, 2, 128, 6>(b, "vel-W chunks=8", 8);
+	run_variant<W, 2, 256, 3>(b, "vel-W chunks=8", 8);
+	run_variant<W, 4, 128, 4>(b, "vel-W chunks=8", 8);
 	run_variant<W, 4, 512, 1>(b, "vel-W", 1);
 	run_variant<W, 6, 128, 3>(b, "vel-W", 1);
 	run_variant<W, 6, 256, 1>(b, "vel-W", 1);
