@@ -20,6 +20,7 @@
 // result_array.  With several accelerators enabled the targets are split into
 // contiguous shards, one per device, sources replicated.
 #include <cuda_runtime.h>
+#include <omp.h>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -81,16 +82,29 @@ void build_info(int n_dev) {
 	std::abort();
 }
 
+// Threads for the host-side gather.  Not left to OMP_NUM_THREADS: launchers such as
+// torchrun export OMP_NUM_THREADS=1, which would serialise a 1M-pointer chase.
+[[maybe_unused]] int gather_threads() {
+	static int n = 0;
+	if (n == 0) {
+		const char *env = std::getenv("CVTX_B200_GATHER_THREADS");
+		n = env ? std::atoi(env) : 0;
+		if (n <= 0) { n = omp_get_num_procs(); if (n > 4) n = 4; }
+		if (n < 1) n = 1;
+	}
+	return n;
+}
+
 // Copy n rows of `row_bytes` through an array of pointers into contiguous memory.
 void gather_rows(void *dst, const void *const *ptrs, long n, size_t row_bytes) {
 	char *out = (char *)dst;
-#pragma omp parallel for schedule(static) if (n > 32768)
+#pragma omp parallel for schedule(static) num_threads(gather_threads()) if (n > 32768)
 	for (long i = 0; i < n; ++i) std::memcpy(out + (size_t)i * row_bytes, ptrs[i], row_bytes);
 }
 void copy_rows(void *dst, const void *src, long n, size_t row_bytes) {
 	const size_t total = (size_t)n * row_bytes, piece = 1 << 20;
 	const long pieces = (long)((total + piece - 1) / piece);
-#pragma omp parallel for schedule(static) if (pieces > 8)
+#pragma omp parallel for schedule(static) num_threads(gather_threads()) if (pieces > 8)
 	for (long i = 0; i < pieces; ++i) {
 		const size_t lo = (size_t)i * piece, len = lo + piece <= total ? piece : total - lo;
 		std::memcpy((char *)dst + lo, (const char *)src + lo, len);
@@ -153,6 +167,14 @@ CVTX_API void cvtx_initialise() {
 	if (n < 0) {
 		std::fprintf(stderr, "cvortex: CUDA initialisation failed: %s\n", cvtx_b200_last_error());
 		n = 0;
+	}
+	if (n == 0) {
+		// Same ABI behaviour as the reference without an OpenCL device (zero accelerators, host
+		// loops), but never silently: say it, and let deployments that must not run on the host
+		// turn it into a hard error.
+		std::fprintf(stderr, "cvortex: no CUDA accelerator found; cvtx_*_M2M_* calls will run the host loops.\n");
+		const char *req = std::getenv("CVTX_B200_REQUIRE_GPU");
+		if (req && req[0] == '1') { std::fprintf(stderr, "cvortex: CVTX_B200_REQUIRE_GPU=1 -> aborting.\n"); std::abort(); }
 	}
 	g_enabled.assign((size_t)n, 0);
 	// Default: accelerator 0 only, as the reference does (src/opencl_acc.cpp:192-201).

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from util import (REGS, VISC_REGS, SHAPES, call_abi, filaments, make_case, op_cases, particles2d,
-                  particles3d, points, rel_l2, upstream_per_target_ok)
+                  particles3d, points, rel_l2, upstream_per_target_ok, vort_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -58,7 +58,7 @@ def is_strict(op, reg):
 
 
 # ---- the reference's own differential test recipe (N = 1000, sigma 0.3, nu 0.1) ----
-@pytest.mark.parametrize("op,reg", op_cases())
+@pytest.mark.parametrize("op,reg", op_cases() + vort_cases())
 def test_reference_recipe_overlap(gpu, oracle, op, reg):
     rng = np.random.default_rng(1000 + seed_of(op, reg))
     n = 1000
@@ -75,7 +75,7 @@ def test_reference_recipe_overlap(gpu, oracle, op, reg):
 
 
 # ---- the benchmark regime (sigma = 0.02, box 10), ragged sizes ----
-@pytest.mark.parametrize("op,reg", op_cases())
+@pytest.mark.parametrize("op,reg", op_cases() + vort_cases())
 def test_bench_regime(gpu, oracle, op, reg):
     rng = np.random.default_rng(2000 + seed_of(op, reg))
     src, tgt = make_case(op, rng, 5003, 1237, self_targets=SHAPES[op][3])
@@ -88,7 +88,7 @@ def test_bench_regime(gpu, oracle, op, reg):
 
 
 # ---- upstream's Linux input scale: everything inside [0, 1.53e-4], rho < 1e-3 ----
-@pytest.mark.parametrize("op,reg", op_cases())
+@pytest.mark.parametrize("op,reg", op_cases() + vort_cases())
 def test_tiny_box_regime(gpu, oracle, op, reg):
     rng = np.random.default_rng(3000 + seed_of(op, reg))
     src, tgt = make_case(op, rng, 1000, 1000, box=1.53e-4, self_targets=True)

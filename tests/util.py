@@ -67,6 +67,8 @@ def make_case(op, rng, n, m, box=10.0, self_targets=False):
     """(sources, targets) for `op`.  self_targets: targets are the first m sources (exercises
     the coincident-pair rule the way the reference's benchmark does for dvort / visc)."""
     sc, tc, _, tparticles = SHAPES[op]
+    if op == "P3D_M2M_vort":
+        op = "P3D_M2M_vel"
     if op.startswith("P2D"):
         src = particles2d(rng, n, box)
         tgt = src[:m].copy() if (tparticles and self_targets) else (particles2d(rng, m, box) if tparticles else points(rng, m, 2, box))
@@ -92,6 +94,11 @@ def op_cases():
         out += [("P3D_M2M_visc_dvort", reg), ("P2D_M2M_visc_dvort", reg)]
     out += [("F3D_M2M_vel", "singular"), ("F3D_M2M_dvort", "singular")]
     return out
+
+
+def vort_cases():
+    """cvtx_P3D_M2M_vort (singular has zeta = 0 everywhere)."""
+    return [("P3D_M2M_vort", r) for r in ("winckelmans", "planetary", "gaussian")]
 
 
 def call_abi(lib, op, src, tgt, reg, sigma, nu):
