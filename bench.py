@@ -41,30 +41,44 @@ if ROOT not in sys.path:
 
 SIGMA, NU = 0.02, 1.0
 WORKLOADS = {
-    # name: (n particles, [(op, reg)], self-targets per op)
-    "p3d_vel+dvort_gaussian_1M": (1_000_000, [("P3D_M2M_vel", "gaussian"), ("P3D_M2M_dvort", "gaussian")]),
-    "p3d_vel_winckelmans_1M": (1_000_000, [("P3D_M2M_vel", "winckelmans")]),
-    "p3d_vel_winckelmans_10k": (10_000, [("P3D_M2M_vel", "winckelmans")]),
-    "p3d_visc_winckelmans_4M": (4_000_000, [("P3D_M2M_visc_dvort", "winckelmans")]),
-    "p2d_vel+visc_gaussian_4M": (4_000_000, [("P2D_M2M_vel", "gaussian"), ("P2D_M2M_visc_dvort", "gaussian")]),
+    # name: (n sources, n targets, [(op, reg)])      -- BASELINE.json configs[0..4] + the north-star headline
+    "p3d_vel_winckelmans_10k": (10_000, 10_000, [("P3D_M2M_vel", "winckelmans")]),                                   # configs[0]
+    "p3d_vel+dvort_gaussian_1M": (1_000_000, 1_000_000, [("P3D_M2M_vel", "gaussian"), ("P3D_M2M_dvort", "gaussian")]),  # configs[1]
+    "p3d_visc_winckelmans_4M": (4_000_000, 4_000_000, [("P3D_M2M_visc_dvort", "winckelmans")]),                      # configs[2]
+    "p2d_vel+visc_gaussian_4M": (4_000_000, 4_000_000, [("P2D_M2M_vel", "gaussian"), ("P2D_M2M_visc_dvort", "gaussian")]),  # configs[3]
+    "f3d_vel+dvort_100k_on_2M": (100_000, 2_000_000, [("F3D_M2M_vel", "singular"), ("F3D_M2M_dvort", "singular")]),  # configs[4]
+    "p3d_vel_winckelmans_1M": (1_000_000, 1_000_000, [("P3D_M2M_vel", "winckelmans")]),                              # headline target
 }
 DEFAULT_WORKLOAD = "p3d_vel+dvort_gaussian_1M"
-PARTICLE_TARGETS = {"P3D_M2M_dvort", "P3D_M2M_visc_dvort", "P2D_M2M_visc_dvort"}
+PARTICLE_TARGETS = {"P3D_M2M_dvort", "P3D_M2M_visc_dvort", "P2D_M2M_visc_dvort", "F3D_M2M_dvort"}
 
 
-def make_inputs(n, ops):
-    """Seeded version of the reference benchmark's arrays (one stream per array)."""
-    two_d = ops[0][0].startswith("P2D")
-    rng_p, rng_x = np.random.default_rng(20261017), np.random.default_rng(20261018)
+def make_inputs(n, m, ops):
+    """Seeded version of the reference benchmark's arrays (one stream per array).
+    Returns (S sources, TP particle targets, TX point targets).  For the particle ops the
+    particle targets ARE the sources (self-interaction, as bench/benchP3D.c:283-415 does) and
+    the point targets an independent uniform cloud; filaments (no upstream bench) follow
+    SURVEY 8d: start uniform, end = start + U(-0.1, 0.1)^3, strength U[0, 10), acting on m
+    independent particles / points."""
+    two_d, fil = ops[0][0].startswith("P2D"), ops[0][0].startswith("F3D")
+    rng_p, rng_x, rng_t = (np.random.default_rng(s) for s in (20261017, 20261018, 20261019))
     if two_d:
-        P = rng_p.uniform(0.0, 10.0, (n, 4)).astype(np.float32)
-        P[:, 3] = 0.01
-        X = rng_x.uniform(0.0, 10.0, (n, 2)).astype(np.float32)
+        S = rng_p.uniform(0.0, 10.0, (n, 4)).astype(np.float32)
+        S[:, 3] = 0.01
+        TX = rng_x.uniform(0.0, 10.0, (m, 2)).astype(np.float32)
+        TP = S[:m] if m <= n else None
+    elif fil:
+        S = rng_p.uniform(0.0, 10.0, (n, 7)).astype(np.float32)
+        S[:, 3:6] = S[:, 0:3] + rng_x.uniform(-0.1, 0.1, (n, 3)).astype(np.float32)
+        TP = rng_t.uniform(0.0, 10.0, (m, 7)).astype(np.float32)
+        TP[:, 6] = 0.01
+        TX = np.ascontiguousarray(TP[:, :3])
     else:
-        P = rng_p.uniform(0.0, 10.0, (n, 7)).astype(np.float32)
-        P[:, 6] = 0.01
-        X = rng_x.uniform(0.0, 10.0, (n, 3)).astype(np.float32)
-    return P, X
+        S = rng_p.uniform(0.0, 10.0, (n, 7)).astype(np.float32)
+        S[:, 6] = 0.01
+        TX = rng_x.uniform(0.0, 10.0, (m, 3)).astype(np.float32)
+        TP = S[:m] if m <= n else None
+    return S, TP, TX
 
 
 def out_cols(op):
@@ -123,13 +137,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm / cpu baseline
-def time_reference_cpu(n, ops, n_sample_targets, repeats=1):
+def time_reference_cpu(n, m, ops, n_sample_targets, repeats=1):
     """Time the reference's own OpenMP CPU path (oracle/_ref, else the oracle port) on all n
     sources x a strided sample of targets.  Returns (Gpair/s, seconds, kind, cores, description)."""
     from oracle import binding
-    P, X = make_inputs(n, ops)
-    idx = np.arange(0, n, max(1, n // n_sample_targets))[:n_sample_targets]
-    Xs, Ps = np.ascontiguousarray(X[idx]), np.ascontiguousarray(P[idx])
+    P, TP, X = make_inputs(n, m, ops)
+    idx = np.arange(0, m, max(1, m // n_sample_targets))[:n_sample_targets]
+    Xs, Ps = np.ascontiguousarray(X[idx]), np.ascontiguousarray(TP[idx])
     ora = binding.Oracle()
     cores = ora.num_threads()
     if binding.have_ref():
@@ -141,6 +155,8 @@ def time_reference_cpu(n, ops, n_sample_targets, repeats=1):
         def run(op, reg):
             fn = getattr(ref, op)
             tg = Ps if op in PARTICLE_TARGETS else Xs
+            if op.startswith("F3D"):
+                return fn(P, tg)
             return fn(P, tg, reg, SIGMA, NU) if op.endswith("visc_dvort") else fn(P, tg, reg, SIGMA)
     else:
         kind = "port"
@@ -163,24 +179,24 @@ def time_reference_cpu(n, ops, n_sample_targets, repeats=1):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n, ops = WORKLOADS[args.workload]
+    n, m, ops = WORKLOADS[args.workload]
     from oracle import binding
     cores = binding.Oracle().num_threads()
     # bounded sample: ~2-4 s per step on this box's cores
-    m_s = max(64, min(n, 32 * cores)) if n >= 100_000 else n
+    m_s = max(64, min(m, 32 * cores)) if n >= 100_000 else m
     times = []
     for k in range(args.warmup + args.steps):
-        rate, dt, kind, cores, desc = time_reference_cpu(n, ops, m_s)
+        rate, dt, kind, cores, desc = time_reference_cpu(n, m, ops, m_s)
         if k >= args.warmup:
             times.append(dt)
-    pairs = float(n) * min(m_s, n) * len(ops)
+    pairs = float(n) * min(m_s, m) * len(ops)
     total = sum(times)
     value = pairs * len(times) / total / 1e9
     line = {
         "impl": "reference", "metric": "pair-interactions/s", "value": value, "unit": "Gpair/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, n, ops, world=args.gpus),
+        "config": workload_config(args.workload, n, m, ops, world=args.gpus),
         "cpu_baseline": {"value": value, "unit": "Gpair/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "Gpair/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,9 +204,9 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, n, ops, world):
-    return {"workload": name, "ops": [f"cvtx_{o}/{r}" for o, r in ops], "n_sources": n, "n_targets": n,
-            "sigma": SIGMA, "kinematic_visc": NU, "pair_interactions_per_step": float(n) * n * len(ops),
+def workload_config(name, n, m, ops, world):
+    return {"workload": name, "ops": [f"cvtx_{o}/{r}" for o, r in ops], "n_sources": n, "n_targets": m,
+            "sigma": SIGMA, "kinematic_visc": NU, "pair_interactions_per_step": float(n) * m * len(ops),
             "parallelism": f"targets sharded over {world} GPU(s), sources replicated",
             "l2": "256 MiB scratch write between steps (L2 flush); sources (32 MB packed) are L2-resident by design"}
 
@@ -232,13 +248,14 @@ def main():
     be = api.backend()
     lib = api.library()
 
-    n, ops = WORKLOADS[args.workload]
-    P, X = make_inputs(n, ops)
-    lo, hi = target_range(n, rank, world)
+    n, m, ops = WORKLOADS[args.workload]
+    P, TP, X = make_inputs(n, m, ops)
+    lo, hi = target_range(m, rank, world)
     m_local = hi - lo
-    # HBM-resident state: this rank's shard of the particles (sources) and its targets
-    src_local = torch.from_numpy(P[lo:hi]).to(dev)
-    tgts = {op: torch.from_numpy(np.ascontiguousarray((P if op in PARTICLE_TARGETS else X)[lo:hi])).to(dev) for op, _ in ops}
+    slo, shi = target_range(n, rank, world)
+    # HBM-resident state: this rank's shard of the sources and its contiguous range of targets
+    src_local = torch.from_numpy(np.ascontiguousarray(P[slo:shi])).to(dev)
+    tgts = {op: torch.from_numpy(np.ascontiguousarray((TP if op in PARTICLE_TARGETS else X)[lo:hi])).to(dev) for op, _ in ops}
     outs = {op: torch.empty((m_local, out_cols(op)), device=dev) for op, _ in ops}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sharded = ShardedM2M(be, local_rank, n)
@@ -283,7 +300,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nl, op=dist.ReduceOp.SUM)
     ms = float(t.item())
-    pairs_per_step = float(n) * n * len(ops)
+    pairs_per_step = float(n) * m * len(ops)
     value = pairs_per_step * args.steps / (ms * 1e-3) / 1e9
 
     # per-kernel durations (events on the launching stream, inside the timed region)
@@ -297,13 +314,16 @@ def main():
     # ---- e2e: the reference's ABI with host pointer arrays, wall clock
     e2e = None
     if not args.no_e2e:
-        host_t = {op: np.ascontiguousarray((P if op in PARTICLE_TARGETS else X)[lo:hi]) for op, _ in ops}
+        host_t = {op: np.ascontiguousarray((TP if op in PARTICLE_TARGETS else X)[lo:hi]) for op, _ in ops}
 
         def e2e_step():
             res = []
             for op, reg in ops:
                 fn = getattr(lib, op)
-                res.append(fn(P, host_t[op], reg, SIGMA, NU) if op.endswith("visc_dvort") else fn(P, host_t[op], reg, SIGMA))
+                if op.startswith("F3D"):
+                    res.append(fn(P, host_t[op]))
+                else:
+                    res.append(fn(P, host_t[op], reg, SIGMA, NU) if op.endswith("visc_dvort") else fn(P, host_t[op], reg, SIGMA))
                 assert be.last_dispatch() == 1
             return res
         e2e_step()
@@ -361,14 +381,14 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding
             cores = binding.Oracle().num_threads()
-            m_s = max(256, min(n, 96 * cores)) if n >= 100_000 else n
-            rate_c, secs, kind, cores, desc = time_reference_cpu(n, ops, m_s)
+            m_s = max(256, min(m, 96 * cores)) if n >= 100_000 else m
+            rate_c, secs, kind, cores, desc = time_reference_cpu(n, m, ops, m_s)
             cpu = {"value": rate_c, "unit": "Gpair/s", "cores": cores, "kind": kind, "sample": desc + f", {secs:.1f} s"}
         line = {
             "metric": "pair-interactions/s", "value": value, "unit": "Gpair/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, n, ops, world),
+            "config": workload_config(args.workload, n, m, ops, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()),
             "roofline": roofline, "cpu_baseline": cpu,
         }

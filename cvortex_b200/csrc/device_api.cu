@@ -94,18 +94,20 @@ struct Plan { int T, B, gx, gy, tiles_per_chunk; };
 
 // Pick targets-per-thread and the number of source chunks so that the grid is
 // many waves of equal work units (see the header of m2m_kernel.cuh).
-Plan make_plan(int n_src, int n_tgt, int n_out, int sm_count) {
+Plan make_plan(int n_src, int n_tgt, int n_out, int sm_count, int pref_T) {
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
-	static const int cand_T[3] = {4, 2, 1}, cand_B[3] = {256, 256, 128}, cand_occ[3] = {2, 3, 8};
+	// candidates, largest register tile first; start at the op's measured preference
+	static const int cand_T[4] = {8, 4, 2, 1}, cand_B[4] = {128, 256, 256, 128}, cand_occ[4] = {2, 2, 3, 8};
 	Plan p = {};
 	const int cmax = n_src_tiles >= 2 ? n_src_tiles / 2 : 1;  // a chunk is at least two tiles
-	int pick = 2;
-	for (int v = 0; v < 3; ++v) {
+	int pick = 3;
+	const int first = pref_T >= 8 ? 0 : (pref_T >= 4 ? 1 : (pref_T >= 2 ? 2 : 3));
+	for (int v = first; v < 4; ++v) {
 		const long tiles_t = ((long)n_tgt + cand_B[v] * cand_T[v] - 1) / (cand_B[v] * cand_T[v]);
 		if (tiles_t * cmax >= 2L * sm_count * cand_occ[v]) { pick = v; break; }
 	}
 	const int fT = g_force_T.load();
-	if (fT == 4) pick = 0; else if (fT == 2) pick = 1; else if (fT == 1) pick = 2;
+	if (fT == 8) pick = 0; else if (fT == 4) pick = 1; else if (fT == 2) pick = 2; else if (fT == 1) pick = 3;
 	p.T = cand_T[pick]; p.B = cand_B[pick];
 	const long tiles_t = ((long)n_tgt + p.B * p.T - 1) / (p.B * p.T);
 	const long want_units = 24L * sm_count * cand_occ[pick];
@@ -127,7 +129,8 @@ struct Launcher {
 	M2MArgs args; Plan plan; cudaStream_t st; cudaError_t err;
 	template <class P> void run() {
 		const dim3 grid(plan.gx, plan.gy);
-		if (plan.T == 4) m2m_kernel<P, 4, 256, 2><<<grid, 256, 0, st>>>(args);
+		if (plan.T == 8) m2m_kernel<P, 8, 128, 2><<<grid, 128, 0, st>>>(args);
+		else if (plan.T == 4) m2m_kernel<P, 4, 256, 2><<<grid, 256, 0, st>>>(args);
 		else if (plan.T == 2) m2m_kernel<P, 2, 256, 3><<<grid, 256, 0, st>>>(args);
 		else m2m_kernel<P, 1, 128, 8><<<grid, 128, 0, st>>>(args);
 		err = cudaGetLastError();
@@ -135,8 +138,8 @@ struct Launcher {
 };
 
 struct Info {
-	int lane, sfu, tcols, nout;
-	template <class P> void run() { lane = P::LANE_OPS; sfu = P::SFU_OPS; tcols = P::TCOLS; nout = P::NOUT; }
+	int lane, sfu, tcols, nout, pref_T;
+	template <class P> void run() { lane = P::LANE_OPS; sfu = P::SFU_OPS; tcols = P::TCOLS; nout = P::NOUT; pref_T = P::PREF_T; }
 };
 
 struct ConstsOf {
@@ -211,7 +214,7 @@ int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tp
 	Info q = {};
 	if (!d || n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "bad device or counts");
 	if (!dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "bad op");
-	const Plan p = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount);
+	const Plan p = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount, q.pref_T);
 	if (block) *block = p.B;
 	if (tpt) *tpt = p.T;
 	if (grid_x) *grid_x = p.gx;
@@ -259,7 +262,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 		return CVTX_B200_OK;
 	}
 
-	const Plan plan = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount);
+	const Plan plan = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount, q.pref_T);
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
 	const int n_pad = n_src_tiles * kSrcTile;
 	const bool two = src_kind(op) != SRC_P2D;

@@ -53,6 +53,9 @@
 //           order over a smooth field (that is what PSE computes), so a long
 //           FP32 chain would lose what the reference keeps by summing every
 //           pair in double (src/P3D.cpp:283-295, src/P2D.cpp:222-230)
+//   PREF_T  targets per thread that measured fastest on B200 for large problems
+//           (profiles/sweep_ops_r1.txt); the planner falls back to smaller
+//           tiles when there are too few targets to fill the chip
 //   LANE_OPS, SFU_OPS   algorithmic FP32 lane-ops / MUFU ops per pair of THIS
 //                       formulation (FMA = 1 lane-op; compares/selects not
 //                       counted) -- the roofline denominators, see DESIGN.md
@@ -310,7 +313,7 @@ template <int W> CVTX_HD Rad3<W> rad3(const Vec<W> *tg, const f4 a) {
 // source  a = {x, y, z, vol}   b = {wx, wy, wz, 0}
 // ===========================================================================
 template <int REG> struct P3DVel {
-	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0;
+	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 15 + Reg3D<REG>::A_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
@@ -343,7 +346,7 @@ template <int REG> struct P3DVel {
 // parallel vorticity, and the hoisted sum would cancel catastrophically there.
 // ===========================================================================
 template <int REG> struct P3DDvort {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 22 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
@@ -400,7 +403,7 @@ template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 };
 
 template <int REG> struct P3DVisc {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 4, NOUT = 3, CHAIN = 8;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 4, NOUT = 3, CHAIN = 8, PREF_T = 4;
 	static constexpr int LANE_OPS = 14 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
@@ -465,7 +468,7 @@ template <> struct Zeta3D<REG_GAUSSIAN> {     // zeta = sqrt(2/pi) exp(-rho^2/2)
 };
 
 template <int REG> struct P3DVort {
-	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0;
+	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 9 + Zeta3D<REG>::OPS, SFU_OPS = Zeta3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
@@ -534,7 +537,7 @@ template <> struct Reg2D<REG_GAUSSIAN> {      // K = (1 - exp(-rho^2/2))/r^2
 };
 
 template <int REG> struct P2DVel {
-	static constexpr int NSRC4 = 1, TCOLS = 2, NTGT = 2, NACC = 2, NOUT = 2, CHAIN = 0;
+	static constexpr int NSRC4 = 1, TCOLS = 2, NTGT = 2, NACC = 2, NOUT = 2, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 7 + Reg2D<REG>::OPS, SFU_OPS = Reg2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
@@ -578,7 +581,7 @@ template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFu
 };
 
 template <int REG> struct P2DVisc {
-	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 2, NOUT = 1, CHAIN = 8;
+	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 2, NOUT = 1, CHAIN = 8, PREF_T = REG == REG_WINCKELMANS ? 2 : 4;
 	static constexpr int LANE_OPS = 8 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
@@ -624,7 +627,7 @@ template <int W> CVTX_HD Fil<W> filament_geometry(const Vec<W> *tg, const f4 a, 
 }
 
 struct F3DVel {
-	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0;
+	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 37, SFU_OPS = 3;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
@@ -660,7 +663,7 @@ struct F3DVel {
 // running sums: sum A (3), sum B (1); w_t applied once in finish().
 // ===========================================================================
 struct F3DDvort {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 43, SFU_OPS = 3;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {

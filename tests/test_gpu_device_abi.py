@@ -118,3 +118,57 @@ def test_full_size_4m_visc_strength_scaling(gpu, torch_cuda):
     b = _device_run(dev, torch, "P3D_M2M_visc_dvort", "winckelmans", src2, src2[:m].contiguous(), 0.02)
     assert torch.isfinite(a).all()
     assert torch.equal(b, 2 * a)
+
+
+def test_full_size_4m_p2d_sampled_parity(gpu, oracle, torch_cuda):
+    """Config 4 (4M 2D particles, Gaussian): vel and visc_dvort on a 262k-target shard against all
+    4M sources; the oracle checks 128 strided targets, and permuting the sources must not change
+    any result beyond summation-order rounding."""
+    torch = torch_cuda
+    _, dev = gpu
+    n, m = 4_000_000, 262_144
+    rng = np.random.default_rng(44)
+    P = rng.uniform(0, 10, (n, 4)).astype(np.float32)
+    P[:, 3] = 0.01
+    src = torch.from_numpy(P).cuda()
+    idx = np.arange(0, m, m // 128)[:128]
+    for op, tgt_np in (("P2D_M2M_vel", np.ascontiguousarray(P[:m, :2])), ("P2D_M2M_visc_dvort", np.ascontiguousarray(P[:m]))):
+        tgt = torch.from_numpy(tgt_np).cuda()
+        full = _device_run(dev, torch, op, "gaussian", src, tgt, 0.02)
+        assert torch.isfinite(full).all()
+        want = oracle.m2m(op, P, np.ascontiguousarray(tgt_np[idx]), "gaussian", 0.02, 1.0)
+        got = full[torch.from_numpy(idx).cuda()].cpu().numpy().reshape(want.shape)
+        e = rel_l2(got, want)
+        print(f"{op}/gaussian 4M sampled gpu-vs-ref {e:.2e}")
+        assert e <= TOL
+        perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+        again = _device_run(dev, torch, op, "gaussian", src[perm].contiguous(), tgt, 0.02)
+        assert float(torch.linalg.norm((again - full).double()) / torch.linalg.norm(full.double())) <= 2e-6
+
+
+def test_full_size_filaments_100k_on_2m(gpu, oracle, torch_cuda):
+    """Config 5 (100k filaments on 2M points / particles): full run on the GPU, 256 strided targets
+    checked against the oracle (FP64 arbitrates, see is_strict in test_gpu_parity.py), and
+    linearity in the filament strengths checked on every target."""
+    from util import filaments
+    torch = torch_cuda
+    _, dev = gpu
+    n, m = 100_000, 2_000_000
+    rng = np.random.default_rng(55)
+    F = filaments(rng, n, seg=0.1)
+    T = particles3d(rng, m, vol=0.01)
+    src = torch.from_numpy(F).cuda()
+    idx = np.arange(0, m, m // 256)[:256]
+    for op, tgt_np in (("F3D_M2M_vel", np.ascontiguousarray(T[:, :3])), ("F3D_M2M_dvort", T)):
+        tgt = torch.from_numpy(tgt_np).cuda()
+        full = _device_run(dev, torch, op, "singular", src, tgt, 0.0)
+        assert torch.isfinite(full).all()
+        sub = np.ascontiguousarray(tgt_np[idx])
+        f32, f64 = oracle.m2m(op, F, sub), oracle.m2m(op, F, sub, f64=True)
+        got = full[torch.from_numpy(idx).cuda()].cpu().numpy()
+        e_par, e_gpu, e_ref = rel_l2(got, f32), rel_l2(got, f64), rel_l2(f32, f64)
+        print(f"{op} 100k x 2M sampled: gpu-vs-ref {e_par:.2e} gpu-vs-f64 {e_gpu:.2e} ref-vs-f64 {e_ref:.2e}")
+        assert e_par <= TOL or e_gpu <= 3.0 * e_ref + 1e-6
+        src2 = src.clone()
+        src2[:, 6] *= 4                                           # strengths x4 -> results x4 exactly
+        assert torch.equal(_device_run(dev, torch, op, "singular", src2, tgt, 0.0), 4 * full)

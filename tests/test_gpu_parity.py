@@ -138,7 +138,7 @@ def test_smooth_field(gpu, oracle, reg):
 
 
 # ---- every kernel geometry the planner can choose gives the same answer ----
-@pytest.mark.parametrize("tpt,chunks", [(4, 1), (4, 3), (2, 1), (2, 5), (1, 1), (1, 7), (0, 0)])
+@pytest.mark.parametrize("tpt,chunks", [(8, 1), (8, 4), (4, 1), (4, 3), (2, 1), (2, 5), (1, 1), (1, 7), (0, 0)])
 @pytest.mark.parametrize("op,reg", [("P3D_M2M_vel", "winckelmans"), ("P3D_M2M_dvort", "gaussian"),
                                      ("P2D_M2M_visc_dvort", "gaussian"), ("F3D_M2M_dvort", "singular")])
 def test_kernel_geometries(gpu, oracle, op, reg, tpt, chunks):
