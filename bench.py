@@ -311,6 +311,35 @@ def main():
         kern[op] = {"reg": reg, "ms": float(d.mean()), "lane_ops": info["lane_ops"], "sfu_ops": info["sfu_ops"],
                     "pairs": float(n) * m_local}
 
+    # ---- config 2 "as fused pass" (SURVEY 8d): velocity AT the particles + stretching in one
+    # sweep over the sources (thin-ABI op CVTX_B200_P3D_VEL_DVORT); counted as 2 pair-interactions
+    # per (source, target) like the two separate ops it replaces
+    fused = None
+    if [o for o, _ in ops] == ["P3D_M2M_vel", "P3D_M2M_dvort"]:
+        reg = ops[0][1]
+        out6 = torch.empty((m_local, 6), device=dev)
+        full = sharded.gather_sources(src_local)
+        for _ in range(2):
+            be.m2m("P3D_M2M_vel_dvort", reg, local_rank, stream.cuda_stream, full, n, tgts["P3D_M2M_dvort"], m_local, out6, SIGMA, NU)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            full = sharded.gather_sources(src_local)
+            be.m2m("P3D_M2M_vel_dvort", reg, local_rank, stream.cuda_stream, full, n, tgts["P3D_M2M_dvort"], m_local, out6, SIGMA, NU)
+            flush.zero_()
+        f1.record(stream)
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fms = float(tf.item()) / args.steps
+        finfo = be.op_info("P3D_M2M_vel_dvort", reg)
+        fused = {"value": 2.0 * n * m / (fms * 1e-3) / 1e9, "unit": "Gpair/s", "ms_per_step": fms,
+                 "lane_ops_per_source_target": finfo["lane_ops"],
+                 "note": "vel evaluated at the particle positions (not the independent point cloud of the "
+                         "separate-op step) fused with dvort; additive thin-ABI op, not part of `value`"}
+
     # ---- e2e: the reference's ABI with host pointer arrays, wall clock
     e2e = None
     if not args.no_e2e:
@@ -390,7 +419,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, n, m, ops, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "fused_vel_dvort": fused,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

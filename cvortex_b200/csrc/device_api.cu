@@ -21,7 +21,7 @@
 
 using namespace cvtx;
 
-static_assert((int)CVTX_B200_P3D_VEL == OP_P3D_VEL && (int)CVTX_B200_F3D_DVORT == OP_F3D_DVORT, "op ids");
+static_assert((int)CVTX_B200_P3D_VEL == OP_P3D_VEL && (int)CVTX_B200_F3D_DVORT == OP_F3D_DVORT && (int)CVTX_B200_P3D_VEL_DVORT == OP_P3D_VEL_DVORT, "op ids");
 static_assert((int)CVTX_B200_SINGULAR == REG_SINGULAR && (int)CVTX_B200_GAUSSIAN == REG_GAUSSIAN, "reg ids");
 
 // ---- shared runtime pieces (declared in runtime.h) ----------------------------
@@ -92,36 +92,53 @@ int ensure_ready(Device *d) {                   // caller holds d->mu and has do
 // ---- launch planning ----------------------------------------------------------
 struct Plan { int T, B, gx, gy, tiles_per_chunk; };
 
-// Pick targets-per-thread and the number of source chunks so that the grid is
-// many waves of equal work units (see the header of m2m_kernel.cuh).
+// Pick the block geometry (targets per thread) and the number of source chunks.
+// Model: a launch is `waves` rounds of co-resident blocks; a block costs its tile count x its
+// target slots (a thread slot computes whether or not it holds a real target), shared `occ` ways,
+// over the geometry's measured relative efficiency, plus a fixed prologue; half a wave is lost
+// in the tail on average.  For large problems this reduces to "the op's preferred geometry,
+// >= 24 waves"; for small ones it trades padding against parallelism (10k x 10k, few targets).
 Plan make_plan(int n_src, int n_tgt, int n_out, int sm_count, int pref_T) {
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
-	// candidates, largest register tile first; start at the op's measured preference
 	static const int cand_T[4] = {8, 4, 2, 1}, cand_B[4] = {128, 256, 256, 128}, cand_occ[4] = {2, 2, 3, 8};
-	Plan p = {};
-	const int cmax = n_src_tiles >= 2 ? n_src_tiles / 2 : 1;  // a chunk is at least two tiles
-	int pick = 3;
+	static const double cand_eff[4] = {1.0, 0.985, 0.96, 0.79};      // profiles/sweep_ops_r1.txt, ubench_r1.txt
+	const double kPrologue = 16000.0;                                 // slot-pairs: ~1.5 us of one SM
+	const long mem_cap = (1L << 30) / ((long)n_tgt * n_out * 8 + 1);  // keep FP64 partials under 1 GiB
+	const int fT = g_force_T.load(), fC = g_force_chunks.load();
 	const int first = pref_T >= 8 ? 0 : (pref_T >= 4 ? 1 : (pref_T >= 2 ? 2 : 3));
-	for (int v = first; v < 4; ++v) {
-		const long tiles_t = ((long)n_tgt + cand_B[v] * cand_T[v] - 1) / (cand_B[v] * cand_T[v]);
-		if (tiles_t * cmax >= 2L * sm_count * cand_occ[v]) { pick = v; break; }
+	Plan p = {};
+	double best = 1e300;
+	for (int v = 0; v < 4; ++v) {
+		if (fT ? cand_T[v] != fT : v < first) continue;
+		const long slots_t = (long)cand_B[v] * cand_T[v];
+		const long tiles_t = ((long)n_tgt + slots_t - 1) / slots_t;
+		const long resident = (long)sm_count * cand_occ[v];
+		// candidate tiles-per-chunk values: every small one, then n_src_tiles / k
+		for (int pass = 0; pass < 2; ++pass) {
+			for (int k = 1; k <= 64; ++k) {
+				long tpc = pass == 0 ? k : (n_src_tiles + k - 1) / k;
+				if (n_src_tiles == 0) tpc = 0;
+				else if (tpc < 1 || tpc > n_src_tiles) continue;
+				long c = n_src_tiles ? (n_src_tiles + tpc - 1) / tpc : 1;
+				if (fC > 0) {
+					c = fC < n_src_tiles ? fC : (n_src_tiles ? n_src_tiles : 1);
+					tpc = n_src_tiles ? (n_src_tiles + c - 1) / c : 0;
+					c = n_src_tiles ? (n_src_tiles + tpc - 1) / tpc : 1;
+				}
+				if (c > 1 && c > mem_cap) continue;
+				if (c > 65535) continue;                                  // gridDim.y
+				if (c > 32 && tiles_t * 32 >= 24 * resident) continue;    // enough waves already: spare the partials
+				const long ctas = tiles_t * c;
+				const long waves = (ctas + resident - 1) / resident;
+				const double block = (double)tpc * kSrcTile * slots_t * cand_occ[v] / cand_eff[v] + kPrologue;
+				const double cost = ((double)waves + 0.5) * block + (c > 1 ? 2.0 * kPrologue : 0.0);
+				if (cost < best) {
+					best = cost;
+					p.T = cand_T[v]; p.B = cand_B[v]; p.gx = (int)tiles_t; p.gy = (int)c; p.tiles_per_chunk = (int)tpc;
+				}
+			}
+		}
 	}
-	const int fT = g_force_T.load();
-	if (fT == 8) pick = 0; else if (fT == 4) pick = 1; else if (fT == 2) pick = 2; else if (fT == 1) pick = 3;
-	p.T = cand_T[pick]; p.B = cand_B[pick];
-	const long tiles_t = ((long)n_tgt + p.B * p.T - 1) / (p.B * p.T);
-	const long want_units = 24L * sm_count * cand_occ[pick];
-	long c = (want_units + tiles_t - 1) / tiles_t;
-	const long mem_cap = (1L << 30) / ((long)n_tgt * n_out * 8 + 1);   // keep FP64 partials under 1 GiB
-	if (c > mem_cap) c = mem_cap;
-	if (c > cmax) c = cmax;
-	if (c < 1) c = 1;
-	const int fC = g_force_chunks.load();
-	if (fC > 0) c = fC < n_src_tiles ? fC : n_src_tiles;
-	if (n_src_tiles == 0) c = 1;
-	p.tiles_per_chunk = n_src_tiles ? (int)((n_src_tiles + c - 1) / c) : 0;
-	p.gy = n_src_tiles ? (n_src_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk : 1;
-	p.gx = (int)tiles_t;
 	return p;
 }
 
@@ -247,6 +264,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	Device *d = get_device(device);
 	if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
 	if (n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "negative count");
+	if (n_src > 2147483647 - 2 * kSrcTile) return fail(CVTX_B200_ERR_ARGUMENT, "too many sources for 32-bit tile indexing");
 	if (op_is_filament(op)) reg = REG_SINGULAR;
 	Info q = {};
 	if (!dispatch_op(op, reg, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "no kernel for this (op, regularisation)");

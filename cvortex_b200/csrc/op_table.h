@@ -21,14 +21,18 @@ enum OpId {
 	OP_P2D_VISC = 5,    // cvtx_P2D_M2M_visc_dvort  libcvtx.h:362-370
 	OP_F3D_VEL = 6,     // cvtx_F3D_M2M_vel         libcvtx.h:285-290
 	OP_F3D_DVORT = 7,   // cvtx_F3D_M2M_dvort       libcvtx.h:292-297
-	OP_COUNT = 8
+	OP_P3D_VEL_DVORT = 8,   // fused vel + dvort on particle targets (thin ABI only)
+	OP_COUNT = 9
 };
 
 enum SrcKind { SRC_P3D = 0, SRC_P2D = 1, SRC_F3D = 2 };
 
-inline SrcKind src_kind(int op) { return op <= OP_P3D_VORT ? SRC_P3D : (op <= OP_P2D_VISC ? SRC_P2D : SRC_F3D); }
+inline SrcKind src_kind(int op) {
+	if (op == OP_P3D_VEL_DVORT) return SRC_P3D;
+	return op <= OP_P3D_VORT ? SRC_P3D : (op <= OP_P2D_VISC ? SRC_P2D : SRC_F3D);
+}
 inline int src_cols(int op) { return src_kind(op) == SRC_P2D ? 4 : 7; }   // floats per raw source row
-inline bool op_is_filament(int op) { return op >= OP_F3D_VEL; }
+inline bool op_is_filament(int op) { return op == OP_F3D_VEL || op == OP_F3D_DVORT; }
 
 // Is (op, reg) a combination the reference accelerates?  visc ops only exist
 // for the two regularisations with an eta (reference src/nbody.cl:498-510,
@@ -98,7 +102,8 @@ template <class F> inline bool dispatch_op(int op, int reg, F &f) {
 	case OP_P2D_VEL:   CVTX_REG_CASES(P2DVel)
 	case OP_P2D_VISC:  CVTX_ETA_CASES(P2DVisc)
 	case OP_F3D_VEL:   f.template run<F3DVel>(); return true;
-	default:           f.template run<F3DDvort>(); return true;
+	case OP_F3D_DVORT: f.template run<F3DDvort>(); return true;
+	default:           CVTX_REG_CASES(P3DVelDvort)
 	}
 #undef CVTX_REG_CASES
 #undef CVTX_ETA_CASES

@@ -379,6 +379,52 @@ template <int REG> struct P3DDvort {
 };
 
 // ===========================================================================
+// Fused cvtx_P3D_M2M_vel + cvtx_P3D_M2M_dvort on the SAME particle targets, one
+// pass over the sources (SURVEY 7 step 4 / 8d config 2 "fused pass"): a time
+// stepper needs u(x_t) and dw_t for the same particles, and the two sums share
+// rad, r^2, the regularisation factor A = g/r^3 and the MUFU work.  Not an
+// entry point of the reference ABI (there vel takes bare points); reachable
+// through the thin ABI as CVTX_B200_P3D_VEL_DVORT.  out row = {u (3), dw (3)}.
+// ===========================================================================
+template <int REG> struct P3DVelDvort {
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 6, NOUT = 6, CHAIN = 0, PREF_T = 4;
+	static constexpr int LANE_OPS = 31 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
+	CVTX_HD static void load_target(const float *row, float *tg) {
+		for (int i = 0; i < 6; ++i) tg[i] = row[i];
+	}
+	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		Vec<W> A, Bn;
+		Reg3D<REG>::AB(d.r2, k, A, Bn);
+		// velocity: A (rad x w_s)          (A is zeroed at r = 0, where rad x w_s = 0 anyway)
+		const Vec<W> ux = vfms(d.y, b.z, vmul(d.z, b.y));
+		const Vec<W> uy = vfms(d.z, b.x, vmul(d.x, b.z));
+		const Vec<W> uz = vfms(d.x, b.y, vmul(d.y, b.x));
+		acc[0] = vfma(A, ux, acc[0]);
+		acc[1] = vfma(A, uy, acc[1]);
+		acc[2] = vfma(A, uz, acc[2]);
+		// stretching: A c + Bn (rad.c) rad,  c = w_t x w_s
+		const Vec<W> cx = vfms(tg[4], b.z, vmul(tg[5], b.y));
+		const Vec<W> cy = vfms(tg[5], b.x, vmul(tg[3], b.z));
+		const Vec<W> cz = vfms(tg[3], b.y, vmul(tg[4], b.x));
+		const Vec<W> trip = vfma(d.z, cz, vfma(d.y, cy, vmul(d.x, cx)));
+		const Vec<W> s = vmul(Bn, trip);
+		acc[3] = vfma(s, d.x, vfma(A, cx, acc[3]));
+		acc[4] = vfma(s, d.y, vfma(A, cy, acc[4]));
+		acc[5] = vfma(s, d.z, vfma(A, cz, acc[5]));
+	}
+	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
+		out[0] = acc[0] * k.s1; out[1] = acc[1] * k.s1; out[2] = acc[2] * k.s1;
+		out[3] = acc[3] * k.s0; out[4] = acc[4] * k.s0; out[5] = acc[5] * k.s0;
+	}
+	static PairConsts make_consts(float sigma, float nu) {
+		PairConsts k = P3DDvort<REG>::make_consts(sigma, nu);     // s0: stretching scale (signed sigma^3)
+		k.s1 = P3DVel<REG>::make_consts(sigma, nu).s0;            // s1: velocity scale -scaleA/(4 pi)
+		return k;
+	}
+};
+
+// ===========================================================================
 // cvtx_P3D_M2M_visc_dvort   dw_t = (2 nu/sigma^2) sum_s (w_s V_t - w_t V_s) eta(rho)
 // reference: src/P3D.cpp:116-144 (pair), :275-296 (sum), :432-456 (entry)
 // running sums: sum eta (w_s - w_t) (3), sum eta (V_s - V_t) (1); only

@@ -19,6 +19,7 @@ from . import _native
 OPS = {
     "P3D_M2M_vel": 0, "P3D_M2M_dvort": 1, "P3D_M2M_visc_dvort": 2, "P3D_M2M_vort": 3,
     "P2D_M2M_vel": 4, "P2D_M2M_visc_dvort": 5, "F3D_M2M_vel": 6, "F3D_M2M_dvort": 7,
+    "P3D_M2M_vel_dvort": 8,      # fused, thin ABI only (see include/cvtx_b200.h)
 }
 REGS = {"singular": 0, "winckelmans": 1, "planetary": 2, "gaussian": 3}
 

@@ -55,7 +55,11 @@ enum cvtx_b200_op {
 	CVTX_B200_P2D_VEL = 4,        /* cvtx_P2D_M2M_vel         src (n,4)  tgt (m,2)  out (m,2) */
 	CVTX_B200_P2D_VISC_DVORT = 5, /* cvtx_P2D_M2M_visc_dvort  src (n,4)  tgt (m,4)  out (m,1) */
 	CVTX_B200_F3D_VEL = 6,        /* cvtx_F3D_M2M_vel         src (n,7)  tgt (m,3)  out (m,3) */
-	CVTX_B200_F3D_DVORT = 7       /* cvtx_F3D_M2M_dvort       src (n,7)  tgt (m,7)  out (m,3) */
+	CVTX_B200_F3D_DVORT = 7,      /* cvtx_F3D_M2M_dvort       src (n,7)  tgt (m,7)  out (m,3) */
+	/* Additive (no counterpart in libcvtx.h): cvtx_P3D_M2M_vel evaluated AT the induced particles'
+	 * positions fused with cvtx_P3D_M2M_dvort on them, one pass over the sources.
+	 * out row = {u_x, u_y, u_z, dw_x, dw_y, dw_z}. */
+	CVTX_B200_P3D_VEL_DVORT = 8   /*                          src (n,7)  tgt (m,7)  out (m,6) */
 };
 
 /* Regularisations: the four values of cvtx_VortFunc::cl_kernel_name_ext the

@@ -58,3 +58,17 @@ def test_lane_op_metadata_is_consistent(hostcheck):
         assert hostcheck.hostcheck_meta(op, reg, v) == 0
         assert (v[0], v[1]) == (lane, sfu), (op, reg, v[0], v[1])
     assert hostcheck.hostcheck_meta(2, 0, v) == -1      # visc needs an eta: no singular variant
+
+
+@pytest.mark.parametrize("reg", ["singular", "winckelmans", "planetary", "gaussian"])
+def test_fused_vel_dvort_equals_the_two_separate_ops(hostcheck, oracle, reg):
+    """Thin-ABI op 8: velocity at the induced particles' positions + stretching, one pass."""
+    rng = np.random.default_rng(3)
+    src, tgt = make_case("P3D_M2M_dvort", rng, 900, 400, self_targets=True)
+    out = np.zeros((400, 6), np.float32)
+    assert hostcheck.hostcheck_m2m(8, REG[reg], src, 900, tgt, 400, out, 0.3, 0.0) == 0
+    vel = oracle.m2m("P3D_M2M_vel", src, np.ascontiguousarray(tgt[:, :3]), reg, 0.3)
+    dv = oracle.m2m("P3D_M2M_dvort", src, tgt, reg, 0.3)
+    assert rel_l2(out[:, :3], vel) <= 1e-5
+    e_ref = rel_l2(dv, oracle.m2m("P3D_M2M_dvort", src, tgt, reg, 0.3, f64=True))
+    assert rel_l2(out[:, 3:], dv) <= 1e-5 + 2 * e_ref
