@@ -8,14 +8,15 @@
 // It is NOT a transcription: every formula is rewritten so that
 //   * sigma powers, 1/4pi, nu ... leave the pair loop (they scale the finished
 //     sums once, in FP64);
-//   * target-only factors leave it too, using bilinearity:
-//       visc      : w_s V_t - w_t V_s = (w_s - w_t) V_t - w_t (V_s - V_t), so
-//                   dw_t = V_t sum eta (w_s - w_t) - w_t sum eta (V_s - V_t)
-//                   (differences taken per pair: for a smooth field the plain
-//                   hoisting V_t sum(eta w_s) - w_t sum(eta V_s) cancels
-//                   catastrophically; measured 8x worse than the reference)
+//   * target-only factors leave it too where that is numerically safe:
 //       F3D dvort : sum_s (B w_t + A x w_t) = (sum B) w_t + (sum A) x w_t
-//     P3D dvort deliberately keeps c = w_t x w_s per pair for the same reason;
+//     and stay per pair where it is not (measured):
+//       visc      : (w_s V_t - w_t V_s) is formed per pair.  Both hoisted forms,
+//                   V_t sum(eta w_s) - w_t sum(eta V_s) and
+//                   V_t sum eta (w_s - w_t) - w_t sum eta (V_s - V_t), end in a
+//                   subtraction that cancels (smooth fields / random strengths)
+//                   and lose up to 100x per target against the reference;
+//       P3D dvort : c = w_t x w_s is formed per pair for the same reason;
 //   * Winckelmans terms are division-free and regular at r = 0
 //       g/r^3          = (rho^2+2.5)(rho^2+1)^-5/2 / sigma^3
 //       (3g/rho^3 - zeta)/r^2 = (3rho^2+10.5)(rho^2+1)^-7/2 / sigma^2
@@ -427,7 +428,7 @@ template <int REG> struct P3DVelDvort {
 // ===========================================================================
 // cvtx_P3D_M2M_visc_dvort   dw_t = (2 nu/sigma^2) sum_s (w_s V_t - w_t V_s) eta(rho)
 // reference: src/P3D.cpp:116-144 (pair), :275-296 (sum), :432-456 (entry)
-// running sums: sum eta (w_s - w_t) (3), sum eta (V_s - V_t) (1); only
+// running sums: the three components of the result itself; only
 // Winckelmans / Gaussian have an eta (src/VortFunc.cpp:101-108, :245).
 // ===========================================================================
 template <int REG> struct Eta3D;
@@ -449,24 +450,22 @@ template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 };
 
 template <int REG> struct P3DVisc {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 4, NOUT = 3, CHAIN = 8, PREF_T = 4;
-	static constexpr int LANE_OPS = 14 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 8, PREF_T = 4;
+	static constexpr int LANE_OPS = 15 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
 	}
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
 		const Vec<W> eta = keep_if_pos(d.r2, Eta3D<REG>::eta(d.r2, k));   // coincident pair contributes nothing
-		acc[0] = vfma(eta, vsub(b.x, tg[3]), acc[0]);
-		acc[1] = vfma(eta, vsub(b.y, tg[4]), acc[1]);
-		acc[2] = vfma(eta, vsub(b.z, tg[5]), acc[2]);
-		acc[3] = vfma(eta, vsub(a.w, tg[6]), acc[3]);
+		// w_s V_t - w_t V_s per pair, one product rounded and one FMA (the reference rounds both
+		// products and the sum, src/P3D.cpp:136-140)
+		acc[0] = vfma(eta, vfms(tg[6], b.x, vmul(tg[3], a.w)), acc[0]);
+		acc[1] = vfma(eta, vfms(tg[6], b.y, vmul(tg[4], a.w)), acc[1]);
+		acc[2] = vfma(eta, vfms(tg[6], b.z, vmul(tg[5], a.w)), acc[2]);
 	}
-	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &k) {
-		const double vt = row[6];
-		out[0] = k.s0 * (vt * acc[0] - (double)row[3] * acc[3]);
-		out[1] = k.s0 * (vt * acc[1] - (double)row[4] * acc[3]);
-		out[2] = k.s0 * (vt * acc[2] - (double)row[5] * acc[3]);
+	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
+		out[0] = k.s0 * acc[0]; out[1] = k.s0 * acc[1]; out[2] = k.s0 * acc[2];
 	}
 	static PairConsts make_consts(float sigma, float nu) {
 		PairConsts k = {}; const double s = fabs((double)sigma);
@@ -627,18 +626,17 @@ template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFu
 };
 
 template <int REG> struct P2DVisc {
-	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 2, NOUT = 1, CHAIN = 8, PREF_T = REG == REG_WINCKELMANS ? 2 : 4;
-	static constexpr int LANE_OPS = 8 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
+	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 8, PREF_T = REG == REG_WINCKELMANS ? 2 : 4;
+	static constexpr int LANE_OPS = 7 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
 		const Vec<W> r2 = vfma(dy, dy, vmul(dx, dx));
 		const Vec<W> eta = keep_if_pos(r2, Eta2D<REG>::eta(r2, k));
-		acc[0] = vfma(eta, vsub(a.z, tg[2]), acc[0]);      // sum eta (G_s - G_t)
-		acc[1] = vfma(eta, vsub(a.w, tg[3]), acc[1]);      // sum eta (A_s - A_t)
+		acc[0] = vfma(eta, vfms(tg[3], a.z, vmul(tg[2], a.w)), acc[0]);      // eta (G_s A_t - G_t A_s)
 	}
-	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &k) {
-		out[0] = k.s0 * ((double)row[3] * acc[0] - (double)row[2] * acc[1]);
+	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &k) {
+		out[0] = k.s0 * acc[0];
 	}
 	static PairConsts make_consts(float sigma, float nu) {
 		PairConsts k = {}; const double s = fabs((double)sigma);

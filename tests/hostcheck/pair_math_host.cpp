@@ -41,7 +41,11 @@ template <int W> struct Runner {
 			}
 			double dacc[W][P::NACC];
 			for (int l = 0; l < W; ++l) for (int c = 0; c < P::NACC; ++c) dacc[l][c] = 0.0;
+#ifdef HOSTCHECK_CHAIN
+			const int chain = HOSTCHECK_CHAIN;      // experiment: one chain length for every op
+#else
 			const int chain = P::CHAIN ? P::CHAIN : S;
+#endif
 			for (long t0 = 0; t0 < npad; t0 += chain) {
 				Vec<W> acc[P::NACC];
 				for (int c = 0; c < P::NACC; ++c) acc[c] = bc<W>(0.0f);
