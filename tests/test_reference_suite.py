@@ -51,7 +51,7 @@ def test_reference_test_program_passes_on_the_host_path(product):
 # its rounding.  The mean per-target error of these ops is 1e-7 .. 6e-7 and their array-level relative
 # L2 error (the north-star metric) is <= 2e-6 (tests/test_gpu_parity.py).
 CANCELLING = ("F3D M2M vel", "F3D M2M dvort", "P2D M2M visc dvort gaussian", "P2D M2M visc dvort winckelmans",
-              "P3D M2M dvort gaussian", "P3D M2M visc dvort gaussian", "P3D M2M visc dvort winckelmans")
+              "P3D M2M dvort gaussian")
 
 
 @pytest.mark.gpu
