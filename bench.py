@@ -343,16 +343,26 @@ def main():
     # ---- e2e: the reference's ABI with host pointer arrays, wall clock
     e2e = None
     if not args.no_e2e:
-        host_t = {op: np.ascontiguousarray((TP if op in PARTICLE_TARGETS else X)[lo:hi]) for op, _ in ops}
+        # what a C caller holds between calls: the struct arrays, the arrays of pointers into them
+        # (built once, as the reference's bench setup does) and preallocated result arrays
+        from cvortex_b200.abi import PointerRows
+        srcs = PointerRows(P, P.shape[1])
+        host_t, host_o = {}, {}
+        for op, _ in ops:
+            rows = np.ascontiguousarray((TP if op in PARTICLE_TARGETS else X)[lo:hi])
+            host_t[op] = PointerRows(rows, rows.shape[1]) if op in PARTICLE_TARGETS else rows
+            host_o[op] = np.empty((m_local, out_cols(op)), dtype=np.float32)
 
         def e2e_step():
             res = []
             for op, reg in ops:
                 fn = getattr(lib, op)
                 if op.startswith("F3D"):
-                    res.append(fn(P, host_t[op]))
+                    res.append(fn(srcs, host_t[op], out=host_o[op]))
+                elif op.endswith("visc_dvort"):
+                    res.append(fn(srcs, host_t[op], reg, SIGMA, NU, out=host_o[op]))
                 else:
-                    res.append(fn(P, host_t[op], reg, SIGMA, NU) if op.endswith("visc_dvort") else fn(P, host_t[op], reg, SIGMA))
+                    res.append(fn(srcs, host_t[op], reg, SIGMA, out=host_o[op]))
                 assert be.last_dispatch() == 1
             return res
         e2e_step()
@@ -365,7 +375,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        h2d = sum(P.nbytes + host_t[op].nbytes for op, _ in ops)
+        h2d = sum(P.nbytes + (host_t[op].rows if op in PARTICLE_TARGETS else host_t[op]).nbytes for op, _ in ops)
         d2h = sum(r.nbytes for r in res)
         e2e = {"value": pairs_per_step * args.steps / dt / 1e9, "unit": "Gpair/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / args.steps,

@@ -65,6 +65,20 @@ def pointer_array(rows: np.ndarray) -> np.ndarray:
     return rows.ctypes.data + stride * np.arange(rows.shape[0], dtype=np.uint64)
 
 
+class PointerRows:
+    """Particles as a C caller holds them: the struct array plus the array of pointers to its
+    elements, built once (the reference's benchmark does the same in its setup,
+    bench/bencharraysetup.c:43-58) and passed to any number of calls."""
+
+    def __init__(self, rows, cols: int):
+        self.rows = _rows(rows, cols)
+        self.ptrs = pointer_array(self.rows)
+
+    @property
+    def shape(self):
+        return self.rows.shape
+
+
 class CvtxLibrary:
     """A loaded library exporting the reference's ``cvtx_*`` ABI."""
 
@@ -164,54 +178,53 @@ class CvtxLibrary:
         return np.array(r.x[:], dtype=np.float32)
 
     # ---- the hot path: all-pairs M2M ----
-    def _m2m(self, name, src, scols, tgt, tcols, ocols, tail, tgt_is_particles):
-        src, tgt = _rows(src, scols), _rows(tgt, tcols)
-        sp = pointer_array(src)
-        out = np.full((tgt.shape[0], ocols), np.nan, dtype=np.float32)
+    def _m2m(self, name, src, scols, tgt, tcols, ocols, tail, tgt_is_particles, out=None):
+        src = src if isinstance(src, PointerRows) else PointerRows(src, scols)
+        if out is None:
+            out = np.full((tgt.shape[0], ocols), np.nan, dtype=np.float32)
         if tgt_is_particles:
-            tp = pointer_array(tgt)
-            targ = tp.ctypes.data
+            tgt = tgt if isinstance(tgt, PointerRows) else PointerRows(tgt, tcols)
+            targ = tgt.ptrs.ctypes.data
         else:
-            tp = None
+            tgt = _rows(tgt, tcols)
             targ = tgt.ctypes.data
-        getattr(self.lib, name)(sp.ctypes.data, src.shape[0], targ, tgt.shape[0], out.ctypes.data, *tail)
-        del sp, tp
-        return out[:, 0] if ocols == 1 else out
+        getattr(self.lib, name)(src.ptrs.ctypes.data, src.shape[0], targ, tgt.shape[0], out.ctypes.data, *tail)
+        return out[:, 0] if ocols == 1 and out.ndim == 2 else out
 
-    def P3D_M2M_vel(self, particles, mes, reg, sigma):
+    def P3D_M2M_vel(self, particles, mes, reg, sigma, out=None):
         """cvtx_P3D_M2M_vel (libcvtx.h:213-220): (n,7) particles on (m,3) points -> (m,3)."""
         return self._m2m("cvtx_P3D_M2M_vel", particles, 7, mes, 3, 3,
-                         (C.byref(self.vortfunc(reg)), sigma), False)
+                         (C.byref(self.vortfunc(reg)), sigma), False, out)
 
-    def P3D_M2M_dvort(self, particles, induced, reg, sigma):
+    def P3D_M2M_dvort(self, particles, induced, reg, sigma, out=None):
         """cvtx_P3D_M2M_dvort (libcvtx.h:222-229): (n,7) on (m,7) particles -> (m,3)."""
         return self._m2m("cvtx_P3D_M2M_dvort", particles, 7, induced, 7, 3,
-                         (C.byref(self.vortfunc(reg)), sigma), True)
+                         (C.byref(self.vortfunc(reg)), sigma), True, out)
 
-    def P3D_M2M_visc_dvort(self, particles, induced, reg, sigma, nu):
+    def P3D_M2M_visc_dvort(self, particles, induced, reg, sigma, nu, out=None):
         """cvtx_P3D_M2M_visc_dvort (libcvtx.h:231-239)."""
         return self._m2m("cvtx_P3D_M2M_visc_dvort", particles, 7, induced, 7, 3,
-                         (C.byref(self.vortfunc(reg)), sigma, nu), True)
+                         (C.byref(self.vortfunc(reg)), sigma, nu), True, out)
 
-    def P3D_M2M_vort(self, particles, mes, reg, sigma):
+    def P3D_M2M_vort(self, particles, mes, reg, sigma, out=None):
         """cvtx_P3D_M2M_vort (libcvtx.h:241-248)."""
         return self._m2m("cvtx_P3D_M2M_vort", particles, 7, mes, 3, 3,
-                         (C.byref(self.vortfunc(reg)), sigma), False)
+                         (C.byref(self.vortfunc(reg)), sigma), False, out)
 
-    def P2D_M2M_vel(self, particles, mes, reg, sigma):
+    def P2D_M2M_vel(self, particles, mes, reg, sigma, out=None):
         """cvtx_P2D_M2M_vel (libcvtx.h:329-336): (n,4) on (m,2) -> (m,2)."""
         return self._m2m("cvtx_P2D_M2M_vel", particles, 4, mes, 2, 2,
-                         (C.byref(self.vortfunc(reg)), sigma), False)
+                         (C.byref(self.vortfunc(reg)), sigma), False, out)
 
-    def P2D_M2M_visc_dvort(self, particles, induced, reg, sigma, nu):
+    def P2D_M2M_visc_dvort(self, particles, induced, reg, sigma, nu, out=None):
         """cvtx_P2D_M2M_visc_dvort (libcvtx.h:362-370): (n,4) on (m,4) -> (m,)."""
         return self._m2m("cvtx_P2D_M2M_visc_dvort", particles, 4, induced, 4, 1,
-                         (C.byref(self.vortfunc(reg)), sigma, nu), True)
+                         (C.byref(self.vortfunc(reg)), sigma, nu), True, out)
 
-    def F3D_M2M_vel(self, filaments, mes):
+    def F3D_M2M_vel(self, filaments, mes, out=None):
         """cvtx_F3D_M2M_vel (libcvtx.h:285-290): (n,7) filaments on (m,3) -> (m,3)."""
-        return self._m2m("cvtx_F3D_M2M_vel", filaments, 7, mes, 3, 3, (), False)
+        return self._m2m("cvtx_F3D_M2M_vel", filaments, 7, mes, 3, 3, (), False, out)
 
-    def F3D_M2M_dvort(self, filaments, induced):
+    def F3D_M2M_dvort(self, filaments, induced, out=None):
         """cvtx_F3D_M2M_dvort (libcvtx.h:292-297): (n,7) filaments on (m,7) particles -> (m,3)."""
-        return self._m2m("cvtx_F3D_M2M_dvort", filaments, 7, induced, 7, 3, (), True)
+        return self._m2m("cvtx_F3D_M2M_dvort", filaments, 7, induced, 7, 3, (), True, out)

@@ -49,11 +49,11 @@
 //   NACC    FP32 running sums per target
 //   NOUT    output floats per target
 //   CHAIN   sources per FP32 running-sum chain before it is flushed into the
-//           FP64 accumulator (0 = one chain per shared-memory tile).  The
-//           viscous ops use short chains: their pair terms cancel to second
-//           order over a smooth field (that is what PSE computes), so a long
-//           FP32 chain would lose what the reference keeps by summing every
-//           pair in double (src/P3D.cpp:283-295, src/P2D.cpp:222-230)
+//           FP64 accumulator (0 = one chain per 256-source shared-memory
+//           tile, which every op uses today: with the pair terms formed as
+//           the reference forms them, a 256-long FP32 chain measured no
+//           worse than 8-long ones even where the sum cancels to second
+//           order; the knob stays for ops that need it)
 //   PREF_T  targets per thread that measured fastest on B200 for large problems
 //           (profiles/sweep_ops_r1.txt); the planner falls back to smaller
 //           tiles when there are too few targets to fill the chip
@@ -450,7 +450,7 @@ template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 };
 
 template <int REG> struct P3DVisc {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 8, PREF_T = 4;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 15 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
@@ -626,7 +626,7 @@ template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFu
 };
 
 template <int REG> struct P2DVisc {
-	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 8, PREF_T = REG == REG_WINCKELMANS ? 2 : 4;
+	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 2 : 4;
 	static constexpr int LANE_OPS = 7 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {

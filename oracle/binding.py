@@ -31,7 +31,12 @@ REG_IDS = {"singular": 0, "winckelmans": 1, "planetary": 2, "gaussian": 3}
 
 def build(ref: bool = True) -> None:
     """(Re)build the oracle port and, when /root/reference exists, oracle/_ref."""
-    targets = ["port"] + (["ref"] if ref and os.path.isdir("/root/reference/src") else [])
+    targets = ["port"]
+    if ref and os.path.isdir("/root/reference/src"):
+        targets.append("ref")
+        # the reference's own test program linked against the product library (needs it built)
+        if os.path.exists(os.path.join(os.path.dirname(HERE), "cvortex_b200", "lib", "libcvortex.so")):
+            targets.append("ref_tests")
     subprocess.run(["make", "-C", HERE, "--no-print-directory"] + targets, check=True,
                    stdout=subprocess.DEVNULL)
 
