@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 {
 	constexpr int S = kSrcTile;
 	constexpr int CHAIN = P::CHAIN ? P::CHAIN : S;
-	constexpr int UNROLL = CHAIN < 8 ? CHAIN : 8;
+#ifndef CVTX_UNROLL
+#define CVTX_UNROLL 8
+#endif
+	constexpr int UNROLL = CHAIN < CVTX_UNROLL ? CHAIN : CVTX_UNROLL;
 	static_assert(S % CHAIN == 0, "a tile must hold whole chains");
 	constexpr uint32_t kTileBytes = S * sizeof(float4);
 

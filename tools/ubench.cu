@@ -272,6 +272,25 @@ int main(int argc, char **argv) {
 	run_variant<W, 8, 256, 1>(b, "vel-W", 1);
 	run_variant<W, 8, 256, 1>(b, "vel-W chunks=8", 8);
 
+	printf("\n== more geometries, chunks=8\n");
+	run_variant<W, 6, 128, 3>(b, "vel-W", 8);
+	run_variant<W, 8, 128, 3>(b, "vel-W (168-reg cap)", 8);
+	run_variant<W, 6, 192, 2>(b, "vel-W", 8);
+	run_variant<W, 8, 192, 1>(b, "vel-W", 8);
+	typedef P3DDvort<REG_WINCKELMANS> DW;
+	typedef P3DDvort<REG_GAUSSIAN> DG;
+	run_variant<DW, 8, 128, 2>(b, "dvort-W", 8);
+	run_variant<DW, 6, 128, 3>(b, "dvort-W", 8);
+	run_variant<DW, 8, 128, 3>(b, "dvort-W (168-reg cap)", 8);
+	run_variant<DW, 4, 128, 5>(b, "dvort-W (96-reg cap)", 8);
+	run_variant<DW, 6, 192, 2>(b, "dvort-W", 8);
+	run_variant<DW, 8, 96, 3>(b, "dvort-W", 8);
+	run_variant<DG, 8, 128, 2>(b, "dvort-G", 8);
+	run_variant<DG, 6, 128, 3>(b, "dvort-G", 8);
+	run_variant<DG, 6, 192, 2>(b, "dvort-G", 8);
+	run_variant<P3DVel<REG_GAUSSIAN>, 8, 128, 2>(b, "vel-G", 8);
+	run_variant<P3DVel<REG_GAUSSIAN>, 6, 128, 3>(b, "vel-G", 8);
+
 	printf("\n== every family at T=4, B=256, chunks=8\n");
 	run_variant<P3DVel<REG_SINGULAR>, 4, 256, 2>(b, "P3D vel singular", 8);
 	run_variant<P3DVel<REG_WINCKELMANS>, 4, 256, 2>(b, "P3D vel winckelmans", 8);
