@@ -450,7 +450,7 @@ template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 };
 
 template <int REG> struct P3DVisc {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 4;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 15 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
@@ -626,7 +626,7 @@ template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFu
 };
 
 template <int REG> struct P2DVisc {
-	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 2 : 4;
+	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 2 : 8;
 	static constexpr int LANE_OPS = 7 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
