@@ -110,6 +110,7 @@ class CvtxLibrary:
             "cvtx_P2D_M2M_visc_dvort": (None, [_vp, i, _vp, i, _vp, _VFp, f, f]),
             "cvtx_F3D_M2M_vel": (None, [_vp, i, _vp, i, _vp]),
             "cvtx_F3D_M2M_dvort": (None, [_vp, i, _vp, i, _vp]),
+            "cvtx_F3D_inf_mtrx": (None, [_vp, i, _vp, _vp, i, _vp]),          # libcvtx.h:299-305
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -228,3 +229,13 @@ class CvtxLibrary:
     def F3D_M2M_dvort(self, filaments, induced, out=None):
         """cvtx_F3D_M2M_dvort (libcvtx.h:292-297): (n,7) filaments on (m,7) particles -> (m,3)."""
         return self._m2m("cvtx_F3D_M2M_dvort", filaments, 7, induced, 7, 3, (), True, out)
+
+    def F3D_inf_mtrx(self, filaments, mes, dirs, out=None):
+        """cvtx_F3D_inf_mtrx (libcvtx.h:299-305): (m, n) matrix, [i, j] = u_j(mes_i) . dir_i."""
+        fil = filaments if isinstance(filaments, PointerRows) else PointerRows(filaments, 7)
+        mes, dirs = _rows(mes, 3), _rows(dirs, 3)
+        if out is None:
+            out = np.full((mes.shape[0], fil.shape[0]), np.nan, dtype=np.float32)
+        self.lib.cvtx_F3D_inf_mtrx(fil.ptrs.ctypes.data, fil.shape[0], mes.ctypes.data, dirs.ctypes.data,
+                                   mes.shape[0], out.ctypes.data)
+        return out

@@ -172,6 +172,16 @@ cvtx::Device *cvtx::get_device(int device) {
 	return g_devices[device];
 }
 
+int cvtx::device_stream(int device, cudaStream_t *stream) {
+	Device *d = get_device(device);
+	if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
+	std::lock_guard<std::mutex> lk(d->mu);
+	CUDA_TRY(cudaSetDevice(device));
+	if (int rc = ensure_ready(d)) return rc;
+	*stream = d->stream;
+	return CVTX_B200_OK;
+}
+
 // =============================================================================
 extern "C" {
 
@@ -328,6 +338,35 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	}
 	CUDA_TRY(cudaEventRecord(d->arena_idle, st));
 	g_launches += launched;
+	return CVTX_B200_OK;
+}
+
+int cvtx_b200_f3d_inf_mtrx(int device, void *stream_, const float *fil, int n_fil, const float *mes,
+                           const float *dir, int n_mes, float *out)
+{
+	g_err.clear();
+	Device *d = get_device(device);
+	if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
+	if (n_fil < 0 || n_mes < 0) return fail(CVTX_B200_ERR_ARGUMENT, "negative count");
+	if (n_fil == 0 || n_mes == 0) return CVTX_B200_OK;
+	if (!fil || !mes || !dir || !out) return fail(CVTX_B200_ERR_ARGUMENT, "null pointer");
+	std::lock_guard<std::mutex> lk(d->mu);
+	CUDA_TRY(cudaSetDevice(device));
+	if (int rc = ensure_ready(d)) return rc;
+	constexpr int B = 256, W = 2;
+	const int gx = (n_fil + B * W - 1) / (B * W);
+	// rows per block: enough blocks to fill the chip several times over, at least one tile of rows
+	long want_blocks = 16L * d->prop.multiProcessorCount;
+	int gy = (int)((want_blocks + gx - 1) / gx);
+	if (gy > (n_mes + 127) / 128) gy = (n_mes + 127) / 128;
+	if (gy < 1) gy = 1;
+	if (gy > 65535) gy = 65535;
+	int rows_per_block = (n_mes + gy - 1) / gy;
+	rows_per_block = (rows_per_block + 127) / 128 * 128;
+	gy = (n_mes + rows_per_block - 1) / rows_per_block;
+	f3d_inf_mtrx_kernel<W, B><<<dim3(gx, gy), B, 0, (cudaStream_t)stream_>>>(fil, n_fil, mes, dir, 0, n_mes, rows_per_block, out);
+	CUDA_TRY(cudaGetLastError());
+	g_launches += 1;
 	return CVTX_B200_OK;
 }
 

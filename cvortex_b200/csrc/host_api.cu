@@ -305,4 +305,63 @@ CVTX_API void cvtx_F3D_M2M_dvort(const cvtx_F3D **array_start, const int num_fil
 	host_m2m_f3d_dvort(array_start, num_filaments, induced_start, num_induced, result_array);
 }
 
+// Dense influence matrix.  GPU route: filaments gathered and uploaded once,
+// then the matrix is produced in row slabs that fit the pinned result buffer and streamed back --
+// the m x n floats leaving over PCIe are what bounds this call, not the kernel.
+CVTX_API void cvtx_F3D_inf_mtrx(const cvtx_F3D **array_start, const int num_filaments, const bsv_V3f *mes_start,
+                                const bsv_V3f *dir_start, const int num_mes, float *result_matrix) {
+	std::vector<int> devs = enabled_devices();
+	if (devs.empty()) {
+		g_last_dispatch = 0;
+		host_f3d_inf_mtrx(array_start, num_filaments, mes_start, dir_start, num_mes, result_matrix);
+		return;
+	}
+	g_last_dispatch = 1;
+	g_last_devices = 1;
+	if (num_filaments <= 0 || num_mes <= 0) return;
+	const int dev = devs[0];
+	Device *d = get_device(dev);
+	HostStage &hs = host_stage();
+	std::lock_guard<std::mutex> lk(hs.mu);
+	const size_t fb = sizeof(cvtx_F3D) * (size_t)num_filaments, pb = sizeof(bsv_V3f) * (size_t)num_mes;
+	const size_t row_bytes = sizeof(float) * (size_t)num_filaments;
+	long slab_rows = (long)((size_t)(128u << 20) / row_bytes);
+	if (slab_rows < 1) slab_rows = 1;
+	if (slab_rows > num_mes) slab_rows = num_mes;
+	int rc = CVTX_B200_OK;
+	auto step = [&](cudaError_t e, const char *what) {
+		if (e != cudaSuccess && rc == CVTX_B200_OK) rc = fail(CVTX_B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+		return e == cudaSuccess;
+	};
+	cudaStream_t st = nullptr;
+	bool ok = true;
+	if ((rc = device_stream(dev, &st)) != CVTX_B200_OK) ok = false;
+	ok = ok && step(hs.src.reserve(fb), "pinned filaments") && step(hs.tgt.reserve(2 * pb), "pinned points")
+	     && step(hs.out.reserve(row_bytes * (size_t)slab_rows), "pinned result slab");
+	if (ok) {
+		std::lock_guard<std::mutex> dl(d->mu);
+		ok = step(d->d_src.reserve(fb), "device filaments") && step(d->d_tgt.reserve(2 * pb), "device points")
+		     && step(d->d_out.reserve(row_bytes * (size_t)slab_rows), "device result slab");
+	}
+	if (ok) {
+		gather_rows(hs.src.p, PTRS(array_start), num_filaments, sizeof(cvtx_F3D));
+		std::memcpy(hs.tgt.p, mes_start, pb);
+		std::memcpy((char *)hs.tgt.p + pb, dir_start, pb);
+		ok = step(cudaMemcpyAsync(d->d_src.p, hs.src.p, fb, cudaMemcpyHostToDevice, st), "H2D filaments")
+		     && step(cudaMemcpyAsync(d->d_tgt.p, hs.tgt.p, 2 * pb, cudaMemcpyHostToDevice, st), "H2D points");
+	}
+	for (long r0 = 0; ok && r0 < num_mes; r0 += slab_rows) {
+		const long rows = r0 + slab_rows <= num_mes ? slab_rows : num_mes - r0;
+		const float *mes_d = (const float *)d->d_tgt.p + 3 * r0;
+		const float *dir_d = (const float *)((const char *)d->d_tgt.p + pb) + 3 * r0;
+		const int krc = cvtx_b200_f3d_inf_mtrx(dev, st, (const float *)d->d_src.p, num_filaments, mes_d, dir_d, (int)rows,
+		                                       (float *)d->d_out.p);
+		if (krc != CVTX_B200_OK) { rc = krc; ok = false; break; }
+		ok = step(cudaMemcpyAsync(hs.out.p, d->d_out.p, row_bytes * (size_t)rows, cudaMemcpyDeviceToHost, st), "D2H slab")
+		     && step(cudaStreamSynchronize(st), "sync");
+		if (ok) copy_rows(result_matrix + (size_t)r0 * num_filaments, hs.out.p, rows, row_bytes);
+	}
+	if (!ok) gpu_failure("cvtx_F3D_inf_mtrx", rc);
+}
+
 }  // extern "C"

@@ -223,6 +223,13 @@ void host_m2m_f3d_dvort(const cvtx_F3D **a, int n, const cvtx_P3D **q, int m, bs
 #pragma omp parallel for schedule(static)
 	for (long i = 0; i < m; ++i) out[i] = st(m2s_f3d_dvort(a, n, q[i]));
 }
+/* result_matrix[i * num_filaments + j] = u_j(x_i) . dir_i  (reference src/F3D.cpp:204-227) */
+void host_f3d_inf_mtrx(const cvtx_F3D **a, int n, const bsv_V3f *x, const bsv_V3f *dir, int m, float *out) {
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < m; ++i)
+		for (int j = 0; j < n; ++j)
+			out[(long)i * n + j] = dot(f3d_vel(a[j], ld(x[i])), ld(dir[i]));
+}
 }  // namespace cvtx
 
 // ---- exported scalar entry points -------------------------------------------
@@ -279,14 +286,6 @@ CVTX_API bsv_V3f cvtx_F3D_M2S_vel(const cvtx_F3D **array_start, const int num_fi
 CVTX_API bsv_V3f cvtx_F3D_M2S_dvort(const cvtx_F3D **array_start, const int num_filaments, const cvtx_P3D *induced_particle) {
 	return st(m2s_f3d_dvort(array_start, num_filaments, induced_particle));
 }
-/* result_matrix[i * num_filaments + j] = u_j(x_i) . dir_i  (reference src/F3D.cpp:204-227) */
-CVTX_API void cvtx_F3D_inf_mtrx(const cvtx_F3D **array_start, const int num_filaments, const bsv_V3f *mes_start, const bsv_V3f *dir_start, const int num_mes, float *result_matrix) {
-#pragma omp parallel for schedule(static)
-	for (int i = 0; i < num_mes; ++i)
-		for (int j = 0; j < num_filaments; ++j)
-			result_matrix[(long)i * num_filaments + j] = dot(f3d_vel(array_start[j], ld(mes_start[i])), ld(dir_start[i]));
-}
-
 CVTX_API bsv_V2f cvtx_P2D_S2S_vel(const cvtx_P2D *self, const bsv_V2f mes_point, const cvtx_VortFunc *kernel, float regularisation_radius) {
 	float ux, uy;
 	p2d_vel(self, mes_point, kernel, 1.f / std::fabs(regularisation_radius), &ux, &uy);

@@ -211,4 +211,74 @@ __global__ void pack_sources_kernel(int kind, int cols, const float *__restrict_
 	if (Bq) Bq[i] = b;
 }
 
+// ---------------------------------------------------------------------------
+// cvtx_F3D_inf_mtrx on the device (reference src/F3D.cpp:204-227, CPU only
+// there): out[i * n + j] = u_j(x_i) . dir_i, the dense m x n influence matrix of n filaments on
+// m points.  Nothing is reduced, every pair is an output, so the roles flip against m2m_kernel:
+// a THREAD owns W filaments (lanes of Vec<W>, registers) so that a warp writes 32 consecutive
+// columns of a row (coalesced 128-byte stores), and the POINTS of a row tile are broadcast from
+// shared memory.  37 lane-ops + 4 for the projection per element and 4 bytes written: at the
+// ~800 G elements/s the FP32 pipe allows that is 3.2 TB/s of stores, so the kernel sits near both
+// roofs at once.
+template <int W, int B>
+__global__ void __launch_bounds__(B) f3d_inf_mtrx_kernel(const float *__restrict__ fil, int n,
+                                                          const float *__restrict__ mes, const float *__restrict__ dir,
+                                                          int row0, int row1, int rows_per_block,
+                                                          float *__restrict__ out /* row `row0` of the matrix */)
+{
+	constexpr int TILE = 128;
+	__shared__ float4 sx[TILE], sd[TILE];
+	const int tid = threadIdx.x;
+	const long jbase = (long)blockIdx.x * (B * W) + tid;
+	Vec<W> ax, ay, az, bx, by, bz, g;
+	bool live[W];
+#pragma unroll
+	for (int l = 0; l < W; ++l) {
+		long j = jbase + (long)l * B;
+		live[l] = j < n;
+		j = live[l] ? j : (long)n - 1;
+		const float *r = fil + j * 7;
+		ax.set(l, r[0]); ay.set(l, r[1]); az.set(l, r[2]);
+		bx.set(l, r[3]); by.set(l, r[4]); bz.set(l, r[5]);
+		g.set(l, r[6] / (4.0f * 3.14159265359f));                       // strength / (4 pi_f), src/F3D.cpp:47
+	}
+	const int first = row0 + blockIdx.y * rows_per_block;
+	const int last = min(first + rows_per_block, row1);
+	for (int t0 = first; t0 < last; t0 += TILE) {
+		const int cnt = min(TILE, last - t0);
+		__syncthreads();
+		for (int k = tid; k < cnt; k += B) {
+			const float *x = mes + (size_t)(t0 + k) * 3, *d = dir + (size_t)(t0 + k) * 3;
+			sx[k] = make_float4(x[0], x[1], x[2], 0.f);
+			sd[k] = make_float4(d[0], d[1], d[2], 0.f);
+		}
+		__syncthreads();
+#pragma unroll 4
+		for (int k = 0; k < cnt; ++k) {
+			const float4 x = sx[k], d = sd[k];
+			const Vec<W> px = vsub(x.x, ax), py = vsub(x.y, ay), pz = vsub(x.z, az);      // r1 = x - a
+			const Vec<W> qx = vsub(x.x, bx), qy = vsub(x.y, by), qz = vsub(x.z, bz);      // r2 = x - b
+			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);         // r0 = r1 - r2
+			const Vec<W> cx = vfms(py, qz, vmul(pz, qy));
+			const Vec<W> cy = vfms(pz, qx, vmul(px, qz));
+			const Vec<W> cz = vfms(px, qy, vmul(py, qx));
+			const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
+			const Vec<W> n1 = vfma(pz, pz, vfma(py, py, vmul(px, px)));
+			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
+			const Vec<W> d1 = vfma(pz, oz, vfma(py, oy, vmul(px, ox)));
+			const Vec<W> d2 = vfma(qz, oz, vfma(qy, oy, vmul(qx, ox)));
+			const Vec<W> t1 = vmul(vrcp(c2), g);
+			const Vec<W> t2 = vfms(d1, vrsqrt(n1), vmul(d2, vrsqrt(n2)));
+			const Vec<W> proj = vfma(cz, d.z, vfma(cy, d.y, vmul(cx, d.x)));               // c . dir
+			const Vec<W> val = vmul(vmul(t1, t2), proj);
+			float *row = out + (size_t)(t0 + k - row0) * n;
+#pragma unroll
+			for (int l = 0; l < W; ++l) {
+				const bool ok = (fabsf(t1.lane(l)) <= 3.40282346e38f) && (fabsf(t2.lane(l)) <= 3.40282346e38f);
+				if (live[l]) row[jbase + (long)l * B] = ok ? val.lane(l) : 0.0f;
+			}
+		}
+	}
+}
+
 }  // namespace cvtx

@@ -45,6 +45,8 @@ HostStage &host_stage();
 
 int fail(int code, const std::string &msg);
 Device *get_device(int device);
+// Make `device` current, create its stream / events on first use, hand back its private stream.
+int device_stream(int device, cudaStream_t *stream);
 
 // Run (op, reg) with n_src source rows in host_stage().src and n_tgt target
 // rows in host_stage().tgt.  Targets are split into contiguous shards over

@@ -52,6 +52,8 @@ class DeviceBackend:
         lib.cvtx_b200_m2m.argtypes = [i, i, i, vp, vp, i, vp, i, vp, f, f]
         lib.cvtx_b200_m2m_host.restype = i
         lib.cvtx_b200_m2m_host.argtypes = [i, i, i, vp, i, vp, i, vp, f, f, C.POINTER(sz), C.POINTER(sz)]
+        lib.cvtx_b200_f3d_inf_mtrx.restype = i
+        lib.cvtx_b200_f3d_inf_mtrx.argtypes = [i, vp, vp, i, vp, vp, i, vp]
         lib.cvtx_b200_op_info.restype, lib.cvtx_b200_op_info.argtypes = i, [i, i, ip, ip, ip, ip, ip]
         lib.cvtx_b200_plan.restype, lib.cvtx_b200_plan.argtypes = i, [i, i, i, i, ip, ip, ip, ip]
         lib.cvtx_b200_kernel_launches.restype = C.c_ulonglong
@@ -127,6 +129,12 @@ class DeviceBackend:
                                     _ptr(tgt), n_tgt, _ptr(out), sigma, nu)
         if rc:
             raise BackendError(f"cvtx_b200_m2m({op}, {reg}) failed ({rc}): {self.last_error()}")
+
+    def f3d_inf_mtrx(self, device: int, stream, fil, n_fil: int, mes, dirs, n_mes: int, out) -> None:
+        """Asynchronous dense influence matrix on device pointers (see cvtx_b200_f3d_inf_mtrx)."""
+        rc = self.lib.cvtx_b200_f3d_inf_mtrx(device, _ptr(stream), _ptr(fil), n_fil, _ptr(mes), _ptr(dirs), n_mes, _ptr(out))
+        if rc:
+            raise BackendError(f"cvtx_b200_f3d_inf_mtrx failed ({rc}): {self.last_error()}")
 
     def m2m_host(self, op: str, reg: str, device: int, src: np.ndarray, tgt: np.ndarray,
                  sigma: float = 1.0, nu: float = 0.0, out: np.ndarray | None = None):

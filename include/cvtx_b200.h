@@ -106,6 +106,12 @@ CVTX_B200_API int cvtx_b200_m2m_host(int op, int reg, int device,
                        float *out, float sigma, float nu,
                        size_t *h2d_bytes, size_t *d2h_bytes);
 
+/* cvtx_F3D_inf_mtrx on device pointers (libcvtx.h:299-305; CPU-only in the reference,
+ * src/F3D.cpp:204-227): out_dev[i * n_fil + j] = u_j(mes_i) . dir_i for n_fil filament rows
+ * (7 floats) and n_mes points / directions (3 floats each).  Asynchronous on `stream`. */
+CVTX_B200_API int cvtx_b200_f3d_inf_mtrx(int device, void *stream, const float *fil_dev, int n_fil,
+                                         const float *mes_dev, const float *dir_dev, int n_mes, float *out_dev);
+
 /* ---- introspection ------------------------------------------------------------ */
 /* Shape and roofline metadata of (op, reg): floats per source / target / output
  * row, and the algorithmic FP32 lane-ops and MUFU ops per pair of the kernel's

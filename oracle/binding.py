@@ -78,6 +78,8 @@ class Oracle:
             for op in ("F3D_M2M_vel", "F3D_M2M_dvort"):
                 f = getattr(lib, f"cvtx_oracle_{op}_{prec}")
                 f.restype, f.argtypes = None, [_fp, C.c_int, _fp, C.c_int, outp]
+            f = getattr(lib, f"cvtx_oracle_F3D_inf_mtrx_{prec}")
+            f.restype, f.argtypes = None, [_fp, C.c_int, _fp, _fp, C.c_int, outp]
         lib.cvtx_oracle_P3D_S2S_vel.argtypes = [_fp, _fp, C.c_int, C.c_float, _fp]
         lib.cvtx_oracle_P3D_S2S_dvort.argtypes = [_fp, _fp, C.c_int, C.c_float, _fp]
         lib.cvtx_oracle_P3D_S2S_visc_dvort.argtypes = [_fp, _fp, C.c_int, C.c_float, C.c_float, _fp]
@@ -107,6 +109,13 @@ class Oracle:
             fn(src, tgt, REG_IDS[reg], sigma, nu, out)
         else:
             fn(src, tgt, REG_IDS[reg], sigma, out)
+        return out
+
+    def inf_mtrx(self, fil, pts, dirs, f64: bool = False) -> np.ndarray:
+        """Dense (m, n) influence matrix of n filaments on m points along m directions."""
+        fil, pts, dirs = _f32(fil, 7), _f32(pts, 3), _f32(dirs, 3)
+        out = np.zeros((pts.shape[0], fil.shape[0]), dtype=np.float64 if f64 else np.float32)
+        getattr(self.lib, "cvtx_oracle_F3D_inf_mtrx_" + ("f64" if f64 else "f32"))(fil, fil.shape[0], pts, dirs, pts.shape[0], out)
         return out
 
     # -- M2M -------------------------------------------------------------

@@ -76,6 +76,10 @@ void cvtx_oracle_P2D_M2M_visc_dvort_f32(const float *src4, int n, const float *t
 void cvtx_oracle_F3D_M2M_vel_f32(const float *fil7, int n, const float *pts3, int m, float *out3);
 void cvtx_oracle_F3D_M2M_dvort_f32(const float *fil7, int n, const float *tgt7, int m, float *out3);
 
+/* Dense filament influence matrix (reference cvtx_F3D_inf_mtrx), out[i * n + j]. */
+void cvtx_oracle_F3D_inf_mtrx_f32(const float *fil7, int n, const float *pts3, const float *dirs3, int m, float *out);
+void cvtx_oracle_F3D_inf_mtrx_f64(const float *fil7, int n, const float *pts3, const float *dirs3, int m, double *out);
+
 /* M2M, all-FP64 evaluation of the same formulas; outputs are doubles. */
 void cvtx_oracle_P3D_M2M_vel_f64(const float *src7, int n, const float *pts3, int m, double *out3, int reg, float sigma);
 void cvtx_oracle_P3D_M2M_dvort_f64(const float *src7, int n, const float *tgt7, int m, double *out3, int reg, float sigma);

@@ -136,3 +136,19 @@ def test_python_mirror_refuses_to_run_without_a_gpu(product):
         api.initialise(require_gpu=True)
     with pytest.raises(BackendError):
         api.P3D_M2M_vel(np.zeros((4, 7), np.float32), np.zeros((4, 3), np.float32), "winckelmans", 0.1)
+
+
+def test_inf_mtrx_host_path_equals_reference(product, oracle):
+    """cvtx_F3D_inf_mtrx with every accelerator disabled: the reference's loops, bit for bit."""
+    from util import filaments, points
+    enabled = [k for k in range(product.num_accelerators()) if product.accelerator_enabled(k)]
+    for k in enabled:
+        product.accelerator_disable(k)
+    try:
+        rng = np.random.default_rng(2)
+        F, X = filaments(rng, 90, seg=0.5), points(rng, 37, 3)
+        D = rng.uniform(-1, 1, (37, 3)).astype(np.float32)
+        assert np.array_equal(product.F3D_inf_mtrx(F, X, D), oracle.inf_mtrx(F, X, D))
+    finally:
+        for k in enabled:
+            product.accelerator_enable(k)

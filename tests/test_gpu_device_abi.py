@@ -213,3 +213,32 @@ def test_lifecycle_on_the_gpu(gpu, oracle):
     assert lib.num_accelerators() >= 1 and lib.accelerator_enabled(0) == 1
     b = lib.P3D_M2M_vel(P, X, "winckelmans", 0.1)
     assert dev.last_dispatch() == 1 and np.array_equal(a, b)
+
+
+def test_filament_influence_matrix(gpu, oracle, torch_cuda):
+    """cvtx_F3D_inf_mtrx (CPU-only in the reference): through the public ABI
+    (row slabs streamed back) and through the thin ABI on device pointers."""
+    from util import filaments
+    torch = torch_cuda
+    lib, dev = gpu
+    rng = np.random.default_rng(77)
+    for n, m in ((1000, 700), (513, 129), (3, 2), (2600, 1500)):
+        F, X = filaments(rng, n, seg=0.3), points(rng, m, 3)
+        D = rng.uniform(-1, 1, (m, 3)).astype(np.float32)
+        got = lib.F3D_inf_mtrx(F, X, D)
+        assert dev.last_dispatch() == 1 and got.shape == (m, n) and np.all(np.isfinite(got))
+        f32, f64 = oracle.inf_mtrx(F, X, D), oracle.inf_mtrx(F, X, D, f64=True)
+        e_par, e_gpu, e_ref = rel_l2(got, f32), rel_l2(got, f64), rel_l2(f32, f64)
+        print(f"inf_mtrx {n}x{m}: gpu-vs-ref {e_par:.2e} gpu-vs-f64 {e_gpu:.2e} ref-vs-f64 {e_ref:.2e}")
+        assert e_par <= TOL or e_gpu <= 3.0 * e_ref + 1e-6
+        out = torch.full((m, n), float("nan"), device="cuda")
+        dev.f3d_inf_mtrx(0, torch.cuda.current_stream().cuda_stream, torch.from_numpy(F).cuda(), n,
+                         torch.from_numpy(X).cuda(), torch.from_numpy(D).cuda(), m, out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), got)
+    # a point exactly on a filament's start: the reference's finite-ness rule gives exactly 0
+    F, X = filaments(rng, 40, seg=0.3), points(rng, 8, 3)
+    X[3] = F[5, 0:3]
+    D = np.ones((8, 3), np.float32)
+    got = lib.F3D_inf_mtrx(F, X, D)
+    assert got[3, 5] == 0.0 and np.all(np.isfinite(got))
