@@ -20,7 +20,7 @@
  *   cvtx_b200_m2m_host()  flat host arrays in/out on one device, synchronous:
  *                         pinned staging + H2D + cvtx_b200_m2m + D2H.
  * The pointer-array entry points (`cvtx_P3D_M2M_vel(const cvtx_P3D **...)`) sit on
- * top of these in host_api.cpp: gather, shard targets over the enabled
+ * top of these in host_api.cu: gather, shard targets over the enabled
  * devices, call, scatter.
  *
  * Row formats are the reference's structs verbatim:
