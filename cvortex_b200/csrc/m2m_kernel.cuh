@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 	constexpr int NV = T / W;
 	const long base = (long)blockIdx.x * (B * T) + tid;
 	Vec<W> tg[NV][P::NTGT];
-	double dacc[T][P::NACC];
+	double dacc[T][P::NACC];      // (moving these to shared memory to raise occupancy was measured: no gain)
 #pragma unroll
 	for (int t = 0; t < T; ++t) {
 		long i = base + (long)t * B;
