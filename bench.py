@@ -407,6 +407,9 @@ def main():
             "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": traffic,
             "kernel": f"m2m_kernel<{dom}/{kd['reg']}>", "avg_launch_ms": kd["ms"], "pairs_per_launch": kd["pairs"],
             "lane_ops_per_pair": kd["lane_ops"], "sfu_ops_per_pair": kd["sfu_ops"],
+            "traffic_note": ("DRAM bytes per launch (ncu); the inputs are ~70 MB, the rest are the FP64 partial sums of the "
+                             "source chunks that exist for load balance (DESIGN.md section 3) -- 0.1 ms of HBM time in a "
+                             "1.2 s FP32-pipe-bound launch"),
             "peak_source": (f"nominal FP32 issue peak = {sms} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (sm_max_mhz of "
                             "MEASURED_PEAKS.json) x 2 flop; each algorithmic FP32 lane-op counted as one FMA slot. "
                             "MEASURED_PEAKS.json has no FP32 figure (HBM and bf16 only); an FFMA-only micro-benchmark "
