@@ -222,7 +222,7 @@ def test_filament_influence_matrix(gpu, oracle, torch_cuda):
     torch = torch_cuda
     lib, dev = gpu
     rng = np.random.default_rng(77)
-    for n, m in ((1000, 700), (513, 129), (3, 2), (2600, 1500)):
+    for n, m in ((1000, 700), (513, 129), (3, 2), (2600, 1500), (20000, 2100)):      # the last one needs two row slabs
         F, X = filaments(rng, n, seg=0.3), points(rng, m, 3)
         D = rng.uniform(-1, 1, (m, 3)).astype(np.float32)
         got = lib.F3D_inf_mtrx(F, X, D)
