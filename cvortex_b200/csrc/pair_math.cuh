@@ -207,7 +207,11 @@ template <int W> CVTX_HD Vec<W> gauss_tail(Vec<W> r, float k_t, float k_c) {
 // ---------------------------------------------------------------------------
 // 3D kernels:   A(r2)  ~ g(rho)/r^3           (velocity / first stretching term)
 //               Bn(r2) = -(3 g/rho^3 - zeta)/r^2 in the SAME units as A, so that
-//                        one accumulator set takes  A c + Bn (rad.c) rad
+//                        one accumulator set takes  A c + Bn (rad.c) rad.
+//                        Bn is handed back as two factors B1 * B2 and the caller
+//                        forms (B1 * (rad.c)) * B2: r^-5 alone leaves the FP32
+//                        range for r < 2e-8 or r > 4e7, the reassociated product
+//                        does not (the reference works in rho and is scale-free)
 // Units are chosen per regularisation so the loop needs the fewest lane-ops;
 // the matching sigma power sits in PairConsts::s0 (scaleA).
 // ---------------------------------------------------------------------------
@@ -222,13 +226,14 @@ template <> struct Reg3D<REG_WINCKELMANS> {
 		const Vec<W> ra = vrsqrt(a), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2);
 		return vmul(b, vmul(ra4, ra));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B_) {
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.5f), b2 = vfma(r2, k.c1, k.c2);
 		const Vec<W> ra = vrsqrt(a), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2), ra5 = vmul(ra4, ra);
 		// the self pair must give exactly 0: c = w_t x w_t formed with FMAs is
 		// only zero to rounding, and A(0) = 2.5 would amplify that residue
 		A_ = keep_if_pos(r2, vmul(b, ra5));
-		B_ = vmul(b2, vmul(ra5, ra2));
+		B1 = b2;
+		B2 = vmul(ra5, ra2);
 	}
 	static void consts(PairConsts &k, double s) {
 		k.c0 = (float)(1.0 / (s * s)); k.c1 = (float)(-3.0 / (s * s * s * s)); k.c2 = (float)(-10.5 / (s * s));
@@ -243,10 +248,11 @@ template <> struct Reg3D<REG_SINGULAR> {
 		const Vec<W> ri = vrsqrt(r2);
 		return keep_if_pos(r2, vmul(vmul(ri, ri), ri));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &, Vec<W> &A_, Vec<W> &B_) {
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> ri = vrsqrt(r2), ri2 = vmul(ri, ri), ri3 = vmul(ri2, ri);
 		A_ = keep_if_pos(r2, ri3);
-		B_ = keep_if_pos(r2, vmul(ri3, vmul(ri2, -3.0f)));
+		B1 = keep_if_pos(r2, vmul(ri2, -3.0f));
+		B2 = A_;
 	}
 	static void consts(PairConsts &, double) {}
 	static double scaleA(double) { return 1.0; }
@@ -260,10 +266,11 @@ template <> struct Reg3D<REG_PLANETARY> {
 		const Vec<W> ri = vrsqrt(r2);
 		return pick_if_less(r2, k.c0, bc<W>(k.c1), vmul(vmul(ri, ri), ri));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B_) {
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> ri = vrsqrt(r2), ri2 = vmul(ri, ri), ri3 = vmul(ri2, ri);
 		A_ = pick_if_less(r2, k.c0, keep_if_pos(r2, bc<W>(k.c1)), ri3);        // exact 0 for the self pair, as above
-		B_ = pick_if_less(r2, k.c0, bc<W>(0.0f), vmul(ri3, vmul(ri2, -3.0f)));
+		B1 = pick_if_less(r2, k.c0, bc<W>(0.0f), vmul(ri2, -3.0f));
+		B2 = A_;                                                               // finite in the core, where B1 = 0
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(s * s); k.c1 = (float)(1.0 / (s * s * s)); }
 	static double scaleA(double) { return 1.0; }
@@ -280,15 +287,15 @@ template <> struct Reg3D<REG_GAUSSIAN> {
 		const Vec<W> g = vfma(vneg(e), s, 1.0f);
 		return keep_if_pos(r2, vmul(g, vmul(vmul(ri, ri), ri)));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B_) {
+	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> ri = vrsqrt(r2), r = vmul(r2, ri), ri2 = vmul(ri, ri);
 		const Vec<W> e = vex2(vmul(r2, k.c1));
 		const Vec<W> s = gauss_tail(r, k.c0, k.c2);
 		const Vec<W> g = vfma(vneg(e), s, 1.0f);
 		const Vec<W> a = vmul(g, vmul(ri2, ri));
-		const Vec<W> h = vfma(a, -3.0f, vmul(e, k.c3));
 		A_ = keep_if_pos(r2, a);
-		B_ = keep_if_pos(r2, vmul(h, ri2));
+		B1 = vfma(A_, -3.0f, vmul(e, k.c3));                                   // from the guarded A: finite at r = 0
+		B2 = keep_if_pos(r2, ri2);
 	}
 	static void consts(PairConsts &k, double s) {
 		k.c0 = (float)(0.3275911 * kRecipSqrt2 / s);
@@ -354,13 +361,13 @@ template <int REG> struct P3DDvort {
 	}
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
-		Vec<W> A, Bn;
-		Reg3D<REG>::AB(d.r2, k, A, Bn);
+		Vec<W> A, B1, B2;
+		Reg3D<REG>::AB(d.r2, k, A, B1, B2);
 		const Vec<W> cx = vfms(tg[4], b.z, vmul(tg[5], b.y));
 		const Vec<W> cy = vfms(tg[5], b.x, vmul(tg[3], b.z));
 		const Vec<W> cz = vfms(tg[3], b.y, vmul(tg[4], b.x));
 		const Vec<W> trip = vfma(d.z, cz, vfma(d.y, cy, vmul(d.x, cx)));
-		const Vec<W> s = vmul(Bn, trip);
+		const Vec<W> s = vmul(vmul(B1, trip), B2);
 		acc[0] = vfma(s, d.x, vfma(A, cx, acc[0]));
 		acc[1] = vfma(s, d.y, vfma(A, cy, acc[1]));
 		acc[2] = vfma(s, d.z, vfma(A, cz, acc[2]));
@@ -395,8 +402,8 @@ template <int REG> struct P3DVelDvort {
 	}
 	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
-		Vec<W> A, Bn;
-		Reg3D<REG>::AB(d.r2, k, A, Bn);
+		Vec<W> A, B1, B2;
+		Reg3D<REG>::AB(d.r2, k, A, B1, B2);
 		// velocity: A (rad x w_s)          (A is zeroed at r = 0, where rad x w_s = 0 anyway)
 		const Vec<W> ux = vfms(d.y, b.z, vmul(d.z, b.y));
 		const Vec<W> uy = vfms(d.z, b.x, vmul(d.x, b.z));
@@ -409,7 +416,7 @@ template <int REG> struct P3DVelDvort {
 		const Vec<W> cy = vfms(tg[5], b.x, vmul(tg[3], b.z));
 		const Vec<W> cz = vfms(tg[3], b.y, vmul(tg[4], b.x));
 		const Vec<W> trip = vfma(d.z, cz, vfma(d.y, cy, vmul(d.x, cx)));
-		const Vec<W> s = vmul(Bn, trip);
+		const Vec<W> s = vmul(vmul(B1, trip), B2);
 		acc[3] = vfma(s, d.x, vfma(A, cx, acc[3]));
 		acc[4] = vfma(s, d.y, vfma(A, cy, acc[4]));
 		acc[5] = vfma(s, d.z, vfma(A, cz, acc[5]));
