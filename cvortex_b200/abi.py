@@ -39,6 +39,13 @@ class VortFunc(C.Structure):
 
 assert C.sizeof(VortFunc) == 80 and VortFunc.cl_kernel_name_ext.offset == 48
 
+REDISTRIBUTIONS = ("lambda0", "lambda1", "lambda2", "lambda3", "m4p")
+
+
+class RedistFunc(C.Structure):
+    """``cvtx_RedistFunc`` (libcvtx.h:96-99): the 1-D interpolant and its support radius in cells."""
+    _fields_ = [("func", C.CFUNCTYPE(C.c_float, C.c_float)), ("radius", C.c_float)]
+
 
 class V3f(C.Structure):
     _fields_ = [("x", C.c_float * 3)]
@@ -111,6 +118,10 @@ class CvtxLibrary:
             "cvtx_F3D_M2M_vel": (None, [_vp, i, _vp, i, _vp]),
             "cvtx_F3D_M2M_dvort": (None, [_vp, i, _vp, i, _vp]),
             "cvtx_F3D_inf_mtrx": (None, [_vp, i, _vp, _vp, i, _vp]),          # libcvtx.h:299-305
+            # remeshing / relaxation, libcvtx.h:250-265, 372-379
+            "cvtx_P3D_redistribute_on_grid": (i, [_vp, i, _vp, i, C.POINTER(RedistFunc), f, f]),
+            "cvtx_P2D_redistribute_on_grid": (i, [_vp, i, _vp, i, C.POINTER(RedistFunc), f, f]),
+            "cvtx_P3D_pedrizzetti_relaxation": (None, [_vp, i, f, _VFp, f]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -120,6 +131,11 @@ class CvtxLibrary:
             ctor = getattr(lib, f"cvtx_VortFunc_{reg}")
             ctor.restype, ctor.argtypes = VortFunc, []
             self._vf[reg] = ctor()
+        self._rf = {}
+        for name in REDISTRIBUTIONS:
+            ctor = getattr(lib, f"cvtx_RedistFunc_{name}")
+            ctor.restype, ctor.argtypes = RedistFunc, []
+            self._rf[name] = ctor()
 
     # ---- lifecycle / accelerators (reference src/accelerators.cpp:39-118) ----
     def initialise(self): self.lib.cvtx_initialise()
@@ -138,6 +154,10 @@ class CvtxLibrary:
     def vortfunc(self, reg) -> VortFunc:
         """``cvtx_VortFunc_<reg>()`` of *this* library (or pass a VortFunc through)."""
         return reg if isinstance(reg, VortFunc) else self._vf[reg]
+
+    def redistfunc(self, name) -> RedistFunc:
+        """``cvtx_RedistFunc_<name>()`` of *this* library (or pass a RedistFunc through)."""
+        return name if isinstance(name, RedistFunc) else self._rf[name]
 
     # ---- single pair ----
     def P3D_S2S_vel(self, p, x, reg, sigma):
@@ -239,3 +259,39 @@ class CvtxLibrary:
         self.lib.cvtx_F3D_inf_mtrx(fil.ptrs.ctypes.data, fil.shape[0], mes.ctypes.data, dirs.ctypes.data,
                                    mes.shape[0], out.ctypes.data)
         return out
+
+
+    # ---- remeshing and relaxation (the steps either side of the hot path in a time step) ----
+    def _redistribute(self, name, particles, cols, redist, grid_density, negligible_vort, max_output, count_only, out=None):
+        src = particles if isinstance(particles, PointerRows) else PointerRows(particles, cols)
+        rf = self.redistfunc(redist)
+        fn = getattr(self.lib, name)
+        if count_only:
+            return fn(src.ptrs.ctypes.data, src.shape[0], None, 0, C.byref(rf), grid_density, negligible_vort)
+        if max_output is None:   # the reference's own idiom: ask for the count, then for the particles
+            max_output = fn(src.ptrs.ctypes.data, src.shape[0], None, 0, C.byref(rf), grid_density, negligible_vort)
+        if out is None:
+            out = np.full((max(max_output, 1), cols), np.nan, dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape[0] >= max_output and out.shape[1] == cols
+        n = fn(src.ptrs.ctypes.data, src.shape[0], out.ctypes.data, max_output, C.byref(rf), grid_density, negligible_vort)
+        return out[:n]
+
+    def P3D_redistribute_on_grid(self, particles, redist, grid_density, negligible_vort=0.0, max_output=None,
+                                 count_only=False, out=None):
+        """cvtx_P3D_redistribute_on_grid (libcvtx.h:250-257): (n,7) particles -> (k,7) particles on grid nodes.
+        `out`: a caller-owned (>= max_output, 7) float32 array to write into, as a C caller would hold."""
+        return self._redistribute("cvtx_P3D_redistribute_on_grid", particles, 7, redist, grid_density,
+                                  negligible_vort, max_output, count_only, out)
+
+    def P2D_redistribute_on_grid(self, particles, redist, grid_density, negligible_vort=0.0, max_output=None,
+                                 count_only=False, out=None):
+        """cvtx_P2D_redistribute_on_grid (libcvtx.h:372-379): (n,4) particles -> (k,4) particles on grid nodes."""
+        return self._redistribute("cvtx_P2D_redistribute_on_grid", particles, 4, redist, grid_density,
+                                  negligible_vort, max_output, count_only, out)
+
+    def P3D_pedrizzetti_relaxation(self, particles, fdt, reg, sigma):
+        """cvtx_P3D_pedrizzetti_relaxation (libcvtx.h:259-265): returns the (n,7) particles with relaxed vorticity."""
+        src = PointerRows(np.array(particles, dtype=np.float32, copy=True), 7)
+        self.lib.cvtx_P3D_pedrizzetti_relaxation(src.ptrs.ctypes.data, src.shape[0], fdt,
+                                                 C.byref(self.vortfunc(reg)), sigma)
+        return src.rows

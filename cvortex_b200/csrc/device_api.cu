@@ -35,6 +35,7 @@ int g_device_count = -2;                                       // -2 = not probe
 }  // namespace
 
 int cvtx::fail(int code, const std::string &msg) { g_err = msg; return code; }
+void cvtx::count_launches(unsigned long long n) { g_launches += n; }
 
 cudaError_t cvtx::Buffer::reserve(size_t bytes) {
 	if (bytes <= cap) return cudaSuccess;
@@ -215,6 +216,7 @@ void cvtx_b200_release(void) {
 			cudaDeviceSynchronize();
 			Buffer *all[] = {&d->packedA, &d->packedB, &d->partial, &d->d_src, &d->d_tgt, &d->d_out};
 			for (Buffer *b : all) b->release();
+			for (Buffer &b : d->remesh) b.release();
 			cudaEventDestroy(d->arena_idle); cudaEventDestroy(d->k_start); cudaEventDestroy(d->k_stop);
 			cudaStreamDestroy(d->stream);
 			d->ready = false; d->timed = false;

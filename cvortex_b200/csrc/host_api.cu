@@ -54,6 +54,10 @@ std::vector<int> enabled_devices() {
 	for (size_t i = 0; i < g_enabled.size(); ++i) if (g_enabled[i]) v.push_back((int)i);
 	return v;
 }
+}  // namespace
+std::vector<int> cvtx::enabled_accelerators() { return enabled_devices(); }
+void cvtx::note_dispatch(int on_gpu, int n_devices) { g_last_dispatch = on_gpu; if (on_gpu) g_last_devices = n_devices; }
+namespace {
 
 void build_info(int n_dev) {
 	int rt = 0, drv = 0;
@@ -75,12 +79,14 @@ void build_info(int n_dev) {
 	}
 }
 
-[[noreturn]] void gpu_failure(const char *entry, int rc) {
+}  // namespace
+[[noreturn]] void cvtx::gpu_failure(const char *entry, int rc) {
 	std::fprintf(stderr, "cvortex: %s failed on the GPU path (status %d): %s\n"
 	                     "cvortex: refusing to substitute a CPU result; aborting.\n",
 	             entry, rc, cvtx_b200_last_error());
 	std::abort();
 }
+namespace {
 
 // Threads for the host-side gather.  Not left to OMP_NUM_THREADS: launchers such as
 // torchrun export OMP_NUM_THREADS=1, which would serialise a 1M-pointer chase.
@@ -95,12 +101,14 @@ void build_info(int n_dev) {
 	return n;
 }
 
+}  // namespace
 // Copy n rows of `row_bytes` through an array of pointers into contiguous memory.
-void gather_rows(void *dst, const void *const *ptrs, long n, size_t row_bytes) {
+void cvtx::gather_rows(void *dst, const void *const *ptrs, long n, size_t row_bytes) {
 	char *out = (char *)dst;
 #pragma omp parallel for schedule(static) num_threads(gather_threads()) if (n > 32768)
 	for (long i = 0; i < n; ++i) std::memcpy(out + (size_t)i * row_bytes, ptrs[i], row_bytes);
 }
+namespace {
 void copy_rows(void *dst, const void *src, long n, size_t row_bytes) {
 	const size_t total = (size_t)n * row_bytes, piece = 1 << 20;
 	const long pieces = (long)((total + piece - 1) / piece);

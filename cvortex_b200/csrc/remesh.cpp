@@ -1,0 +1,453 @@
+// remesh.cpp -- the cvtx_* entry points that sit either side of the all-pairs sums in a
+// vortex-particle time step: redistribution onto a regular grid (2-D and 3-D) and
+// Pedrizzetti relaxation.
+//
+// Replaces, in the reference:
+//   * src/RedistFunc.cpp:36-96            the five interpolants and their constructors;
+//   * src/P3D.cpp:509-665, src/P2D.cpp:283-436   cvtx_P3D/P2D_redistribute_on_grid and the
+//     strength-threshold pruning behind them (src/redistribution_helper_funcs.cpp:32-91,
+//     src/array_methods.cpp farray_info / minmax / mean);
+//   * src/P3D.cpp:667-707                 cvtx_P3D_pedrizzetti_relaxation.
+// (On g++ the reference's own tree build is an unfinished stub -- src/UIntKey96.h:243-244
+// `assert(false); /* TO DO. */` -- so under Linux these entry points only work here.)
+//
+// A redistribution call is two stages.  Stage A turns the particles into the set of grid
+// nodes that receive vorticity, with each node's summed strength: on the first enabled
+// accelerator when the caller passed one of the five built-in interpolants
+// (remesh_device.cu), else on the host (host_nodes below, same arithmetic, same bits).
+// Stage B (prune below) is the reference's post-processing on that node set -- it has to
+// end in the caller's host array anyway: drop nodes weaker than negligible_vort x the mean
+// strength, hand the dropped vorticity back evenly, and if the caller's array is still too
+// small find the strength threshold that fits it.
+//
+// Relaxation is one cvtx_P3D_M2M_vort call (GPU when enabled) and a per-particle blend.
+#include <omp.h>
+#include <parallel/algorithm>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/cvtx_b200.h"
+#include "export.h"
+#include "host_hooks.h"
+#include "remesh.h"
+
+using namespace cvtx;
+using namespace cvtx::remesh;
+
+// ---- the interpolants as plain functions (what cvtx_RedistFunc::func points at) -------
+namespace {
+float f_lambda0(float U) { return weight(K_LAMBDA0, U); }
+float f_lambda1(float U) { return weight(K_LAMBDA1, U); }
+float f_lambda2(float U) { return weight(K_LAMBDA2, U); }
+float f_lambda3(float U) { return weight(K_LAMBDA3, U); }
+float f_m4p(float U) { return weight(K_M4P, U); }
+float (*const kBuiltin[K_COUNT])(float) = {f_lambda0, f_lambda1, f_lambda2, f_lambda3, f_m4p};
+
+cvtx_RedistFunc builtin(int kind) {
+	cvtx_RedistFunc r;
+	r.func = kBuiltin[kind];
+	r.radius = kRadius[kind];
+	return r;
+}
+// Which built-in a caller's cvtx_RedistFunc is, or -1 for a user-defined one.
+int builtin_kind(const cvtx_RedistFunc *r) {
+	for (int k = 0; k < K_COUNT; ++k)
+		if (r->func == kBuiltin[k] && r->radius == kRadius[k]) return k;
+	return -1;
+}
+}  // namespace
+
+namespace {
+constexpr long kPiece = 1 << 16;      // rows per unit of host-side parallel work
+// Host threads for the O(n) passes.  Not left to OMP_NUM_THREADS: launchers such as
+// torchrun export OMP_NUM_THREADS=1.
+int host_threads() {
+	static const int n = [] { int p = omp_get_num_procs(); return p > 8 ? 8 : (p < 1 ? 1 : p); }();
+	return n;
+}
+}  // namespace
+
+// ---- grid placement (shared with the device stage) -----------------------------------
+Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const float *rows, long n, int row_floats, uint32_t *max_index) {
+	Grid g;
+	g.h = h;
+	g.rh = 1.f / h;
+	g.kind = kind;
+	g.half = half;
+	// bounds and FP64 coordinate sums: fixed-size pieces in parallel, combined in piece order,
+	// so the result does not depend on the thread count (one piece = the reference's plain
+	// sequential loop, src/array_methods.cpp minmax_xyz_posn / mean_xyz_posn)
+	struct Piece { float lo[3], hi[3]; double sum[3]; };
+	const long pieces = (n + kPiece - 1) / kPiece;
+	std::vector<Piece> piece((size_t)pieces);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
+	for (long p = 0; p < pieces; ++p) {
+		Piece q;
+		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
+		for (int a = 0; a < 3; ++a) { q.lo[a] = q.hi[a] = a < dim ? rows[b * row_floats + a] : 0.f; q.sum[a] = 0.0; }
+		for (long i = b; i < e; ++i)
+			for (int a = 0; a < dim; ++a) {
+				const float x = rows[i * row_floats + a];
+				q.lo[a] = q.lo[a] > x ? x : q.lo[a];
+				q.hi[a] = q.hi[a] < x ? x : q.hi[a];
+				q.sum[a] += (double)x;
+			}
+		piece[(size_t)p] = q;
+	}
+	float lo[3], hi[3];
+	double sum[3] = {0, 0, 0};
+	for (int a = 0; a < 3; ++a) { lo[a] = piece[0].lo[a]; hi[a] = piece[0].hi[a]; }
+	for (const Piece &q : piece)
+		for (int a = 0; a < dim; ++a) {
+			lo[a] = lo[a] > q.lo[a] ? q.lo[a] : lo[a];
+			hi[a] = hi[a] < q.hi[a] ? q.hi[a] : hi[a];
+			sum[a] += q.sum[a];
+		}
+	uint32_t top = 0;
+	for (int a = 0; a < 3; ++a) g.origin[a] = 0.f;
+	for (int a = 0; a < dim; ++a) {
+		const float mean = (float)(sum[a] / (double)n);
+		const float corner = lo[a] - 1.f * ((float)g.half * h);
+		const float cells = roundf((mean - corner) / h) + 5.f;
+		g.origin[a] = mean - cells * h;
+		const uint32_t k = (dim == 3 ? node_index_3d(hi[a], g.origin[a], g.rh) : node_index_2d(hi[a], g.origin[a], g.rh)) + (uint32_t)g.half;
+		top = k > top ? k : top;
+	}
+	if (max_index) *max_index = top;
+	return g;
+}
+
+int cvtx::remesh::code_bits(int dim, uint32_t max_index) {
+	int b = 0;
+	while (b < 32 && (max_index >> b) != 0) ++b;
+	if (b < 1) b = 1;
+	if (dim == 3 ? b > kBits3D : b > 31) return -1;
+	return dim * b;
+}
+
+namespace {
+
+// ---- stage A on the host --------------------------------------------------------------
+// Same records, same stable order by node code, same FP64 sums as remesh_device.cu.
+template <int D>
+void host_nodes(const float *rows, long n, const Grid &g, NodeSet *nodes) {
+	constexpr int ROW = D == 3 ? 7 : 4, COMPS = D == 3 ? 3 : 1;
+	std::vector<uint32_t> offset((size_t)n + 1, 0);
+#pragma omp parallel for schedule(static)
+	for (long i = 0; i < n; ++i) offset[i + 1] = (uint32_t)spread_particle<D>(rows + i * ROW, g, [](uint64_t, const float *) {});
+	for (long i = 0; i < n; ++i) offset[i + 1] += offset[i];
+	const size_t total = offset[n];
+	struct Record { uint64_t code; uint32_t at; };
+	std::vector<Record> rec(total);
+	std::vector<float> share(total * COMPS);
+#pragma omp parallel for schedule(static)
+	for (long i = 0; i < n; ++i) {
+		uint32_t at = offset[i];
+		spread_particle<D>(rows + i * ROW, g, [&](uint64_t m, const float *s) {
+			rec[at] = {m, at};
+			for (int c = 0; c < COMPS; ++c) share[(size_t)at * COMPS + c] = s[c];
+			++at;
+		});
+	}
+	__gnu_parallel::stable_sort(rec.begin(), rec.end(), [](const Record &a, const Record &b) { return a.code < b.code; });
+	nodes->code.clear();
+	nodes->strength.clear();
+	for (size_t j = 0; j < total;) {
+		double acc[COMPS] = {};
+		size_t e = j;
+		for (; e < total && rec[e].code == rec[j].code; ++e)
+			for (int c = 0; c < COMPS; ++c) acc[c] += (double)share[(size_t)rec[e].at * COMPS + c];
+		nodes->code.push_back(rec[j].code);
+		for (int c = 0; c < COMPS; ++c) nodes->strength.push_back((float)acc[c]);
+		j = e;
+	}
+}
+
+// User-defined interpolant: the weights come from the caller's function pointer, one call
+// per axis and stencil offset, so this cannot share spread_particle().  Records are
+// produced in the same order and summed the same way.
+template <int D>
+void host_nodes_user(const float *rows, long n, Grid g, const cvtx_RedistFunc *rf, NodeSet *nodes) {
+	constexpr int ROW = D == 3 ? 7 : 4, COMPS = D == 3 ? 3 : 1;
+	const int R = g.half, S = 2 * R + 1;
+	struct Record { uint64_t code; uint32_t at; };
+	std::vector<Record> rec;
+	std::vector<float> share;
+	std::vector<float> w((size_t)D * S);
+	for (long i = 0; i < n; ++i) {
+		const float *row = rows + i * ROW;
+		uint32_t k0[3] = {0, 0, 0};
+		for (int a = 0; a < D; ++a) {
+			k0[a] = D == 3 ? node_index_3d(row[a], g.origin[a], g.rh) : node_index_2d(row[a], g.origin[a], g.rh);
+			for (int o = 0; o < S; ++o) w[(size_t)a * S + o] = rf->func(cell_distance(row[a], k0[a] + (uint32_t)(o - R), g, a));
+		}
+		for (int a = 0; a < S; ++a)
+			for (int b = 0; b < S; ++b)
+				for (int c = 0; c < (D == 3 ? S : 1); ++c) {
+					float f = w[a] * w[(size_t)S + b];
+					if (D == 3) f = f * w[(size_t)2 * S + c];
+					float s[COMPS];
+					bool any = false;
+					for (int q = 0; q < COMPS; ++q) { s[q] = row[D + q] * f; any = any || s[q] != 0.f; }
+					if (!any) continue;
+					const uint64_t m = D == 3 ? morton3(k0[0] + (uint32_t)(a - R), k0[1] + (uint32_t)(b - R), k0[2] + (uint32_t)(c - R))
+					                          : morton2(k0[0] + (uint32_t)(a - R), k0[1] + (uint32_t)(b - R));
+					rec.push_back({m, (uint32_t)rec.size()});
+					for (int q = 0; q < COMPS; ++q) share.push_back(s[q]);
+				}
+	}
+	std::stable_sort(rec.begin(), rec.end(), [](const Record &a, const Record &b) { return a.code < b.code; });
+	nodes->code.clear();
+	nodes->strength.clear();
+	for (size_t j = 0; j < rec.size();) {
+		double acc[COMPS] = {};
+		size_t e = j;
+		for (; e < rec.size() && rec[e].code == rec[j].code; ++e)
+			for (int c = 0; c < COMPS; ++c) acc[c] += (double)share[(size_t)rec[e].at * COMPS + c];
+		nodes->code.push_back(rec[j].code);
+		for (int c = 0; c < COMPS; ++c) nodes->strength.push_back((float)acc[c]);
+		j = e;
+	}
+}
+
+// ---- stage B: pruning (reference src/P3D.cpp:590-665) ----------------------------------
+
+// The strength above which about `wanted` of the n particles remain: repeated 1024-bin
+// histograms of [min, max], zooming into the bin where the count from the top crosses
+// `wanted` (reference src/redistribution_helper_funcs.cpp:32-91, same arithmetic).
+float strength_cut(const std::vector<float> &s, int n, int wanted) {
+	const int bins = 1024;
+	float fmin = n > 0 ? s[0] : 0.f, fmax = fmin;
+	for (int i = 0; i < n; ++i) { fmin = fmin < s[i] ? fmin : s[i]; fmax = fmax > s[i] ? fmax : s[i]; }
+	double lo = fmin, hi = fmax;
+	if (n < wanted) return (float)(hi * 1.05);
+	std::vector<float> edge(bins);
+	std::vector<int> count(bins);
+	int k = 0;
+	for (;;) {
+		const double range = (hi - lo) * 1.05;
+		for (int i = 0; i < bins; ++i) { count[i] = 0; edge[i] = (float)(lo + i * range / (float)(bins - 1)); }
+		for (int i = 0; i < n; ++i) {
+			const int b = (int)std::floor((double)(bins - 1) * (s[i] - lo) / range);
+			++count[b < 0 ? 0 : (b >= bins ? bins - 1 : b)];
+		}
+		int above = count[bins - 1];
+		for (int i = bins - 2; i >= 0; --i) {
+			hi = edge[i + 1];
+			lo = edge[i];
+			above += count[i];
+			count[i] = above;
+			if (above > wanted) { k = i + 1; break; }
+		}
+		if (lo == hi || count[k] == count[k - 1] || std::fabs((float)(wanted - count[k]) / (float)wanted) < 0.01f * 0.6) break;
+	}
+	return edge[k];
+}
+
+// Keep node i when strength[i] > cut and i < index_limit; spread the dropped vorticity
+// evenly over the kept nodes (reference src/P3D.cpp:636-665).  Pieces of the node list are
+// counted, then moved, in parallel; partial sums are combined in piece order.  Returns how
+// many are kept; `nodes` is replaced by the kept set.
+template <int COMPS>
+int drop_weak(NodeSet &nodes, const std::vector<float> &strength, int n, float cut, int index_limit) {
+	const long pieces = ((long)n + kPiece - 1) / kPiece;
+	struct Tally { long kept; double lost[COMPS]; };
+	std::vector<Tally> tally((size_t)pieces);
+	const float *w = nodes.strength.data();
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
+	for (long p = 0; p < pieces; ++p) {
+		Tally t = {};
+		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
+		for (long i = b; i < e; ++i) {
+			if (strength[(size_t)i] > cut && i < index_limit) ++t.kept;
+			else for (int c = 0; c < COMPS; ++c) t.lost[c] += (double)w[(size_t)i * COMPS + c];
+		}
+		tally[(size_t)p] = t;
+	}
+	long kept = 0;
+	double lost[COMPS] = {};
+	std::vector<long> start((size_t)pieces);
+	for (long p = 0; p < pieces; ++p) {
+		start[(size_t)p] = kept;
+		kept += tally[(size_t)p].kept;
+		for (int c = 0; c < COMPS; ++c) lost[c] += tally[(size_t)p].lost[c];
+	}
+	float each[COMPS];
+	for (int c = 0; c < COMPS; ++c) each[c] = (float)lost[c] / (float)kept;
+	NodeSet out;
+	out.code.resize((size_t)kept);
+	out.strength.resize((size_t)kept * COMPS);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
+	for (long p = 0; p < pieces; ++p) {
+		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
+		size_t at = (size_t)start[(size_t)p];
+		for (long i = b; i < e; ++i)
+			if (strength[(size_t)i] > cut && i < index_limit) {
+				out.code[at] = nodes.code[(size_t)i];
+				for (int c = 0; c < COMPS; ++c) out.strength[at * COMPS + c] = w[(size_t)i * COMPS + c] + each[c];
+				++at;
+			}
+	}
+	nodes.code.swap(out.code);
+	nodes.strength.swap(out.strength);
+	return (int)kept;
+}
+
+// |w| per node and, in FP64, their sum.
+template <int COMPS>
+double magnitudes(const std::vector<float> &w, int n, std::vector<float> &out) {
+	out.resize((size_t)n);
+	const long pieces = ((long)n + kPiece - 1) / kPiece;
+	std::vector<double> part((size_t)pieces, 0.0);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
+	for (long p = 0; p < pieces; ++p) {
+		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
+		double t = 0.0;
+		for (long i = b; i < e; ++i) {
+			float m;
+			if (COMPS == 1) m = std::fabs(w[(size_t)i]);
+			else m = std::sqrt(w[(size_t)i * 3] * w[(size_t)i * 3] + w[(size_t)i * 3 + 1] * w[(size_t)i * 3 + 1] + w[(size_t)i * 3 + 2] * w[(size_t)i * 3 + 2]);
+			out[(size_t)i] = m;
+			t += (double)m;
+		}
+		part[(size_t)p] = t;
+	}
+	double total = 0.0;
+	for (double t : part) total += t;
+	return total;
+}
+
+template <int D, class Particle>
+int prune_and_write(NodeSet &nodes, const Grid &g, Particle *out, int max_out, float negligible) {
+	constexpr int COMPS = D == 3 ? 3 : 1;
+	int n = (int)nodes.code.size();
+	if (n == 0) return 0;
+	std::vector<float> strength;
+	const double total = magnitudes<COMPS>(nodes.strength, n, strength);
+	const float cut = (float)(total / (double)n) * negligible;
+	n = drop_weak<COMPS>(nodes, strength, n, cut, n);
+	if (!out) return n;
+	if (n > max_out) {
+		magnitudes<COMPS>(nodes.strength, n, strength);
+		const float cut2 = strength_cut(strength, n, max_out);
+		// the reference also drops every node at index >= max_out, whatever its strength
+		// (src/P3D.cpp:649: `i < max_keepable` tests the input index); kept as is
+		n = drop_weak<COMPS>(nodes, strength, n, cut2, max_out);
+	}
+	const float size = D == 3 ? g.h * g.h * g.h : g.h * g.h;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > kPiece)
+	for (int i = 0; i < n; ++i) {
+		float *p = (float *)&out[i];
+		const uint64_t m = nodes.code[i];
+		if (D == 3) {
+			p[0] = node_coord((uint32_t)compact3(m), g.origin[0], g.h);
+			p[1] = node_coord((uint32_t)compact3(m >> 1), g.origin[1], g.h);
+			p[2] = node_coord((uint32_t)compact3(m >> 2), g.origin[2], g.h);
+			p[3] = nodes.strength[(size_t)i * 3];
+			p[4] = nodes.strength[(size_t)i * 3 + 1];
+			p[5] = nodes.strength[(size_t)i * 3 + 2];
+			p[6] = size;
+		} else {
+			p[0] = node_coord((uint32_t)compact2(m), g.origin[0], g.h);
+			p[1] = node_coord((uint32_t)compact2(m >> 1), g.origin[1], g.h);
+			p[2] = nodes.strength[i];
+			p[3] = size;
+		}
+	}
+	return n;
+}
+
+// CVTX_B200_TRACE=1: one stderr line per call with the wall time of each stage.
+bool trace_on() {
+	static const int on = [] { const char *e = std::getenv("CVTX_B200_TRACE"); return e && e[0] == '1' ? 1 : 0; }();
+	return on != 0;
+}
+
+template <int D, class Particle>
+int redistribute(const char *entry, const Particle **in, int n_in, Particle *out, int max_out, const cvtx_RedistFunc *rf, float h, float negligible) {
+	constexpr int ROW = D == 3 ? 7 : 4;
+	static_assert(sizeof(Particle) == sizeof(float) * ROW, "particle layout");
+	if (n_in <= 0 || !in || !rf || !(h > 0.f)) return 0;
+	NodeSet nodes;
+	Grid g;
+	const double t0 = omp_get_wtime();
+	const int kind = builtin_kind(rf);
+	const std::vector<int> devs = enabled_accelerators();
+	if (kind >= 0 && !devs.empty()) {
+		note_dispatch(1, 1);
+		const int rc = device_nodes(devs[0], D, kind, h, (const void *const *)in, n_in, &g, &nodes);
+		if (rc != CVTX_B200_OK) gpu_failure(entry, rc);
+	} else {
+		note_dispatch(0, 0);
+		std::vector<float> rows((size_t)n_in * ROW);
+		gather_rows(rows.data(), (const void *const *)in, n_in, sizeof(float) * ROW);
+		uint32_t max_index = 0;
+		const int half = kind >= 0 ? kHalfWidth[kind] : (int)roundf(rf->radius);
+		g = place_grid(D, kind, half, h, rows.data(), n_in, ROW, &max_index);
+		if (code_bits(D, max_index) < 0) {
+			std::fprintf(stderr, "cvortex: %s: grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D); aborting.\n", entry);
+			std::abort();
+		}
+		if (kind >= 0) host_nodes<D>(rows.data(), n_in, g, &nodes);
+		else host_nodes_user<D>(rows.data(), n_in, g, rf, &nodes);
+	}
+	const double t1 = omp_get_wtime();
+	const size_t n_nodes = nodes.code.size();
+	const int kept = prune_and_write<D>(nodes, g, out, max_out, negligible);
+	if (trace_on())
+		std::fprintf(stderr, "cvortex trace: %s n=%d -> %zu nodes -> %d particles; nodes %.3f ms (%s), prune+write %.3f ms\n", entry, n_in,
+		             n_nodes, kept, (t1 - t0) * 1e3, kind >= 0 && !devs.empty() ? "device" : "host", (omp_get_wtime() - t1) * 1e3);
+	return kept;
+}
+
+}  // namespace
+
+extern "C" {
+
+CVTX_API const cvtx_RedistFunc cvtx_RedistFunc_lambda0(void) { return builtin(K_LAMBDA0); }
+CVTX_API const cvtx_RedistFunc cvtx_RedistFunc_lambda1(void) { return builtin(K_LAMBDA1); }
+CVTX_API const cvtx_RedistFunc cvtx_RedistFunc_lambda2(void) { return builtin(K_LAMBDA2); }
+CVTX_API const cvtx_RedistFunc cvtx_RedistFunc_lambda3(void) { return builtin(K_LAMBDA3); }
+CVTX_API const cvtx_RedistFunc cvtx_RedistFunc_m4p(void) { return builtin(K_M4P); }
+
+CVTX_API int cvtx_P3D_redistribute_on_grid(const cvtx_P3D **input_array_start, const int n_input_particles, cvtx_P3D *output_particles,
+                                           int max_output_particles, const cvtx_RedistFunc *redistributor, float grid_density,
+                                           float negligible_vort) {
+	return redistribute<3>("cvtx_P3D_redistribute_on_grid", input_array_start, n_input_particles, output_particles,
+	                       max_output_particles, redistributor, grid_density, negligible_vort);
+}
+
+CVTX_API int cvtx_P2D_redistribute_on_grid(const cvtx_P2D **input_array_start, const int n_input_particles, cvtx_P2D *output_particles,
+                                           int max_output_particles, const cvtx_RedistFunc *redistributor, float grid_density,
+                                           float negligible_vort) {
+	return redistribute<2>("cvtx_P2D_redistribute_on_grid", input_array_start, n_input_particles, output_particles,
+	                       max_output_particles, redistributor, grid_density, negligible_vort);
+}
+
+// alpha_new = (1 - f dt) alpha + f dt |alpha| omega(x)/|omega(x)|, omega = the vorticity field
+// the particles themselves induce at x (reference src/P3D.cpp:667-707); a particle sitting in
+// zero field loses its vorticity, as there.
+CVTX_API void cvtx_P3D_pedrizzetti_relaxation(cvtx_P3D **input_array_start, const int n_input_particles, float fdt,
+                                              const cvtx_VortFunc *kernel, float regularisation_radius) {
+	const int n = n_input_particles;
+	if (n <= 0) return;
+	std::vector<bsv_V3f> where((size_t)n), field((size_t)n);
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; ++i) where[i] = input_array_start[i]->coord;
+	cvtx_P3D_M2M_vort((const cvtx_P3D **)input_array_start, n, where.data(), n, field.data(), kernel, regularisation_radius);
+	const float keep = 1.f - fdt;
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; ++i) {
+		const bsv_V3f a = input_array_start[i]->vorticity, w = field[i];
+		const float wn = bsv_V3f_abs(w);
+		const float pull = bsv_V3f_abs(a) / wn * fdt;
+		bsv_V3f r = bsv_V3f_plus(bsv_V3f_mult(a, keep), bsv_V3f_mult(w, pull));
+		if (!(wn != 0.f)) r = bsv_V3f_zero();
+		input_array_start[i]->vorticity = r;
+	}
+}
+
+}  // extern "C"

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "../../include/cvtx_b200.h"
+#include "host_hooks.h"
 
 namespace cvtx {
 
@@ -32,6 +33,8 @@ struct Device {
 	// raw rows of the staged (host-array) path
 	cudaStream_t stream = nullptr;
 	Buffer d_src, d_tgt, d_out;
+	// work arrays of the grid redistribution (remesh_device.cu)
+	Buffer remesh[12];
 };
 
 // Library-wide pinned (portable) staging: sources, targets and results of ONE
@@ -44,6 +47,7 @@ struct HostStage {
 HostStage &host_stage();
 
 int fail(int code, const std::string &msg);
+void count_launches(unsigned long long n);     // feeds cvtx_b200_kernel_launches()
 Device *get_device(int device);
 // Make `device` current, create its stream / events on first use, hand back its private stream.
 int device_stream(int device, cudaStream_t *stream);

@@ -16,8 +16,11 @@
  *   [host]  small scalar host code (single pairs, one-to-many, many-to-one,
  *           and the all-pairs ops when the caller disabled every accelerator
  *           or passed a user-defined cvtx_VortFunc).
- *   [stub]  outside the all-pairs hot path this build covers (SURVEY.md
- *           section 8): the symbol links, calling it reports that and aborts.
+ *   [B200/remesh]  redistribution onto a grid: the node build (spread, sort by
+ *           node, per-node sums) runs on the first enabled accelerator when the
+ *           cvtx_RedistFunc is one of the five built-ins, on the host otherwise
+ *           (same bits either way); the pruning of weak nodes runs on the host.
+ *           Relaxation is one cvtx_P3D_M2M_vort call plus a per-particle blend.
  *
  * Struct sizes relied on across the ABI (static_asserted in the library):
  *   cvtx_P3D 28, cvtx_F3D 28, cvtx_P2D 16, cvtx_VortFunc 80 (LP64),
@@ -101,7 +104,7 @@ CVTX_EXPORT const cvtx_VortFunc cvtx_VortFunc_winckelmans(void);
 CVTX_EXPORT const cvtx_VortFunc cvtx_VortFunc_planetary(void);
 CVTX_EXPORT const cvtx_VortFunc cvtx_VortFunc_gaussian(void);
 
-/* ---------------------------------------- redistribution kernels [stub] */
+/* ---------------------------------------- redistribution kernels [host] */
 CVTX_EXPORT const cvtx_RedistFunc cvtx_RedistFunc_lambda0(void);
 CVTX_EXPORT const cvtx_RedistFunc cvtx_RedistFunc_lambda1(void);
 CVTX_EXPORT const cvtx_RedistFunc cvtx_RedistFunc_lambda2(void);
@@ -190,7 +193,9 @@ CVTX_EXPORT bsv_V3f cvtx_P3D_M2S_vort(
 	const bsv_V3f mes_point,
 	const cvtx_VortFunc *kernel, float regularisation_radius);
 
-/* ---- redistribution / relaxation [stub] ---- */
+/* ---- redistribution / relaxation [B200/remesh] ----
+ * output_particles == NULL asks for the count only.  When more than
+ * max_output_particles survive negligible_vort, the strongest are kept. */
 CVTX_EXPORT int cvtx_P3D_redistribute_on_grid(
 	const cvtx_P3D **input_array_start, const int n_input_particles,
 	cvtx_P3D *output_particles, int max_output_particles,
@@ -269,7 +274,7 @@ CVTX_EXPORT float cvtx_P2D_M2S_visc_dvort(
 	const cvtx_VortFunc *kernel, float regularisation_radius,
 	float kinematic_visc);
 
-/* ---- redistribution; returns the number of particles created [stub] ---- */
+/* ---- redistribution; returns the number of particles created [B200/remesh] ---- */
 CVTX_EXPORT int cvtx_P2D_redistribute_on_grid(
 	const cvtx_P2D **input_array_start, const int num_particles,
 	cvtx_P2D *output_particles, int num_output_particles,

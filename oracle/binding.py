@@ -27,6 +27,7 @@ PORT_SO = os.path.join(HERE, "_build", "libcvtx_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libcvortex_ref.so")
 
 REG_IDS = {"singular": 0, "winckelmans": 1, "planetary": 2, "gaussian": 3}
+REDIST_IDS = {"lambda0": 0, "lambda1": 1, "lambda2": 2, "lambda3": 3, "m4p": 4}
 
 
 def build(ref: bool = True) -> None:
@@ -80,6 +81,13 @@ class Oracle:
                 f.restype, f.argtypes = None, [_fp, C.c_int, _fp, C.c_int, outp]
             f = getattr(lib, f"cvtx_oracle_F3D_inf_mtrx_{prec}")
             f.restype, f.argtypes = None, [_fp, C.c_int, _fp, _fp, C.c_int, outp]
+        lib.cvtx_oracle_redist.restype, lib.cvtx_oracle_redist.argtypes = C.c_float, [C.c_int, C.c_float]
+        lib.cvtx_oracle_redist_radius.restype, lib.cvtx_oracle_redist_radius.argtypes = C.c_float, [C.c_int]
+        for name in ("cvtx_oracle_P3D_redistribute", "cvtx_oracle_P2D_redistribute"):
+            f = getattr(lib, name)
+            f.restype, f.argtypes = C.c_int, [_fp, C.c_int, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        lib.cvtx_oracle_P3D_pedrizzetti.restype = None
+        lib.cvtx_oracle_P3D_pedrizzetti.argtypes = [_fp, C.c_int, C.c_float, C.c_int, C.c_float, _fp]
         lib.cvtx_oracle_P3D_S2S_vel.argtypes = [_fp, _fp, C.c_int, C.c_float, _fp]
         lib.cvtx_oracle_P3D_S2S_dvort.argtypes = [_fp, _fp, C.c_int, C.c_float, _fp]
         lib.cvtx_oracle_P3D_S2S_visc_dvort.argtypes = [_fp, _fp, C.c_int, C.c_float, C.c_float, _fp]
@@ -116,6 +124,35 @@ class Oracle:
         fil, pts, dirs = _f32(fil, 7), _f32(pts, 3), _f32(dirs, 3)
         out = np.zeros((pts.shape[0], fil.shape[0]), dtype=np.float64 if f64 else np.float32)
         getattr(self.lib, "cvtx_oracle_F3D_inf_mtrx_" + ("f64" if f64 else "f32"))(fil, fil.shape[0], pts, dirs, pts.shape[0], out)
+        return out
+
+    # -- redistribution / relaxation -------------------------------------
+    def redist(self, which: str, U: float) -> float:
+        return float(self.lib.cvtx_oracle_redist(REDIST_IDS[which], U))
+
+    def redist_radius(self, which: str) -> float:
+        return float(self.lib.cvtx_oracle_redist_radius(REDIST_IDS[which]))
+
+    def redistribute(self, particles, which: str, grid_density: float, negligible_vort: float = 0.0,
+                     max_output=None, count_only: bool = False):
+        """Particles (n,7) or (n,4) -> the particles the reference would create on the grid."""
+        particles = np.ascontiguousarray(particles, dtype=np.float32)
+        cols = particles.shape[1]
+        fn = self.lib.cvtx_oracle_P3D_redistribute if cols == 7 else self.lib.cvtx_oracle_P2D_redistribute
+        n = particles.shape[0]
+        dummy = np.zeros((1, cols), dtype=np.float32)
+        if count_only:
+            return fn(particles, n, dummy, 0, 0, REDIST_IDS[which], grid_density, negligible_vort)
+        if max_output is None:
+            max_output = fn(particles, n, dummy, 0, 0, REDIST_IDS[which], grid_density, negligible_vort)
+        out = np.full((max(max_output, 1), cols), np.nan, dtype=np.float32)
+        k = fn(particles, n, out, max_output, 1, REDIST_IDS[which], grid_density, negligible_vort)
+        return out[:k]
+
+    def pedrizzetti(self, particles, fdt: float, reg: str, sigma: float) -> np.ndarray:
+        particles = _f32(particles, 7)
+        out = np.empty_like(particles)
+        self.lib.cvtx_oracle_P3D_pedrizzetti(particles, particles.shape[0], fdt, REG_IDS[reg], sigma, out)
         return out
 
     # -- M2M -------------------------------------------------------------

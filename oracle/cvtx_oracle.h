@@ -90,6 +90,25 @@ void cvtx_oracle_P2D_M2M_visc_dvort_f64(const float *src4, int n, const float *t
 void cvtx_oracle_F3D_M2M_vel_f64(const float *fil7, int n, const float *pts3, int m, double *out3);
 void cvtx_oracle_F3D_M2M_dvort_f64(const float *fil7, int n, const float *tgt7, int m, double *out3);
 
+/* ---- redistribution onto a grid and relaxation (cvtx_oracle_remesh.c) ----
+ * The steps either side of the all-pairs sums in a time step.  Sequential, reference
+ * arithmetic; pinned against the reference's own implementation (see that file). */
+enum {
+	CVTX_ORACLE_LAMBDA0 = 0,
+	CVTX_ORACLE_LAMBDA1 = 1,
+	CVTX_ORACLE_LAMBDA2 = 2,
+	CVTX_ORACLE_LAMBDA3 = 3,
+	CVTX_ORACLE_M4P = 4
+};
+float cvtx_oracle_redist(int which, float U);          /* reference src/RedistFunc.cpp:36-96 */
+float cvtx_oracle_redist_radius(int which);
+/* Returns the number of particles created; writes them to out (capacity max_out rows) when
+ * have_out is non-zero (reference passes output_particles == NULL to ask for the count). */
+int cvtx_oracle_P3D_redistribute(const float *src7, int n, float *out7, int max_out, int have_out, int which, float h, float negligible);
+int cvtx_oracle_P2D_redistribute(const float *src4, int n, float *out4, int max_out, int have_out, int which, float h, float negligible);
+/* out7 = src7 with relaxed vorticity (reference cvtx_P3D_pedrizzetti_relaxation). */
+void cvtx_oracle_P3D_pedrizzetti(const float *src7, int n, float fdt, int reg, float sigma, float *out7);
+
 /* Number of OpenMP threads the M2M loops will use. */
 int cvtx_oracle_num_threads(void);
 

@@ -1,0 +1,112 @@
+"""GPU tests of redistribution onto a grid and relaxation, through the public cvtx_* ABI:
+against the reference's own numbers (golden fixtures, and live when oracle/_ref travelled),
+against the oracle port, and -- bit for bit -- against the library's own host stage."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from test_remesh import tol_for
+from util import REDISTS, assert_same_remesh, remesh_cases, remesh_particles
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_remesh.npz")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def fn_of(lib, dim):
+    return lib.P3D_redistribute_on_grid if dim == 3 else lib.P2D_redistribute_on_grid
+
+
+def on_host(product, call):
+    """Run `call` with every accelerator switched off (the library's host stage)."""
+    enabled = [k for k in range(product.num_accelerators()) if product.accelerator_enabled(k)]
+    for k in enabled:
+        product.accelerator_disable(k)
+    try:
+        return call()
+    finally:
+        for k in enabled:
+            product.accelerator_enable(k)
+
+
+@pytest.mark.parametrize("case", remesh_cases(), ids=lambda c: f"{c[0]}d-{c[1]}-negl{c[3]}-cap{c[4]}")
+def test_gpu_matches_reference_golden(gpu, golden, case):
+    product, dev = gpu
+    dim, name, h, negl, cap = case
+    key = f"remesh|{dim}|{name}|{negl}|{cap}"
+    p, want = golden[key + "|in"], golden[key + "|out"]
+    before = dev.kernel_launches()
+    got = fn_of(product, dim)(p, name, h, negl, max_output=cap)
+    assert dev.last_dispatch() == 1 and dev.kernel_launches() - before >= 3, "the CUDA stage must have run"
+    assert_same_remesh(got, want, tol=tol_for(cap), what=key)
+    assert abs(fn_of(product, dim)(p, name, h, negl, count_only=True) - int(golden[key + "|count"][0])) <= 2
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("name", REDISTS)
+def test_gpu_and_host_stage_give_the_same_bits(gpu, dim, name):
+    """Same shares, same stable order, same FP64 node sums: the two stages are interchangeable."""
+    product, dev = gpu
+    rng = np.random.default_rng(zlib.crc32(f"bits{dim}{name}".encode()))
+    n = 30011
+    p = remesh_particles(rng, n, dim)
+    h = float(np.cbrt(2.0 / n)) if dim == 3 else float(np.sqrt(2.0 / n))
+    for negl, cap in ((0.0, None), (1e-4, None), (0.01, n // 3)):
+        got = fn_of(product, dim)(p, name, h, negl, max_output=cap)
+        assert dev.last_dispatch() == 1
+        want = on_host(product, lambda: fn_of(product, dim)(p, name, h, negl, max_output=cap))
+        assert dev.last_dispatch() == 0
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dim, name, negl, cap)
+
+
+def test_gpu_matches_oracle_and_live_reference(gpu, oracle, ref):
+    product, _ = gpu
+    for dim, h in ((3, 0.05), (2, 0.02)):
+        for name in REDISTS:
+            rng = np.random.default_rng(zlib.crc32(f"gpu-live{dim}{name}".encode()))
+            p = remesh_particles(rng, 4000, dim)
+            for negl, cap in ((0.0, None), (0.05, None), (0.01, 500)):
+                got = fn_of(product, dim)(p, name, h, negl, max_output=cap)
+                assert_same_remesh(got, oracle.redistribute(p, name, h, negl, max_output=cap), tol=tol_for(cap),
+                                   what=f"oracle {dim} {name} {negl} {cap}")
+                if ref is not None:
+                    assert_same_remesh(got, fn_of(ref, dim)(p, name, h, negl, max_output=cap), tol=tol_for(cap),
+                                       what=f"reference {dim} {name} {negl} {cap}")
+
+
+@pytest.mark.parametrize("dim,n", [(3, 1_000_000), (2, 1_000_000)])
+def test_benchmark_size_conserves_vorticity_and_is_deterministic(gpu, dim, n):
+    """The reference benchmark's largest case (bench/benchredistribution.c:49-61: a million
+    particles in the unit box, about two per cell, M4', negligible_vort 1e-4, room for 4n)."""
+    product, _ = gpu
+    p = remesh_particles(np.random.default_rng(77), n, dim, signed=False)
+    h = float(np.cbrt(2.0 / n))
+    out = fn_of(product, dim)(p, "m4p", h, 1e-4, max_output=4 * n)
+    w = slice(3, 6) if dim == 3 else slice(2, 3)
+    assert 0 < len(out) <= 4 * n
+    assert np.allclose(out[:, w].astype(np.float64).sum(0), p[:, w].astype(np.float64).sum(0), rtol=1e-5)
+    lo, hi = p[:, :dim].min(0) - 2.5 * h, p[:, :dim].max(0) + 2.5 * h
+    assert np.all(out[:, :dim] >= lo) and np.all(out[:, :dim] <= hi)
+    again = fn_of(product, dim)(p, "m4p", h, 1e-4, max_output=4 * n)
+    assert np.array_equal(out.view(np.uint32), again.view(np.uint32))
+
+
+@pytest.mark.parametrize("reg", ["winckelmans", "gaussian", "planetary"])
+def test_relaxation_on_the_gpu(gpu, golden, oracle, reg):
+    product, dev = gpu
+    p, want = golden[f"relax|{reg}|in"], golden[f"relax|{reg}|out"]
+    sigma, fdt = (float(v) for v in golden[f"relax|{reg}|par"])
+    got = product.P3D_pedrizzetti_relaxation(p, fdt, reg, sigma)
+    assert dev.last_dispatch() == 1, "the vorticity field must have come from the CUDA kernel"
+    assert np.array_equal(got[:, :3], p[:, :3]) and np.array_equal(got[:, 6], p[:, 6])
+    assert np.abs(got[:, 3:6] - want[:, 3:6]).max() <= 1e-5 * np.abs(want[:, 3:6]).max()
+    big = remesh_particles(np.random.default_rng(4), 20000, 3)
+    got = product.P3D_pedrizzetti_relaxation(big, 0.2, reg, 0.05)
+    want = oracle.pedrizzetti(big, 0.2, reg, 0.05)
+    assert np.abs(got[:, 3:6] - want[:, 3:6]).max() <= 1e-5 * np.abs(want[:, 3:6]).max()
