@@ -71,7 +71,8 @@ int host_threads() {
 }  // namespace
 
 // ---- grid placement (shared with the device stage) -----------------------------------
-Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const float *rows, long n, int row_floats, uint32_t *max_index) {
+Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const void *const *particles, float *rows, long n, int row_floats,
+                              uint32_t *max_index) {
 	Grid g;
 	g.h = h;
 	g.rh = 1.f / h;
@@ -87,6 +88,8 @@ Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const float 
 	for (long p = 0; p < pieces; ++p) {
 		Piece q;
 		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
+		if (particles)   // gather this piece through the caller's pointer array first
+			for (long i = b; i < e; ++i) std::memcpy(rows + i * row_floats, particles[i], sizeof(float) * (size_t)row_floats);
 		for (int a = 0; a < 3; ++a) { q.lo[a] = q.hi[a] = a < dim ? rows[b * row_floats + a] : 0.f; q.sum[a] = 0.0; }
 		for (long i = b; i < e; ++i)
 			for (int a = 0; a < dim; ++a) {
@@ -247,13 +250,25 @@ float strength_cut(const std::vector<float> &s, int n, int wanted) {
 	return edge[k];
 }
 
-// Keep node i when strength[i] > cut and i < index_limit; spread the dropped vorticity
-// evenly over the kept nodes (reference src/P3D.cpp:636-665).  Pieces of the node list are
-// counted, then moved, in parallel; partial sums are combined in piece order.  Returns how
-// many are kept; `nodes` is replaced by the kept set.
+// Which nodes survive a cut: node i stays when strength[i] > cut and i < index_limit; the
+// vorticity of the others is handed back evenly to the survivors (reference
+// src/P3D.cpp:636-665).  The node list is walked in fixed pieces, in parallel; partial sums
+// are combined in piece order, so the result does not depend on the thread count.
 template <int COMPS>
-int drop_weak(NodeSet &nodes, const std::vector<float> &strength, int n, float cut, int index_limit) {
-	const long pieces = ((long)n + kPiece - 1) / kPiece;
+struct Cut {
+	float cut;
+	long index_limit, kept;
+	float each[COMPS];            // what every survivor receives
+	std::vector<long> start;      // output position of each piece's first survivor
+	bool keeps(float strength, long i) const { return strength > cut && i < index_limit; }
+};
+
+template <int COMPS>
+Cut<COMPS> plan_cut(const NodeSet &nodes, const std::vector<float> &strength, long n, float cut, long index_limit) {
+	Cut<COMPS> c;
+	c.cut = cut;
+	c.index_limit = index_limit;
+	const long pieces = (n + kPiece - 1) / kPiece;
 	struct Tally { long kept; double lost[COMPS]; };
 	std::vector<Tally> tally((size_t)pieces);
 	const float *w = nodes.strength.data();
@@ -262,38 +277,39 @@ int drop_weak(NodeSet &nodes, const std::vector<float> &strength, int n, float c
 		Tally t = {};
 		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
 		for (long i = b; i < e; ++i) {
-			if (strength[(size_t)i] > cut && i < index_limit) ++t.kept;
-			else for (int c = 0; c < COMPS; ++c) t.lost[c] += (double)w[(size_t)i * COMPS + c];
+			if (c.keeps(strength[(size_t)i], i)) ++t.kept;
+			else for (int q = 0; q < COMPS; ++q) t.lost[q] += (double)w[(size_t)i * COMPS + q];
 		}
 		tally[(size_t)p] = t;
 	}
-	long kept = 0;
+	c.kept = 0;
 	double lost[COMPS] = {};
-	std::vector<long> start((size_t)pieces);
+	c.start.resize((size_t)pieces);
 	for (long p = 0; p < pieces; ++p) {
-		start[(size_t)p] = kept;
-		kept += tally[(size_t)p].kept;
-		for (int c = 0; c < COMPS; ++c) lost[c] += tally[(size_t)p].lost[c];
+		c.start[(size_t)p] = c.kept;
+		c.kept += tally[(size_t)p].kept;
+		for (int q = 0; q < COMPS; ++q) lost[q] += tally[(size_t)p].lost[q];
 	}
-	float each[COMPS];
-	for (int c = 0; c < COMPS; ++c) each[c] = (float)lost[c] / (float)kept;
-	NodeSet out;
-	out.code.resize((size_t)kept);
-	out.strength.resize((size_t)kept * COMPS);
+	for (int q = 0; q < COMPS; ++q) c.each[q] = (float)lost[q] / (float)c.kept;
+	return c;
+}
+
+// Hand every survivor of `c`, in order, to sink(position, code, adjusted strength).
+template <int COMPS, class Sink>
+void apply_cut(const Cut<COMPS> &c, const NodeSet &nodes, const std::vector<float> &strength, long n, Sink &&sink) {
+	const long pieces = (n + kPiece - 1) / kPiece;
+	const float *w = nodes.strength.data();
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
 	for (long p = 0; p < pieces; ++p) {
 		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
-		size_t at = (size_t)start[(size_t)p];
+		long at = c.start[(size_t)p];
 		for (long i = b; i < e; ++i)
-			if (strength[(size_t)i] > cut && i < index_limit) {
-				out.code[at] = nodes.code[(size_t)i];
-				for (int c = 0; c < COMPS; ++c) out.strength[at * COMPS + c] = w[(size_t)i * COMPS + c] + each[c];
-				++at;
+			if (c.keeps(strength[(size_t)i], i)) {
+				float adjusted[COMPS];
+				for (int q = 0; q < COMPS; ++q) adjusted[q] = w[(size_t)i * COMPS + q] + c.each[q];
+				sink(at++, nodes.code[(size_t)i], adjusted);
 			}
 	}
-	nodes.code.swap(out.code);
-	nodes.strength.swap(out.strength);
-	return (int)kept;
 }
 
 // |w| per node and, in FP64, their sum.
@@ -323,41 +339,48 @@ double magnitudes(const std::vector<float> &w, int n, std::vector<float> &out) {
 template <int D, class Particle>
 int prune_and_write(NodeSet &nodes, const Grid &g, Particle *out, int max_out, float negligible) {
 	constexpr int COMPS = D == 3 ? 3 : 1;
-	int n = (int)nodes.code.size();
+	long n = (long)nodes.code.size();
 	if (n == 0) return 0;
 	std::vector<float> strength;
-	const double total = magnitudes<COMPS>(nodes.strength, n, strength);
-	const float cut = (float)(total / (double)n) * negligible;
-	n = drop_weak<COMPS>(nodes, strength, n, cut, n);
-	if (!out) return n;
-	if (n > max_out) {
-		magnitudes<COMPS>(nodes.strength, n, strength);
-		const float cut2 = strength_cut(strength, n, max_out);
-		// the reference also drops every node at index >= max_out, whatever its strength
-		// (src/P3D.cpp:649: `i < max_keepable` tests the input index); kept as is
-		n = drop_weak<COMPS>(nodes, strength, n, cut2, max_out);
+	const double total = magnitudes<COMPS>(nodes.strength, (int)n, strength);
+	Cut<COMPS> c = plan_cut<COMPS>(nodes, strength, n, (float)(total / (double)n) * negligible, n);
+	if (!out) return (int)c.kept;
+	if (c.kept > max_out) {
+		// the caller's array is too small: materialise the survivors, find the strength that
+		// fits, cut again.  The reference also drops every node at index >= max_out whatever
+		// its strength (src/P3D.cpp:649: `i < max_keepable` tests the input index); kept as is.
+		NodeSet kept;
+		kept.code.resize((size_t)c.kept);
+		kept.strength.resize((size_t)c.kept * COMPS);
+		apply_cut<COMPS>(c, nodes, strength, n, [&](long at, uint64_t code, const float *w) {
+			kept.code[(size_t)at] = code;
+			for (int q = 0; q < COMPS; ++q) kept.strength[(size_t)at * COMPS + q] = w[q];
+		});
+		nodes.code.swap(kept.code);
+		nodes.strength.swap(kept.strength);
+		n = c.kept;
+		magnitudes<COMPS>(nodes.strength, (int)n, strength);
+		c = plan_cut<COMPS>(nodes, strength, n, strength_cut(strength, (int)n, max_out), max_out);
 	}
 	const float size = D == 3 ? g.h * g.h * g.h : g.h * g.h;
-#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > kPiece)
-	for (int i = 0; i < n; ++i) {
-		float *p = (float *)&out[i];
-		const uint64_t m = nodes.code[i];
+	apply_cut<COMPS>(c, nodes, strength, n, [&](long at, uint64_t m, const float *w) {
+		float *p = (float *)&out[at];
 		if (D == 3) {
 			p[0] = node_coord((uint32_t)compact3(m), g.origin[0], g.h);
 			p[1] = node_coord((uint32_t)compact3(m >> 1), g.origin[1], g.h);
 			p[2] = node_coord((uint32_t)compact3(m >> 2), g.origin[2], g.h);
-			p[3] = nodes.strength[(size_t)i * 3];
-			p[4] = nodes.strength[(size_t)i * 3 + 1];
-			p[5] = nodes.strength[(size_t)i * 3 + 2];
+			p[3] = w[0];
+			p[4] = w[COMPS > 1 ? 1 : 0];
+			p[5] = w[COMPS > 2 ? 2 : 0];
 			p[6] = size;
 		} else {
 			p[0] = node_coord((uint32_t)compact2(m), g.origin[0], g.h);
 			p[1] = node_coord((uint32_t)compact2(m >> 1), g.origin[1], g.h);
-			p[2] = nodes.strength[i];
+			p[2] = w[0];
 			p[3] = size;
 		}
-	}
-	return n;
+	});
+	return (int)c.kept;
 }
 
 // CVTX_B200_TRACE=1: one stderr line per call with the wall time of each stage.
@@ -383,10 +406,9 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 	} else {
 		note_dispatch(0, 0);
 		std::vector<float> rows((size_t)n_in * ROW);
-		gather_rows(rows.data(), (const void *const *)in, n_in, sizeof(float) * ROW);
 		uint32_t max_index = 0;
 		const int half = kind >= 0 ? kHalfWidth[kind] : (int)roundf(rf->radius);
-		g = place_grid(D, kind, half, h, rows.data(), n_in, ROW, &max_index);
+		g = place_grid(D, kind, half, h, (const void *const *)in, rows.data(), n_in, ROW, &max_index);
 		if (code_bits(D, max_index) < 0) {
 			std::fprintf(stderr, "cvortex: %s: grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D); aborting.\n", entry);
 			std::abort();

@@ -19,10 +19,12 @@ struct NodeSet {
 // Where the grid sits for a given particle set (reference src/P3D.cpp:538-550,
 // src/P2D.cpp:312-323): a node coincides with the mean position, and the origin is
 // pushed at least `half` + 5 cells below the lowest particle.  `rows` are the gathered
-// particle structs (row_floats floats each, coordinates first); `kind` is -1 and `half` the
+// particle structs (row_floats floats each, coordinates first) -- gathered here, in the same
+// pass, when `particles` (the caller's array of pointers) is not null; `kind` is -1 and `half` the
 // caller's (int)roundf(radius) for a user-defined interpolant.  max_index receives the
 // largest node index any stencil can touch.
-Grid place_grid(int dim, int kind, int half, float h, const float *rows, long n, int row_floats, uint32_t *max_index);
+Grid place_grid(int dim, int kind, int half, float h, const void *const *particles, float *rows, long n, int row_floats,
+                uint32_t *max_index);
 
 // Bits of Morton code needed for indices <= max_index; -1 when the grid is larger than
 // the codes can hold (2^21 nodes per axis in 3-D, 2^31 in 2-D).

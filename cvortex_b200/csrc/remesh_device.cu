@@ -4,22 +4,24 @@
 // cvtx_P2D_redistribute_on_grid (src/P3D.cpp:552-589, src/P2D.cpp:325-362): there, every
 // thread inserts its particles' (2R+1)^D shares into a private oct/quadtree one key at a
 // time and the trees are merged serially (src/GridParticleOcttree.cpp:76-135,216-280).
-// Here the same shares are produced by one thread per particle, sorted by the Morton code
-// of their node and summed per node:
+// Here the same shares are produced per particle, sorted by the Morton code of their node
+// and summed per node:
 //
 //   spread_count   particle -> number of non-zero shares            (28 B read / particle)
 //   [scan]         offsets of each particle's run of shares         (CUB)
 //   spread_emit    particle -> (Morton code, share) records, one warp per particle,
-//                  coalesced                                        (8 + 4 + 4 D' B / share)
+//                  coalesced                                   (K + 4 + 4 COMPS B / share)
 //   [radix sort]   (code, record index) pairs, only the code bits the grid uses (CUB)
 //   [run lengths]  distinct codes = nodes, records per node         (CUB)
 //   [scan]         first record of each node                        (CUB)
 //   node_sums      node -> FP64 sum of its shares in record order, rounded to FP32
 //
-// The sort is stable and node_sums walks a node's records in order, so the result does
-// not depend on scheduling: the same input gives the same bits on every run, and the
-// same bits as the host stage of remesh.cpp.  The stage is HBM-bound; the bytes above
-// are its algorithmic traffic.
+// K, the width of a code, is 4 bytes when the grid fits (2^10 nodes per axis in 3-D, 2^16
+// in 2-D -- a million particles at two per cell need 2^7), else 8.  The sort is stable and
+// node_sums walks a node's records in order, so the result does not depend on scheduling:
+// the same input gives the same bits on every run, and the same bits as the host stage of
+// remesh.cpp.  The stage is HBM-bound; the bytes above are its algorithmic traffic
+// (DESIGN.md section 9).
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -53,35 +55,41 @@ __global__ void __launch_bounds__(kBlock) spread_count(const float *__restrict__
 
 // One warp per particle: lane l of round r owns stencil entry 32 r + l (the reference's
 // order, x offset outermost), so a particle's records leave the warp as contiguous,
-// coalesced runs; a ballot ranks the non-zero shares.  The D (2R+1) per-axis weights are
-// computed once, by the first lanes, and shuffled to the entries that use them.
-template <int D>
+// coalesced runs; a ballot ranks the non-zero shares.  The D (2R+1) per-axis weights and
+// per-axis Morton pieces are computed once, by the first lanes, and shuffled to the
+// entries that use them.  R (the stencil half-width) is a template parameter so that the
+// entry -> (ix, iy, iz) split is constant division.
+template <int D, int R, class K>
 __global__ void __launch_bounds__(kBlock) spread_emit(const float *__restrict__ rows, long n, Grid g, const uint32_t *__restrict__ offset,
-                                                      uint64_t *__restrict__ code, uint32_t *__restrict__ record, float *__restrict__ share) {
-	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
+                                                      K *__restrict__ code, uint32_t *__restrict__ record, float *__restrict__ share) {
+	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS, S = 2 * R + 1, ENTRIES = D == 3 ? S * S * S : S * S;
 	const long i = ((long)blockIdx.x * kBlock + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= n) return;
 	float row[ROW];
 	for (int c = 0; c < ROW; ++c) row[c] = rows[i * ROW + c];
-	const int R = g.half, S = 2 * R + 1, entries = D == 3 ? S * S * S : S * S;
-	uint32_t k0[D];
-	for (int a = 0; a < D; ++a) k0[a] = D == 3 ? node_index_3d(row[a], g.origin[a], g.rh) : node_index_2d(row[a], g.origin[a], g.rh);
 	float w_lane = 0.f;
+	K m_lane = 0;
 	if (lane < D * S) {
 		const int a = lane / S, o = lane - a * S;
-		w_lane = weight(g.kind, cell_distance(row[a], k0[a] + (uint32_t)(o - R), g, a));
+		const float x = a == 0 ? row[0] : (a == 1 ? row[1] : row[D - 1]);
+		const uint32_t k = (D == 3 ? node_index_3d(x, g.origin[a], g.rh) : node_index_2d(x, g.origin[a], g.rh)) + (uint32_t)(o - R);
+		w_lane = weight(g.kind, cell_distance(x, k, g, a));
+		m_lane = (K)((D == 3 ? spread3(k) : spread2(k)) << a);
 	}
 	uint32_t at = offset[i];
-	for (int base = 0; base < entries; base += 32) {
+#pragma unroll
+	for (int base = 0; base < ENTRIES; base += 32) {
 		const int e = base + lane;
-		const bool valid = e < entries;
+		const bool valid = e < ENTRIES;
 		const int ec = valid ? e : 0;
-		int ix, iy, iz = 0;
-		if (D == 3) { ix = ec / (S * S); iy = (ec / S) % S; iz = ec % S; } else { ix = ec / S; iy = ec % S; }
-		const float wx = __shfl_sync(0xffffffffu, w_lane, ix), wy = __shfl_sync(0xffffffffu, w_lane, S + iy);
-		float f = rm_mul(wx, wy);
-		if (D == 3) f = rm_mul(f, __shfl_sync(0xffffffffu, w_lane, 2 * S + iz));
+		const int ix = D == 3 ? ec / (S * S) : ec / S, iy = D == 3 ? (ec / S) % S : ec % S, iz = D == 3 ? ec % S : 0;
+		float f = rm_mul(__shfl_sync(0xffffffffu, w_lane, ix), __shfl_sync(0xffffffffu, w_lane, S + iy));
+		K m = __shfl_sync(0xffffffffu, m_lane, ix) | __shfl_sync(0xffffffffu, m_lane, S + iy);
+		if (D == 3) {
+			f = rm_mul(f, __shfl_sync(0xffffffffu, w_lane, 2 * S + iz));
+			m |= __shfl_sync(0xffffffffu, m_lane, 2 * S + iz);
+		}
 		float s[COMPS];
 		bool nz = false;
 		for (int c = 0; c < COMPS; ++c) { s[c] = rm_mul(row[D + c], f); nz = nz || s[c] != 0.f; }
@@ -89,8 +97,7 @@ __global__ void __launch_bounds__(kBlock) spread_emit(const float *__restrict__ 
 		const uint32_t votes = __ballot_sync(0xffffffffu, nz);
 		if (nz) {
 			const uint32_t pos = at + __popc(votes & ((1u << lane) - 1u));
-			code[pos] = D == 3 ? morton3(k0[0] + (uint32_t)(ix - R), k0[1] + (uint32_t)(iy - R), k0[D - 1] + (uint32_t)(iz - R))
-			                   : morton2(k0[0] + (uint32_t)(ix - R), k0[1] + (uint32_t)(iy - R));
+			code[pos] = m;
 			record[pos] = pos;
 			for (int c = 0; c < COMPS; ++c) share[(size_t)pos * COMPS + c] = s[c];
 		}
@@ -116,7 +123,19 @@ __global__ void __launch_bounds__(kBlock) node_sums(const uint32_t *__restrict__
 
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-void copy_bytes(void *dst, const void *src, size_t bytes) {
+// Pinned staging -> the caller's vectors, in parallel pieces; codes are widened to 64
+// bits on the way when the device used 32.
+template <class K>
+void fetch_codes(uint64_t *dst, const K *src, size_t n) {
+	const size_t piece = 1 << 18;
+	const long pieces = (long)((n + piece - 1) / piece);
+#pragma omp parallel for schedule(static) num_threads(4) if (pieces > 4)
+	for (long p = 0; p < pieces; ++p) {
+		const size_t lo = (size_t)p * piece, hi = lo + piece < n ? lo + piece : n;
+		for (size_t i = lo; i < hi; ++i) dst[i] = (uint64_t)src[i];
+	}
+}
+void fetch_bytes(void *dst, const void *src, size_t bytes) {
 	const size_t piece = 1 << 20;
 	const long pieces = (long)((bytes + piece - 1) / piece);
 #pragma omp parallel for schedule(static) num_threads(4) if (pieces > 4)
@@ -126,7 +145,7 @@ void copy_bytes(void *dst, const void *src, size_t bytes) {
 	}
 }
 
-template <int D>
+template <int D, class K>
 int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &g, int bits, NodeSet *nodes) {
 	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
 	Buffer *b = d->remesh;
@@ -152,26 +171,27 @@ int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &
 	if (total == 0) return CVTX_B200_OK;
 	if (total > 0x7fffffffu) return fail(CVTX_B200_ERR_ARGUMENT, "redistribution creates more than 2^31 particle-node shares");
 
-	CUDA_TRY(b[CODE_A].reserve(sizeof(uint64_t) * (size_t)total));
-	CUDA_TRY(b[CODE_B].reserve(sizeof(uint64_t) * (size_t)total));
+	CUDA_TRY(b[CODE_A].reserve(sizeof(K) * (size_t)total));
+	CUDA_TRY(b[CODE_B].reserve(sizeof(K) * (size_t)total));
 	CUDA_TRY(b[REC_A].reserve(sizeof(uint32_t) * ((size_t)total + 1)));
 	CUDA_TRY(b[REC_B].reserve(sizeof(uint32_t) * (size_t)total));
 	CUDA_TRY(b[SHARE].reserve(sizeof(float) * COMPS * (size_t)total));
-	uint64_t *code_a = (uint64_t *)b[CODE_A].p, *code_b = (uint64_t *)b[CODE_B].p;
+	K *code_a = (K *)b[CODE_A].p, *code_b = (K *)b[CODE_B].p;
 	uint32_t *rec_a = (uint32_t *)b[REC_A].p, *rec_b = (uint32_t *)b[REC_B].p;
 	float *share = (float *)b[SHARE].p;
-	spread_emit<D><<<blocks_for((size_t)n * 32), kBlock, 0, st>>>(rows, n, g, offset, code_a, rec_a, share);
+	if (g.half == 1) spread_emit<D, 1, K><<<blocks_for((size_t)n * 32), kBlock, 0, st>>>(rows, n, g, offset, code_a, rec_a, share);
+	else spread_emit<D, 2, K><<<blocks_for((size_t)n * 32), kBlock, 0, st>>>(rows, n, g, offset, code_a, rec_a, share);
 
 	CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp, code_a, code_b, rec_a, rec_b, (int)total, 0, bits, st));
 	CUDA_TRY(b[TEMP].reserve(temp));
 	CUDA_TRY(cub::DeviceRadixSort::SortPairs(b[TEMP].p, temp, code_a, code_b, rec_a, rec_b, (int)total, 0, bits, st));
 
 	// code_a / rec_a are free again: they take the distinct codes and their run lengths
-	uint64_t *node_code = code_a;
-	uint32_t *run = rec_a, *n_runs = count;              // count[] is no longer needed either
-	CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, temp, code_b, node_code, run, n_runs, (int)total, st));
+	K *node_code = code_a;
+	uint32_t *run_length = rec_a, *n_runs = count;       // count[] is no longer needed either
+	CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, temp, code_b, node_code, run_length, n_runs, (int)total, st));
 	CUDA_TRY(b[TEMP].reserve(temp));
-	CUDA_TRY(cub::DeviceRunLengthEncode::Encode(b[TEMP].p, temp, code_b, node_code, run, n_runs, (int)total, st));
+	CUDA_TRY(cub::DeviceRunLengthEncode::Encode(b[TEMP].p, temp, code_b, node_code, run_length, n_runs, (int)total, st));
 	uint32_t n_nodes = 0;
 	CUDA_TRY(cudaMemcpyAsync(&n_nodes, n_runs, sizeof(n_nodes), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
@@ -180,25 +200,26 @@ int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &
 	CUDA_TRY(b[SUMS].reserve(sizeof(float) * COMPS * (size_t)n_nodes));
 	uint32_t *first = (uint32_t *)b[FIRST].p;
 	float *sums = (float *)b[SUMS].p;
-	CUDA_TRY(cudaMemsetAsync(run + n_nodes, 0, sizeof(uint32_t), st));      // so that the scan ends with `total`
-	CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, run, first, (int)n_nodes + 1, st));
+	CUDA_TRY(cudaMemsetAsync(run_length + n_nodes, 0, sizeof(uint32_t), st));   // so that the scan ends with `total`
+	CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, run_length, first, (int)n_nodes + 1, st));
 	CUDA_TRY(b[TEMP].reserve(temp));
-	CUDA_TRY(cub::DeviceScan::ExclusiveSum(b[TEMP].p, temp, run, first, (int)n_nodes + 1, st));
+	CUDA_TRY(cub::DeviceScan::ExclusiveSum(b[TEMP].p, temp, run_length, first, (int)n_nodes + 1, st));
 	node_sums<COMPS><<<blocks_for(n_nodes), kBlock, 0, st>>>(first, rec_b, share, n_nodes, sums);
 	count_launches(2);
 	CUDA_TRY(cudaGetLastError());
 
 	// results: pinned staging first (a pageable destination would be bounced by the driver)
 	HostStage &hs = host_stage();
-	const size_t code_bytes = sizeof(uint64_t) * (size_t)n_nodes, sum_bytes = sizeof(float) * COMPS * (size_t)n_nodes;
-	CUDA_TRY(hs.out.reserve(code_bytes + sum_bytes));
+	const size_t code_bytes = sizeof(K) * (size_t)n_nodes, sum_bytes = sizeof(float) * COMPS * (size_t)n_nodes;
+	const size_t sums_at = (code_bytes + 15) & ~(size_t)15;
+	CUDA_TRY(hs.out.reserve(sums_at + sum_bytes));
 	CUDA_TRY(cudaMemcpyAsync(hs.out.p, node_code, code_bytes, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + code_bytes, sums, sum_bytes, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + sums_at, sums, sum_bytes, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	nodes->code.resize(n_nodes);
 	nodes->strength.resize((size_t)n_nodes * COMPS);
-	copy_bytes(nodes->code.data(), hs.out.p, code_bytes);
-	copy_bytes(nodes->strength.data(), (const char *)hs.out.p + code_bytes, sum_bytes);
+	fetch_codes<K>(nodes->code.data(), (const K *)hs.out.p, n_nodes);
+	fetch_bytes(nodes->strength.data(), (const char *)hs.out.p + sums_at, sum_bytes);
 	return CVTX_B200_OK;
 }
 
@@ -212,26 +233,27 @@ int device_nodes(int device, int dim, int kind, float h, const void *const *part
 	if (int rc = device_stream(device, &st)) return rc;
 	Device *d = get_device(device);
 	const int row_floats = dim == 3 ? 7 : 4;
+	static const bool trace = [] { const char *e = std::getenv("CVTX_B200_TRACE"); return e && e[0] == '1'; }();
 
-	// gather the particles into the pinned staging area, place the grid from them
+	// gather the particles into the pinned staging area and place the grid, in one pass
 	HostStage &hs = host_stage();
 	std::lock_guard<std::mutex> stage_lock(hs.mu);
 	CUDA_TRY(hs.src.reserve(sizeof(float) * row_floats * (size_t)n));
-	static const bool trace = [] { const char *e = std::getenv("CVTX_B200_TRACE"); return e && e[0] == '1'; }();
 	const double t0 = omp_get_wtime();
-	gather_rows(hs.src.p, particles, n, sizeof(float) * row_floats);
-	const double t1 = omp_get_wtime();
 	const float *rows = (const float *)hs.src.p;
 	uint32_t max_index = 0;
-	*grid = place_grid(dim, kind, kHalfWidth[kind], h, rows, n, row_floats, &max_index);
+	*grid = place_grid(dim, kind, kHalfWidth[kind], h, particles, (float *)hs.src.p, n, row_floats, &max_index);
 	const int bits = code_bits(dim, max_index);
 	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
 
 	std::lock_guard<std::mutex> device_lock(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
-	const double t2 = omp_get_wtime();
-	const int rc = dim == 3 ? run<3>(d, st, rows, n, *grid, bits, nodes) : run<2>(d, st, rows, n, *grid, bits, nodes);
-	if (trace) std::fprintf(stderr, "cvortex trace:   gather %.3f ms, grid %.3f ms, H2D + kernels + D2H %.3f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (omp_get_wtime() - t2) * 1e3);
+	const double t1 = omp_get_wtime();
+	int rc;
+	if (bits <= 32) rc = dim == 3 ? run<3, uint32_t>(d, st, rows, n, *grid, bits, nodes) : run<2, uint32_t>(d, st, rows, n, *grid, bits, nodes);
+	else rc = dim == 3 ? run<3, uint64_t>(d, st, rows, n, *grid, bits, nodes) : run<2, uint64_t>(d, st, rows, n, *grid, bits, nodes);
+	if (trace) std::fprintf(stderr, "cvortex trace:   gather + grid %.3f ms, H2D + kernels + D2H %.3f ms (%d-bit codes)\n", (t1 - t0) * 1e3,
+	                        (omp_get_wtime() - t1) * 1e3, bits <= 32 ? 32 : 64);
 	return rc;
 }
 

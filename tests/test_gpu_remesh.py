@@ -80,6 +80,21 @@ def test_gpu_matches_oracle_and_live_reference(gpu, oracle, ref):
                                        what=f"reference {dim} {name} {negl} {cap}")
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_fine_grids_use_wide_codes(gpu, oracle, dim):
+    """More than 2^10 (3-D) / 2^16 (2-D) nodes per axis: the device switches to 64-bit node
+    codes.  Sparse particles on a very fine grid, so the node count stays small."""
+    product, dev = gpu
+    p = remesh_particles(np.random.default_rng(31), 3000, dim)
+    h = 4e-4 if dim == 3 else 1e-5
+    for name in ("lambda1", "m4p"):
+        got = fn_of(product, dim)(p, name, h, 0.0)
+        assert dev.last_dispatch() == 1
+        want = on_host(product, lambda: fn_of(product, dim)(p, name, h, 0.0))
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert_same_remesh(got, oracle.redistribute(p, name, h, 0.0), what=f"fine {dim} {name}")
+
+
 @pytest.mark.parametrize("dim,n", [(3, 1_000_000), (2, 1_000_000)])
 def test_benchmark_size_conserves_vorticity_and_is_deterministic(gpu, dim, n):
     """The reference benchmark's largest case (bench/benchredistribution.c:49-61: a million
