@@ -127,3 +127,23 @@ def F3D_M2M_vel(filaments, mes):
 
 def F3D_M2M_dvort(filaments, induced):
     return _checked(library().F3D_M2M_dvort, filaments, induced)
+
+
+def F3D_inf_mtrx(filaments, mes, dirs):
+    return _checked(library().F3D_inf_mtrx, filaments, mes, dirs)
+
+
+# ---- the steps either side of the all-pairs sums (reference src/P3D.cpp:509-707, src/P2D.cpp:283-436) ----
+
+def P3D_redistribute_on_grid(particles, redist, grid_density, negligible_vort=0.0, max_output=None):
+    """`redist` is one of "lambda0" .. "lambda3", "m4p" (the GPU path) -- a user-defined
+    cvtx_RedistFunc runs on the host: call library().P3D_redistribute_on_grid for that."""
+    return _checked(library().P3D_redistribute_on_grid, particles, redist, grid_density, negligible_vort, max_output)
+
+
+def P2D_redistribute_on_grid(particles, redist, grid_density, negligible_vort=0.0, max_output=None):
+    return _checked(library().P2D_redistribute_on_grid, particles, redist, grid_density, negligible_vort, max_output)
+
+
+def P3D_pedrizzetti_relaxation(particles, fdt, reg, sigma):
+    return _checked(library().P3D_pedrizzetti_relaxation, particles, fdt, reg, sigma)
