@@ -37,7 +37,7 @@ def build(ref: bool = True) -> None:
         targets.append("ref")
         # the reference's own test program linked against the product library (needs it built)
         if os.path.exists(os.path.join(os.path.dirname(HERE), "cvortex_b200", "lib", "libcvortex.so")):
-            targets.append("ref_tests")
+            targets += ["ref_tests", "ref_bench"]
     subprocess.run(["make", "-C", HERE, "--no-print-directory"] + targets, check=True,
                    stdout=subprocess.DEVNULL)
 
