@@ -73,11 +73,6 @@ int host_threads() {
 // ---- grid placement (shared with the device stage) -----------------------------------
 Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const void *const *particles, float *rows, long n, int row_floats,
                               uint32_t *max_index) {
-	Grid g;
-	g.h = h;
-	g.rh = 1.f / h;
-	g.kind = kind;
-	g.half = half;
 	// bounds and FP64 coordinate sums: fixed-size pieces in parallel, combined in piece order,
 	// so the result does not depend on the thread count (one piece = the reference's plain
 	// sequential loop, src/array_methods.cpp minmax_xyz_posn / mean_xyz_posn)
@@ -109,6 +104,16 @@ Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const void *
 			hi[a] = hi[a] < q.hi[a] ? q.hi[a] : hi[a];
 			sum[a] += q.sum[a];
 		}
+	return grid_from_bounds(dim, kind, half, h, lo, hi, sum, n, max_index);
+}
+
+Grid cvtx::remesh::grid_from_bounds(int dim, int kind, int half, float h, const float *lo, const float *hi, const double *sum, long n,
+                                    uint32_t *max_index) {
+	Grid g;
+	g.h = h;
+	g.rh = 1.f / h;
+	g.kind = kind;
+	g.half = half;
 	uint32_t top = 0;
 	for (int a = 0; a < 3; ++a) g.origin[a] = 0.f;
 	for (int a = 0; a < dim; ++a) {
@@ -222,32 +227,19 @@ void host_nodes_user(const float *rows, long n, Grid g, const cvtx_RedistFunc *r
 // histograms of [min, max], zooming into the bin where the count from the top crosses
 // `wanted` (reference src/redistribution_helper_funcs.cpp:32-91, same arithmetic).
 float strength_cut(const std::vector<float> &s, int n, int wanted) {
-	const int bins = 1024;
-	float fmin = n > 0 ? s[0] : 0.f, fmax = fmin;
-	for (int i = 0; i < n; ++i) { fmin = fmin < s[i] ? fmin : s[i]; fmax = fmax > s[i] ? fmax : s[i]; }
-	double lo = fmin, hi = fmax;
-	if (n < wanted) return (float)(hi * 1.05);
-	std::vector<float> edge(bins);
-	std::vector<int> count(bins);
-	int k = 0;
-	for (;;) {
-		const double range = (hi - lo) * 1.05;
-		for (int i = 0; i < bins; ++i) { count[i] = 0; edge[i] = (float)(lo + i * range / (float)(bins - 1)); }
-		for (int i = 0; i < n; ++i) {
-			const int b = (int)std::floor((double)(bins - 1) * (s[i] - lo) / range);
-			++count[b < 0 ? 0 : (b >= bins ? bins - 1 : b)];
-		}
-		int above = count[bins - 1];
-		for (int i = bins - 2; i >= 0; --i) {
-			hi = edge[i + 1];
-			lo = edge[i];
-			above += count[i];
-			count[i] = above;
-			if (above > wanted) { k = i + 1; break; }
-		}
-		if (lo == hi || count[k] == count[k - 1] || std::fabs((float)(wanted - count[k]) / (float)wanted) < 0.01f * 0.6) break;
-	}
-	return edge[k];
+	return strength_cut_with(
+	    n, wanted,
+	    [&](float *fmin, float *fmax) {
+		    *fmin = *fmax = n > 0 ? s[0] : 0.f;
+		    for (int i = 0; i < n; ++i) { *fmin = *fmin < s[i] ? *fmin : s[i]; *fmax = *fmax > s[i] ? *fmax : s[i]; }
+	    },
+	    [&](double lo, double range, int *count) {
+		    for (int i = 0; i < kCutBins; ++i) count[i] = 0;
+		    for (int i = 0; i < n; ++i) {
+			    const int b = (int)std::floor((double)(kCutBins - 1) * (s[i] - lo) / range);
+			    ++count[b < 0 ? 0 : (b >= kCutBins ? kCutBins - 1 : b)];
+		    }
+	    });
 }
 
 // Which nodes survive a cut: node i stays when strength[i] > cut and i < index_limit; the

@@ -26,6 +26,9 @@ struct NodeSet {
 Grid place_grid(int dim, int kind, int half, float h, const void *const *particles, float *rows, long n, int row_floats,
                 uint32_t *max_index);
 
+// The same placement from bounds already reduced (lo / hi per axis, FP64 coordinate sums).
+Grid grid_from_bounds(int dim, int kind, int half, float h, const float *lo, const float *hi, const double *sum, long n, uint32_t *max_index);
+
 // Bits of Morton code needed for indices <= max_index; -1 when the grid is larger than
 // the codes can hold (2^21 nodes per axis in 3-D, 2^31 in 2-D).
 int code_bits(int dim, uint32_t max_index);
@@ -33,6 +36,45 @@ int code_bits(int dim, uint32_t max_index);
 // Device stage: particles (array of pointers to cvtx_P3D / cvtx_P2D) -> node set, on
 // `device`.  Returns a cvtx_b200_status; fills grid and nodes on success.
 int device_nodes(int device, int dim, int kind, float h, const void *const *particles, long n, Grid *grid, NodeSet *nodes);
+
+// Device-resident redistribution (the additive cvtx_b200_redistribute of cvtx_b200.h): rows_dev
+// in, out_dev (capacity max_out rows, may be null = count only) out, both on `device`.
+int device_redistribute(int device, void *stream, int dim, int kind, const float *rows_dev, long n, float h, float negligible,
+                        float *out_dev, int max_out, int *n_out);
+
+// The strength above which about `wanted` of the n particles remain: repeated 1024-bin
+// histograms of [min, max], zooming into the bin where the count from the top crosses
+// `wanted` (reference src/redistribution_helper_funcs.cpp:32-91, same arithmetic).  The
+// data stay with the caller: minmax(&min, &max) and histogram(lo, range, counts[1024]) --
+// bin = floor(1023 (s - lo) / range) in FP64, clamped to [0, 1023] -- are supplied by the
+// host stage (a loop) and by the device stage (kernels), so both take the same decisions.
+constexpr int kCutBins = 1024;
+template <class MinMax, class Histogram>
+float strength_cut_with(int n, int wanted, MinMax &&minmax, Histogram &&histogram) {
+	float fmin = 0.f, fmax = 0.f;
+	minmax(&fmin, &fmax);
+	double lo = fmin, hi = fmax;
+	if (n < wanted) return (float)(hi * 1.05);
+	std::vector<float> edge(kCutBins);
+	std::vector<int> count(kCutBins);
+	int k = 0;
+	for (;;) {
+		const double range = (hi - lo) * 1.05;
+		for (int i = 0; i < kCutBins; ++i) edge[i] = (float)(lo + i * range / (float)(kCutBins - 1));
+		histogram(lo, range, count.data());
+		int above = count[kCutBins - 1];
+		for (int i = kCutBins - 2; i >= 0; --i) {
+			hi = edge[i + 1];
+			lo = edge[i];
+			above += count[i];
+			count[i] = above;
+			if (above > wanted) { k = i + 1; break; }
+		}
+		const float miss = (float)(wanted - count[k]) / (float)wanted;
+		if (lo == hi || count[k] == count[k - 1] || (double)(miss < 0.f ? -miss : miss) < 0.01f * 0.6) break;
+	}
+	return edge[k];
+}
 
 }  // namespace remesh
 }  // namespace cvtx

@@ -30,6 +30,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <vector>
 #include "remesh.h"
 #include "runtime.h"
 
@@ -145,17 +147,19 @@ void fetch_bytes(void *dst, const void *src, size_t bytes) {
 	}
 }
 
+enum { ROWS, COUNT, OFFSET, CODE_A, CODE_B, REC_A, REC_B, SHARE, TEMP, FIRST, SUMS,        // node build
+       PARTIAL, STRENGTH, KEEP, POSITION, CODE_C, SUMS_C, HISTOGRAM };                     // device-resident pruning
+
+// Node build on rows that are already on the device.  On return (stream synchronised)
+// node_code[0..n_nodes) and sums[0..n_nodes * COMPS) hold the nodes in ascending code order.
 template <int D, class K>
-int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &g, int bits, NodeSet *nodes) {
-	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
+int build_nodes(Device *d, cudaStream_t st, const float *rows, long n, const Grid &g, int bits, K **node_code_out, float **sums_out, uint32_t *n_nodes_out) {
+	constexpr int COMPS = Layout<D>::COMPS;
 	Buffer *b = d->remesh;
-	enum { ROWS, COUNT, OFFSET, CODE_A, CODE_B, REC_A, REC_B, SHARE, TEMP, FIRST, SUMS };
-	CUDA_TRY(b[ROWS].reserve(sizeof(float) * ROW * (size_t)n));
+	*n_nodes_out = 0;
 	CUDA_TRY(b[COUNT].reserve(sizeof(uint32_t) * (size_t)(n + 1)));
 	CUDA_TRY(b[OFFSET].reserve(sizeof(uint32_t) * (size_t)(n + 1)));
-	float *rows = (float *)b[ROWS].p;
 	uint32_t *count = (uint32_t *)b[COUNT].p, *offset = (uint32_t *)b[OFFSET].p;
-	CUDA_TRY(cudaMemcpyAsync(rows, rows_host, sizeof(float) * ROW * (size_t)n, cudaMemcpyHostToDevice, st));
 
 	spread_count<D><<<blocks_for((size_t)n + 1), kBlock, 0, st>>>(rows, n, g, count);
 	size_t temp = 0;
@@ -166,10 +170,7 @@ int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &
 	CUDA_TRY(cudaMemcpyAsync(&total, offset + n, sizeof(total), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	count_launches(1);
-	nodes->code.clear();
-	nodes->strength.clear();
 	if (total == 0) return CVTX_B200_OK;
-	if (total > 0x7fffffffu) return fail(CVTX_B200_ERR_ARGUMENT, "redistribution creates more than 2^31 particle-node shares");
 
 	CUDA_TRY(b[CODE_A].reserve(sizeof(K) * (size_t)total));
 	CUDA_TRY(b[CODE_B].reserve(sizeof(K) * (size_t)total));
@@ -207,6 +208,27 @@ int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &
 	node_sums<COMPS><<<blocks_for(n_nodes), kBlock, 0, st>>>(first, rec_b, share, n_nodes, sums);
 	count_launches(2);
 	CUDA_TRY(cudaGetLastError());
+	*node_code_out = node_code;
+	*sums_out = sums;
+	*n_nodes_out = n_nodes;
+	return CVTX_B200_OK;
+}
+
+// The public-ABI route: rows from pinned host staging, node set back to the host.
+template <int D, class K>
+int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &g, int bits, NodeSet *nodes) {
+	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
+	Buffer *b = d->remesh;
+	CUDA_TRY(b[ROWS].reserve(sizeof(float) * ROW * (size_t)n));
+	float *rows = (float *)b[ROWS].p;
+	CUDA_TRY(cudaMemcpyAsync(rows, rows_host, sizeof(float) * ROW * (size_t)n, cudaMemcpyHostToDevice, st));
+	K *node_code = nullptr;
+	float *sums = nullptr;
+	uint32_t n_nodes = 0;
+	nodes->code.clear();
+	nodes->strength.clear();
+	if (int rc = build_nodes<D, K>(d, st, rows, n, g, bits, &node_code, &sums, &n_nodes)) return rc;
+	if (n_nodes == 0) return CVTX_B200_OK;
 
 	// results: pinned staging first (a pageable destination would be bounced by the driver)
 	HostStage &hs = host_stage();
@@ -220,6 +242,244 @@ int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &
 	nodes->strength.resize((size_t)n_nodes * COMPS);
 	fetch_codes<K>(nodes->code.data(), (const K *)hs.out.p, n_nodes);
 	fetch_bytes(nodes->strength.data(), (const char *)hs.out.p + sums_at, sum_bytes);
+	return CVTX_B200_OK;
+}
+
+// ---- device-resident redistribution: bounds and pruning on the device ---------------------
+// Block-level partial results are combined on the host in block order, so a result never
+// depends on scheduling.  FP64 sums are formed in a different (tree) order than the host
+// stage's, which can only matter when a rounded mean falls within an ulp of a threshold.
+
+struct Bounds { float lo[3], hi[3]; double sum[3]; };
+constexpr int kRowsPerBlock = kBlock * 16;
+
+template <class T, class Op>
+__device__ T block_reduce(T v, Op op, T *scratch /* kBlock / 32 */) {
+	for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_down_sync(0xffffffffu, v, o));
+	if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	T r = scratch[0];
+	if (threadIdx.x == 0) for (int w = 1; w < kBlock / 32; ++w) r = op(r, scratch[w]);
+	__syncthreads();
+	return r;      // valid in thread 0
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlock) bounds_kernel(const float *__restrict__ rows, long n, Bounds *__restrict__ partial) {
+	__shared__ double scratch_d[kBlock / 32];
+	__shared__ float scratch_f[kBlock / 32];
+	const long base = (long)blockIdx.x * kRowsPerBlock;
+	Bounds q;
+	for (int a = 0; a < 3; ++a) { q.lo[a] = 3.4e38f; q.hi[a] = -3.4e38f; q.sum[a] = 0.0; }
+	for (long i = base + threadIdx.x; i < base + kRowsPerBlock && i < n; i += kBlock)
+		for (int a = 0; a < D; ++a) {
+			const float x = rows[i * Layout<D>::ROW + a];
+			q.lo[a] = fminf(q.lo[a], x);
+			q.hi[a] = fmaxf(q.hi[a], x);
+			q.sum[a] += (double)x;
+		}
+	for (int a = 0; a < D; ++a) {
+		const float lo = block_reduce(q.lo[a], [](float x, float y) { return fminf(x, y); }, scratch_f);
+		const float hi = block_reduce(q.hi[a], [](float x, float y) { return fmaxf(x, y); }, scratch_f);
+		const double sum = block_reduce(q.sum[a], [](double x, double y) { return x + y; }, scratch_d);
+		if (threadIdx.x == 0) { partial[blockIdx.x].lo[a] = lo; partial[blockIdx.x].hi[a] = hi; partial[blockIdx.x].sum[a] = sum; }
+	}
+}
+
+// |w| per node in the host stage's FP32 order; per-block FP64 sums of them, min and max.
+struct StrengthPart { double sum; float lo, hi; };
+template <int COMPS>
+__global__ void __launch_bounds__(kBlock) strengths_kernel(const float *__restrict__ w, uint32_t n, float *__restrict__ strength, StrengthPart *__restrict__ partial) {
+	__shared__ double scratch_d[kBlock / 32];
+	__shared__ float scratch_f[kBlock / 32];
+	const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	float m = 0.f;
+	if (i < n) {
+		if (COMPS == 1) m = fabsf(w[i]);
+		else m = __fsqrt_rn(rm_add(rm_add(rm_mul(w[(size_t)i * 3], w[(size_t)i * 3]), rm_mul(w[(size_t)i * 3 + 1], w[(size_t)i * 3 + 1])),
+		                          rm_mul(w[(size_t)i * 3 + 2], w[(size_t)i * 3 + 2])));
+		strength[i] = m;
+	}
+	const double sum = block_reduce((double)m, [](double x, double y) { return x + y; }, scratch_d);
+	const float lo = block_reduce(i < n ? m : 3.4e38f, [](float x, float y) { return fminf(x, y); }, scratch_f);
+	const float hi = block_reduce(i < n ? m : -3.4e38f, [](float x, float y) { return fmaxf(x, y); }, scratch_f);
+	if (threadIdx.x == 0) { partial[blockIdx.x].sum = sum; partial[blockIdx.x].lo = lo; partial[blockIdx.x].hi = hi; }
+}
+
+// keep[i] = strength[i] > cut && i < index_limit; per-block FP64 sums of the dropped vorticity.
+template <int COMPS>
+__global__ void __launch_bounds__(kBlock) keep_kernel(const float *__restrict__ strength, const float *__restrict__ w, uint32_t n, float cut,
+                                                      uint32_t index_limit, uint32_t *__restrict__ keep, double *__restrict__ lost /* [blocks][COMPS] */) {
+	__shared__ double scratch_d[kBlock / 32];
+	const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	const bool in = i < n, stays = in && strength[i] > cut && i < index_limit;
+	if (in) keep[i] = stays ? 1u : 0u;
+	if (i == n) keep[n] = 0u;
+	for (int c = 0; c < COMPS; ++c) {
+		const double s = block_reduce(in && !stays ? (double)w[(size_t)i * COMPS + c] : 0.0, [](double x, double y) { return x + y; }, scratch_d);
+		if (threadIdx.x == 0) lost[(size_t)blockIdx.x * COMPS + c] = s;
+	}
+}
+
+struct Each { float v[3]; };
+
+// Survivors, with their share of the dropped vorticity, to new node arrays (second-cut route).
+template <int COMPS, class K>
+__global__ void __launch_bounds__(kBlock) compact_kernel(const K *__restrict__ code, const float *__restrict__ w, const uint32_t *__restrict__ keep,
+                                                         const uint32_t *__restrict__ position, uint32_t n, Each each, K *__restrict__ code_out,
+                                                         float *__restrict__ w_out) {
+	const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= n || !keep[i]) return;
+	const uint32_t at = position[i];
+	code_out[at] = code[i];
+	for (int c = 0; c < COMPS; ++c) w_out[(size_t)at * COMPS + c] = rm_add(w[(size_t)i * COMPS + c], each.v[c]);
+}
+
+// Survivors as cvtx_P3D / cvtx_P2D rows.
+template <int D, class K>
+__global__ void __launch_bounds__(kBlock) write_rows_kernel(const K *__restrict__ code, const float *__restrict__ w, const uint32_t *__restrict__ keep,
+                                                            const uint32_t *__restrict__ position, uint32_t n, Each each, Grid g, float size,
+                                                            float *__restrict__ out) {
+	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
+	const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= n || !keep[i]) return;
+	float *p = out + (size_t)position[i] * ROW;
+	const uint64_t m = code[i];
+	if (D == 3) {
+		p[0] = node_coord((uint32_t)compact3(m), g.origin[0], g.h);
+		p[1] = node_coord((uint32_t)compact3(m >> 1), g.origin[1], g.h);
+		p[2] = node_coord((uint32_t)compact3(m >> 2), g.origin[2], g.h);
+	} else {
+		p[0] = node_coord((uint32_t)compact2(m), g.origin[0], g.h);
+		p[1] = node_coord((uint32_t)compact2(m >> 1), g.origin[1], g.h);
+	}
+	for (int c = 0; c < COMPS; ++c) p[D + c] = rm_add(w[(size_t)i * COMPS + c], each.v[c]);
+	p[D + COMPS] = size;
+}
+
+__global__ void __launch_bounds__(kBlock) histogram_kernel(const float *__restrict__ strength, uint32_t n, double lo, double range, int *__restrict__ count) {
+	__shared__ int local[kCutBins];
+	for (int b = threadIdx.x; b < kCutBins; b += kBlock) local[b] = 0;
+	__syncthreads();
+	for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+		const double t = floor(__ddiv_rn(__dmul_rn((double)(kCutBins - 1), __dsub_rn((double)strength[i], lo)), range));
+		const int b = t < 0.0 ? 0 : (t >= (double)kCutBins ? kCutBins - 1 : (t == t ? (int)t : 0));
+		atomicAdd(&local[b], 1);
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < kCutBins; b += kBlock) if (local[b]) atomicAdd(&count[b], local[b]);
+}
+
+// One cut on the device: strengths (optionally), keep flags, positions.  Fills each[] and kept.
+template <int COMPS>
+int cut_on_device(Device *d, cudaStream_t st, const float *w, uint32_t n, float cut, uint32_t index_limit, Each *each, uint32_t *kept) {
+	Buffer *b = d->remesh;
+	const unsigned blocks = blocks_for(n + 1);
+	CUDA_TRY(b[KEEP].reserve(sizeof(uint32_t) * ((size_t)n + 1)));
+	CUDA_TRY(b[POSITION].reserve(sizeof(uint32_t) * ((size_t)n + 1)));
+	CUDA_TRY(b[PARTIAL].reserve(sizeof(double) * 3 * (size_t)blocks + sizeof(StrengthPart) * blocks + sizeof(Bounds) * blocks));
+	uint32_t *keep = (uint32_t *)b[KEEP].p, *position = (uint32_t *)b[POSITION].p;
+	double *lost = (double *)b[PARTIAL].p;
+	keep_kernel<COMPS><<<blocks, kBlock, 0, st>>>((const float *)b[STRENGTH].p, w, n, cut, index_limit, keep, lost);
+	size_t temp = 0;
+	CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, keep, position, (int)n + 1, st));
+	CUDA_TRY(b[TEMP].reserve(temp));
+	CUDA_TRY(cub::DeviceScan::ExclusiveSum(b[TEMP].p, temp, keep, position, (int)n + 1, st));
+	std::vector<double> host_lost((size_t)blocks * COMPS);
+	CUDA_TRY(cudaMemcpyAsync(host_lost.data(), lost, sizeof(double) * host_lost.size(), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(kept, position + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	count_launches(1);
+	for (int c = 0; c < 3; ++c) each->v[c] = 0.f;
+	for (int c = 0; c < COMPS; ++c) {
+		double total = 0.0;
+		for (unsigned k = 0; k < blocks; ++k) total += host_lost[(size_t)k * COMPS + c];
+		each->v[c] = (float)total / (float)*kept;
+	}
+	return CVTX_B200_OK;
+}
+
+template <int COMPS>
+int strengths_on_device(Device *d, cudaStream_t st, const float *w, uint32_t n, double *total, float *lo, float *hi) {
+	Buffer *b = d->remesh;
+	const unsigned blocks = blocks_for(n);
+	CUDA_TRY(b[STRENGTH].reserve(sizeof(float) * (size_t)n));
+	CUDA_TRY(b[PARTIAL].reserve(sizeof(double) * 3 * ((size_t)blocks + 1) + sizeof(StrengthPart) * blocks + sizeof(Bounds) * blocks));
+	StrengthPart *part = (StrengthPart *)b[PARTIAL].p;
+	strengths_kernel<COMPS><<<blocks, kBlock, 0, st>>>(w, n, (float *)b[STRENGTH].p, part);
+	std::vector<StrengthPart> host((size_t)blocks);
+	CUDA_TRY(cudaMemcpyAsync(host.data(), part, sizeof(StrengthPart) * blocks, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	count_launches(1);
+	*total = 0.0;
+	*lo = host[0].lo;
+	*hi = host[0].hi;
+	for (const StrengthPart &p : host) { *total += p.sum; *lo = fminf(*lo, p.lo); *hi = fmaxf(*hi, p.hi); }
+	return CVTX_B200_OK;
+}
+
+template <int D, class K>
+int redistribute_resident(Device *d, cudaStream_t st, const float *rows, long n, const Grid &g, int bits, float negligible, float *out,
+                          int max_out, int *n_out) {
+	constexpr int COMPS = Layout<D>::COMPS;
+	Buffer *b = d->remesh;
+	K *code = nullptr;
+	float *w = nullptr;
+	uint32_t n_nodes = 0;
+	*n_out = 0;
+	if (int rc = build_nodes<D, K>(d, st, rows, n, g, bits, &code, &w, &n_nodes)) return rc;
+	if (n_nodes == 0) return CVTX_B200_OK;
+
+	double total = 0.0;
+	float lo = 0.f, hi = 0.f;
+	if (int rc = strengths_on_device<COMPS>(d, st, w, n_nodes, &total, &lo, &hi)) return rc;
+	Each each;
+	uint32_t kept = 0;
+	if (int rc = cut_on_device<COMPS>(d, st, w, n_nodes, (float)(total / (double)n_nodes) * negligible, n_nodes, &each, &kept)) return rc;
+	*n_out = (int)kept;
+	if (!out || kept == 0) return CVTX_B200_OK;
+
+	if ((long)kept > (long)max_out) {
+		// too many for the caller's array: materialise the survivors, find the strength that fits
+		// (same search as the host stage, histograms on the device), cut again
+		CUDA_TRY(b[CODE_C].reserve(sizeof(K) * (size_t)kept));
+		CUDA_TRY(b[SUMS_C].reserve(sizeof(float) * COMPS * (size_t)kept));
+		K *code_c = (K *)b[CODE_C].p;
+		float *w_c = (float *)b[SUMS_C].p;
+		compact_kernel<COMPS, K><<<blocks_for(n_nodes), kBlock, 0, st>>>(code, w, (const uint32_t *)b[KEEP].p, (const uint32_t *)b[POSITION].p,
+		                                                                 n_nodes, each, code_c, w_c);
+		count_launches(1);
+		code = code_c;
+		w = w_c;
+		n_nodes = kept;
+		if (int rc = strengths_on_device<COMPS>(d, st, w, n_nodes, &total, &lo, &hi)) return rc;
+		CUDA_TRY(b[HISTOGRAM].reserve(sizeof(int) * kCutBins));
+		int *count_dev = (int *)b[HISTOGRAM].p;
+		int failed = CVTX_B200_OK;
+		const float cut2 = strength_cut_with(
+		    (int)n_nodes, max_out, [&](float *fmin, float *fmax) { *fmin = lo; *fmax = hi; },
+		    [&](double from, double range, int *count) {
+			    cudaError_t e = cudaMemsetAsync(count_dev, 0, sizeof(int) * kCutBins, st);
+			    histogram_kernel<<<296, kBlock, 0, st>>>((const float *)b[STRENGTH].p, n_nodes, from, range, count_dev);
+			    if (e == cudaSuccess) e = cudaMemcpyAsync(count, count_dev, sizeof(int) * kCutBins, cudaMemcpyDeviceToHost, st);
+			    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+			    count_launches(1);
+			    if (e != cudaSuccess) {
+				    failed = fail(CVTX_B200_ERR_CUDA, std::string("strength histogram: ") + cudaGetErrorString(e));
+				    for (int i = 0; i < kCutBins; ++i) count[i] = i == kCutBins - 1 ? (int)n_nodes : 0;   // ends the search
+			    }
+		    });
+		if (failed) return failed;
+		if (int rc = cut_on_device<COMPS>(d, st, w, n_nodes, cut2, (uint32_t)max_out, &each, &kept)) return rc;
+		*n_out = (int)kept;
+		if (kept == 0) return CVTX_B200_OK;
+	}
+	const float size = D == 3 ? g.h * g.h * g.h : g.h * g.h;
+	write_rows_kernel<D, K><<<blocks_for(n_nodes), kBlock, 0, st>>>(code, w, (const uint32_t *)b[KEEP].p, (const uint32_t *)b[POSITION].p, n_nodes,
+	                                                                each, g, size, out);
+	count_launches(1);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaStreamSynchronize(st));
 	return CVTX_B200_OK;
 }
 
@@ -245,6 +505,7 @@ int device_nodes(int device, int dim, int kind, float h, const void *const *part
 	*grid = place_grid(dim, kind, kHalfWidth[kind], h, particles, (float *)hs.src.p, n, row_floats, &max_index);
 	const int bits = code_bits(dim, max_index);
 	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
+	if ((double)n * (dim == 3 ? 125.0 : 25.0) > 2147483647.0) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles for one redistribution call (2^31 shares)");
 
 	std::lock_guard<std::mutex> device_lock(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
@@ -257,5 +518,54 @@ int device_nodes(int device, int dim, int kind, float h, const void *const *part
 	return rc;
 }
 
+int device_redistribute(int device, void *stream, int dim, int kind, const float *rows_dev, long n, float h, float negligible, float *out_dev,
+                        int max_out, int *n_out) {
+	if (dim != 2 && dim != 3) return fail(CVTX_B200_ERR_ARGUMENT, "dimension must be 2 or 3");
+	if (kind < 0 || kind >= K_COUNT) return fail(CVTX_B200_ERR_ARGUMENT, "unknown redistribution function");
+	if (n < 0 || n > 0x7ffffff0L || !n_out || !(h > 0.f) || max_out < 0) return fail(CVTX_B200_ERR_ARGUMENT, "bad count, spacing or null n_out");
+	*n_out = 0;
+	if (n == 0) return CVTX_B200_OK;
+	if (!rows_dev) return fail(CVTX_B200_ERR_ARGUMENT, "null particle rows");
+	cudaStream_t own = nullptr;
+	if (int rc = device_stream(device, &own)) return rc;
+	cudaStream_t st = stream ? (cudaStream_t)stream : own;
+	Device *d = get_device(device);
+	std::lock_guard<std::mutex> device_lock(d->mu);
+	CUDA_TRY(cudaSetDevice(device));
+
+	// bounds of the particle set -> grid placement (same formulas as the host-array route)
+	const unsigned blocks = (unsigned)((n + kRowsPerBlock - 1) / kRowsPerBlock);
+	CUDA_TRY(d->remesh[PARTIAL].reserve(sizeof(Bounds) * blocks));
+	Bounds *partial = (Bounds *)d->remesh[PARTIAL].p;
+	if (dim == 3) bounds_kernel<3><<<blocks, kBlock, 0, st>>>(rows_dev, n, partial);
+	else bounds_kernel<2><<<blocks, kBlock, 0, st>>>(rows_dev, n, partial);
+	std::vector<Bounds> host(blocks);
+	CUDA_TRY(cudaMemcpyAsync(host.data(), partial, sizeof(Bounds) * blocks, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	count_launches(1);
+	float lo[3], hi[3];
+	double sum[3] = {0, 0, 0};
+	for (int a = 0; a < 3; ++a) { lo[a] = host[0].lo[a]; hi[a] = host[0].hi[a]; }
+	for (const Bounds &q : host)
+		for (int a = 0; a < dim; ++a) { lo[a] = fminf(lo[a], q.lo[a]); hi[a] = fmaxf(hi[a], q.hi[a]); sum[a] += q.sum[a]; }
+	uint32_t max_index = 0;
+	const Grid g = grid_from_bounds(dim, kind, kHalfWidth[kind], h, lo, hi, sum, n, &max_index);
+	const int bits = code_bits(dim, max_index);
+	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
+	if ((double)n * (dim == 3 ? 125.0 : 25.0) > 2147483647.0) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles for one redistribution call (2^31 shares)");
+
+	if (bits <= 32)
+		return dim == 3 ? redistribute_resident<3, uint32_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out)
+		                : redistribute_resident<2, uint32_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out);
+	return dim == 3 ? redistribute_resident<3, uint64_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out)
+	                : redistribute_resident<2, uint64_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out);
+}
+
 }  // namespace remesh
 }  // namespace cvtx
+
+// ---- thin C ABI (include/cvtx_b200.h) ------------------------------------------------------
+extern "C" CVTX_B200_API int cvtx_b200_redistribute(int dim, int kind, int device, void *stream, const float *rows_dev, int n,
+                                                    float grid_density, float negligible_vort, float *out_dev, int max_out, int *n_out) {
+	return cvtx::remesh::device_redistribute(device, stream, dim, kind, rows_dev, n, grid_density, negligible_vort, out_dev, max_out, n_out);
+}

@@ -22,6 +22,7 @@ OPS = {
     "P3D_M2M_vel_dvort": 8,      # fused, thin ABI only (see include/cvtx_b200.h)
 }
 REGS = {"singular": 0, "winckelmans": 1, "planetary": 2, "gaussian": 3}
+REDISTS = {"lambda0": 0, "lambda1": 1, "lambda2": 2, "lambda3": 3, "m4p": 4}
 
 
 class BackendError(RuntimeError):
@@ -54,6 +55,8 @@ class DeviceBackend:
         lib.cvtx_b200_m2m_host.argtypes = [i, i, i, vp, i, vp, i, vp, f, f, C.POINTER(sz), C.POINTER(sz)]
         lib.cvtx_b200_f3d_inf_mtrx.restype = i
         lib.cvtx_b200_f3d_inf_mtrx.argtypes = [i, vp, vp, i, vp, vp, i, vp]
+        lib.cvtx_b200_redistribute.restype = i
+        lib.cvtx_b200_redistribute.argtypes = [i, i, i, vp, vp, i, f, f, vp, i, ip]
         lib.cvtx_b200_op_info.restype, lib.cvtx_b200_op_info.argtypes = i, [i, i, ip, ip, ip, ip, ip]
         lib.cvtx_b200_plan.restype, lib.cvtx_b200_plan.argtypes = i, [i, i, i, i, ip, ip, ip, ip]
         lib.cvtx_b200_kernel_launches.restype = C.c_ulonglong
@@ -135,6 +138,19 @@ class DeviceBackend:
         rc = self.lib.cvtx_b200_f3d_inf_mtrx(device, _ptr(stream), _ptr(fil), n_fil, _ptr(mes), _ptr(dirs), n_mes, _ptr(out))
         if rc:
             raise BackendError(f"cvtx_b200_f3d_inf_mtrx failed ({rc}): {self.last_error()}")
+
+    def redistribute(self, dim: int, redist: str, device: int, stream, rows, n: int, grid_density: float,
+                     negligible_vort: float = 0.0, out=None, max_out: int = 0) -> int:
+        """Redistribution onto a grid on device pointers (see cvtx_b200_redistribute): `rows` holds n
+        cvtx_P3D / cvtx_P2D structs on `device`, `out` has room for max_out (None: count only).
+        Returns the number of particles created."""
+        n_out = C.c_int(0)
+        rc = self.lib.cvtx_b200_redistribute(dim, REDISTS[redist], device, _ptr(stream), _ptr(rows), n, grid_density,
+                                             negligible_vort, _ptr(out) if out is not None else None,
+                                             max_out if out is not None else 0, C.byref(n_out))
+        if rc:
+            raise BackendError(f"cvtx_b200_redistribute({dim}D, {redist}) failed ({rc}): {self.last_error()}")
+        return n_out.value
 
     def m2m_host(self, op: str, reg: str, device: int, src: np.ndarray, tgt: np.ndarray,
                  sigma: float = 1.0, nu: float = 0.0, out: np.ndarray | None = None):

@@ -112,6 +112,21 @@ CVTX_B200_API int cvtx_b200_m2m_host(int op, int reg, int device,
 CVTX_B200_API int cvtx_b200_f3d_inf_mtrx(int device, void *stream, const float *fil_dev, int n_fil,
                                          const float *mes_dev, const float *dir_dev, int n_mes, float *out_dev);
 
+/* Redistribution onto a regular grid with the particles resident on the device (additive:
+ * the reference's cvtx_P3D_redistribute_on_grid / cvtx_P2D_redistribute_on_grid,
+ * src/P3D.cpp:509-634 and src/P2D.cpp:283-405, take host pointer arrays and return host
+ * particles).  rows_dev: n cvtx_P3D (dim 3, 7 floats) or cvtx_P2D (dim 2, 4 floats) structs;
+ * out_dev: room for max_out structs of the same kind, or NULL to ask only for the count
+ * that survives negligible_vort, as the reference's NULL idiom does.  Same grid placement,
+ * same nodes, same order and same pruning rules as the host-array entry points; *n_out
+ * receives the number of particles created.  Runs on `stream` (NULL: the library's own) and
+ * returns after it has drained -- the counts steer the host. */
+enum cvtx_b200_redist {
+	CVTX_B200_LAMBDA0 = 0, CVTX_B200_LAMBDA1 = 1, CVTX_B200_LAMBDA2 = 2, CVTX_B200_LAMBDA3 = 3, CVTX_B200_M4P = 4
+};
+CVTX_B200_API int cvtx_b200_redistribute(int dim, int kind, int device, void *stream, const float *rows_dev, int n,
+                                         float grid_density, float negligible_vort, float *out_dev, int max_out, int *n_out);
+
 /* ---- introspection ------------------------------------------------------------ */
 /* Shape and roofline metadata of (op, reg): floats per source / target / output
  * row, and the algorithmic FP32 lane-ops and MUFU ops per pair of the kernel's

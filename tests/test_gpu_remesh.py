@@ -125,3 +125,61 @@ def test_relaxation_on_the_gpu(gpu, golden, oracle, reg):
     got = product.P3D_pedrizzetti_relaxation(big, 0.2, reg, 0.05)
     want = oracle.pedrizzetti(big, 0.2, reg, 0.05)
     assert np.abs(got[:, 3:6] - want[:, 3:6]).max() <= 1e-5 * np.abs(want[:, 3:6]).max()
+
+
+# ---- particles resident on the device (cvtx_b200_redistribute, include/cvtx_b200.h) ----------
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("name", REDISTS)
+def test_device_resident_matches_the_host_array_entry_point(gpu, torch_cuda, dim, name):
+    """Same grid, same nodes, same order; strengths equal unless an FP64 partial sum (formed in a
+    different order on the device) rounds differently -- at most an ulp of FP32."""
+    torch = torch_cuda
+    product, dev = gpu
+    rng = np.random.default_rng(zlib.crc32(f"resident{dim}{name}".encode()))
+    n = 50021
+    p = remesh_particles(rng, n, dim)
+    h = float(np.cbrt(2.0 / n)) if dim == 3 else float(np.sqrt(2.0 / n))
+    rows = torch.from_numpy(p).cuda()
+    cols = p.shape[1]
+    for negl, cap in ((0.0, 4 * n), (1e-3, 4 * n), (0.01, n // 4)):
+        want = fn_of(product, dim)(p, name, h, negl, max_output=cap)
+        out = torch.full((cap, cols), float("nan"), device="cuda")
+        before = dev.kernel_launches()
+        k = dev.redistribute(dim, name, 0, torch.cuda.current_stream().cuda_stream, rows, n, h, negl, out, cap)
+        assert dev.kernel_launches() - before >= 6
+        got = out[:k].cpu().numpy()
+        assert torch.isnan(out[k:]).all(), "nothing may be written past the returned count"
+        assert_same_remesh(got, want, tol=tol_for(None if cap == 4 * n else cap), what=f"{dim} {name} {negl} {cap}")
+        assert k == len(want) or abs(k - len(want)) <= 2
+        # count-only mode: the reference's NULL idiom
+        assert abs(dev.redistribute(dim, name, 0, None, rows, n, h, negl) -
+                   fn_of(product, dim)(p, name, h, negl, count_only=True)) <= 2
+
+
+def test_device_resident_edge_cases(gpu, torch_cuda):
+    torch = torch_cuda
+    _, dev = gpu
+    from cvortex_b200.device import BackendError
+    rows = torch.zeros((10, 7), device="cuda")
+    rows[:, :3] = torch.rand((10, 3), device="cuda")
+    out = torch.zeros((100, 7), device="cuda")
+    assert dev.redistribute(3, "m4p", 0, None, rows, 0, 0.1, 0.0, out, 100) == 0          # no particles
+    assert dev.redistribute(3, "m4p", 0, None, rows, 10, 0.1, 0.0, out, 100) == 0         # no vorticity
+    with pytest.raises(BackendError):
+        dev.redistribute(3, "m4p", 0, None, rows, 10, 0.0, 0.0, out, 100)                 # spacing must be > 0
+    with pytest.raises(BackendError):
+        dev.redistribute(4, "m4p", 0, None, rows, 10, 0.1, 0.0, out, 100)
+    rows[:, 3] = 1.0
+    with pytest.raises(BackendError):
+        dev.redistribute(3, "m4p", 0, None, rows, 10, 1e-8, 0.0, out, 100)                # 2^21 nodes per axis exceeded
+    fine = dev.redistribute(3, "lambda1", 0, None, rows, 10, 4e-4, 0.0, out, 100)         # 64-bit codes
+    assert 10 <= fine <= 80
