@@ -401,6 +401,11 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 		uint32_t max_index = 0;
 		const int half = kind >= 0 ? kHalfWidth[kind] : (int)roundf(rf->radius);
 		g = place_grid(D, kind, half, h, (const void *const *)in, rows.data(), n_in, ROW, &max_index);
+		const double stencil = D == 3 ? (2.0 * half + 1) * (2.0 * half + 1) * (2.0 * half + 1) : (2.0 * half + 1) * (2.0 * half + 1);
+		if ((double)n_in * stencil > 2147483647.0) {
+			std::fprintf(stderr, "cvortex: %s: %d particles x %.0f stencil nodes exceed the 2^31 shares one call can hold; aborting.\n", entry, n_in, stencil);
+			std::abort();
+		}
 		if (code_bits(D, max_index) < 0) {
 			std::fprintf(stderr, "cvortex: %s: grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D); aborting.\n", entry);
 			std::abort();
