@@ -115,13 +115,14 @@ Grid cvtx::remesh::grid_from_bounds(int dim, int kind, int half, float h, const 
 	g.kind = kind;
 	g.half = half;
 	uint32_t top = 0;
-	for (int a = 0; a < 3; ++a) g.origin[a] = 0.f;
+	for (int a = 0; a < 3; ++a) { g.origin[a] = 0.f; g.top[a] = 0; }
 	for (int a = 0; a < dim; ++a) {
 		const float mean = (float)(sum[a] / (double)n);
 		const float corner = lo[a] - 1.f * ((float)g.half * h);
 		const float cells = roundf((mean - corner) / h) + 5.f;
 		g.origin[a] = mean - cells * h;
 		const uint32_t k = (dim == 3 ? node_index_3d(hi[a], g.origin[a], g.rh) : node_index_2d(hi[a], g.origin[a], g.rh)) + (uint32_t)g.half;
+		g.top[a] = k;
 		top = k > top ? k : top;
 	}
 	if (max_index) *max_index = top;
@@ -139,13 +140,30 @@ int cvtx::remesh::code_bits(int dim, uint32_t max_index) {
 namespace {
 
 // ---- stage A on the host --------------------------------------------------------------
-// Same records, same stable order by node code, same FP64 sums as remesh_device.cu.
+// Same shares, same summation order, same FP64 sums as remesh_device.cu.
+// The particle order every stage emits shares in: by cell (remesh_math.h cell_of), then by
+// the caller's index.
+template <int D>
+std::vector<uint32_t> cell_order(const float *rows, long n, const Grid &g) {
+	constexpr int ROW = D == 3 ? 7 : 4;
+	struct Key { uint64_t cell; uint32_t at; };
+	std::vector<Key> key((size_t)n);
+#pragma omp parallel for schedule(static)
+	for (long i = 0; i < n; ++i) key[(size_t)i] = {cell_of<D>(rows + i * ROW, g), (uint32_t)i};
+	__gnu_parallel::stable_sort(key.begin(), key.end(), [](const Key &a, const Key &b) { return a.cell < b.cell; });
+	std::vector<uint32_t> order((size_t)n);
+#pragma omp parallel for schedule(static)
+	for (long i = 0; i < n; ++i) order[(size_t)i] = key[(size_t)i].at;
+	return order;
+}
+
 template <int D>
 void host_nodes(const float *rows, long n, const Grid &g, NodeSet *nodes) {
 	constexpr int ROW = D == 3 ? 7 : 4, COMPS = D == 3 ? 3 : 1;
+	const std::vector<uint32_t> order = cell_order<D>(rows, n, g);
 	std::vector<uint32_t> offset((size_t)n + 1, 0);
 #pragma omp parallel for schedule(static)
-	for (long i = 0; i < n; ++i) offset[i + 1] = (uint32_t)spread_particle<D>(rows + i * ROW, g, [](uint64_t, const float *) {});
+	for (long i = 0; i < n; ++i) offset[i + 1] = (uint32_t)spread_particle<D>(rows + (size_t)order[(size_t)i] * ROW, g, [](uint64_t, const float *) {});
 	for (long i = 0; i < n; ++i) offset[i + 1] += offset[i];
 	const size_t total = offset[n];
 	struct Record { uint64_t code; uint32_t at; };
@@ -154,7 +172,7 @@ void host_nodes(const float *rows, long n, const Grid &g, NodeSet *nodes) {
 #pragma omp parallel for schedule(static)
 	for (long i = 0; i < n; ++i) {
 		uint32_t at = offset[i];
-		spread_particle<D>(rows + i * ROW, g, [&](uint64_t m, const float *s) {
+		spread_particle<D>(rows + (size_t)order[(size_t)i] * ROW, g, [&](uint64_t m, const float *s) {
 			rec[at] = {m, at};
 			for (int c = 0; c < COMPS; ++c) share[(size_t)at * COMPS + c] = s[c];
 			++at;

@@ -4,8 +4,13 @@
 // cvtx_P2D_redistribute_on_grid (src/P3D.cpp:552-589, src/P2D.cpp:325-362): there, every
 // thread inserts its particles' (2R+1)^D shares into a private oct/quadtree one key at a
 // time and the trees are merged serially (src/GridParticleOcttree.cpp:76-135,216-280).
-// Here the same shares are produced per particle, sorted by the Morton code of their node
-// and summed per node:
+// Here the particles are first put in cell order (cell = nearest node; the order shares are
+// summed in, remesh_math.h), then one of two routes builds the nodes.  Dense route, when the
+// grid is small and populated (the usual remeshing case): one thread per grid node, in Morton
+// order, walks the particles of the (2R+1)^D cells around it -- 2R+1 contiguous runs per
+// x-row -- and sums their shares; no share is ever written to memory.  Sort route, for sparse
+// or very fine grids: the shares are produced per particle, sorted by the Morton code of
+// their node and summed per node:
 //
 //   spread_count   particle -> number of non-zero shares            (28 B read / particle)
 //   [scan]         offsets of each particle's run of shares         (CUB)
@@ -27,6 +32,7 @@
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 #include <omp.h>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -123,6 +129,116 @@ __global__ void __launch_bounds__(kBlock) node_sums(const uint32_t *__restrict__
 	for (int c = 0; c < COMPS; ++c) strength[(size_t)k * COMPS + c] = (float)acc[c];
 }
 
+// ---- the summation order: particles by cell, then by the caller's index --------------------
+template <int D>
+__global__ void __launch_bounds__(kBlock) cell_keys(const float *__restrict__ rows, long n, Grid g, uint64_t *__restrict__ key, uint32_t *__restrict__ at) {
+	const long i = (long)blockIdx.x * kBlock + threadIdx.x;
+	if (i >= n) return;
+	float row[D];
+	for (int a = 0; a < D; ++a) row[a] = rows[i * Layout<D>::ROW + a];
+	key[i] = cell_of<D>(row, g);
+	at[i] = (uint32_t)i;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlock) reorder_rows(const float *__restrict__ rows, const uint32_t *__restrict__ at, long n, float *__restrict__ out) {
+	const long j = (long)blockIdx.x * kBlock + threadIdx.x;
+	if (j >= n) return;
+	const size_t from = (size_t)at[j] * Layout<D>::ROW;
+	for (int c = 0; c < Layout<D>::ROW; ++c) out[(size_t)j * Layout<D>::ROW + c] = rows[from + c];
+}
+
+// ---- dense route: one thread per grid node gathers its shares --------------------------------
+__global__ void __launch_bounds__(kBlock) count_cells(const uint64_t *__restrict__ key, long n, uint32_t *__restrict__ count) {
+	const long i = (long)blockIdx.x * kBlock + threadIdx.x;
+	if (i < n) atomicAdd(&count[key[i]], 1u);
+}
+
+// Thread t owns the node whose Morton code is t.  The particles that can reach it are those
+// of the (2R+1)^D cells around it; with cells numbered x fastest and particles sorted by
+// cell, each row of 2R+1 cells along x is ONE contiguous run of particles, walked in order --
+// the same summation order as the sort route and the host stage.  A node exists when at
+// least one share is non-zero (the reference does not insert all-zero shares).
+template <int D, int KIND>
+__global__ void __launch_bounds__(kBlock) gather_nodes(const float4 *__restrict__ rows /* 2 float4 per particle */, const uint32_t *__restrict__ cell_start,
+                                                      Grid g, uint32_t domain, uint32_t *__restrict__ exists, float *__restrict__ dense) {
+	constexpr int COMPS = Layout<D>::COMPS, R = kHalfWidth[KIND];
+	const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+	if (t > domain) return;
+	if (t == domain) { exists[t] = 0u; return; }          // so that the exclusive scan ends with the count
+	uint32_t node[3] = {0, 0, 0};
+	float at[3] = {0.f, 0.f, 0.f};                         // the node's coordinates
+	bool inside = true;
+	for (int a = 0; a < D; ++a) {
+		node[a] = (uint32_t)(D == 3 ? compact3((uint64_t)t >> a) : compact2((uint64_t)t >> a));
+		at[a] = node_coord(node[a], g.origin[a], g.h);
+		inside = inside && node[a] <= g.top[a];
+	}
+	if (!inside) { exists[t] = 0u; return; }
+	const uint64_t nx = (uint64_t)g.top[0] + 1, ny = (uint64_t)g.top[1] + 1;
+	const uint32_t x0 = node[0] >= (uint32_t)R ? node[0] - R : 0u, x1 = node[0] + R <= g.top[0] ? node[0] + R : g.top[0];
+	const uint32_t y0 = node[1] >= (uint32_t)R ? node[1] - R : 0u, y1 = node[1] + R <= g.top[1] ? node[1] + R : g.top[1];
+	const uint32_t z0 = D == 3 ? (node[2] >= (uint32_t)R ? node[2] - R : 0u) : 0u, z1 = D == 3 ? (node[2] + R <= g.top[2] ? node[2] + R : g.top[2]) : 0u;
+	double acc[COMPS];
+	for (int c = 0; c < COMPS; ++c) acc[c] = 0.0;
+	bool any = false;
+	for (uint32_t cz = z0; cz <= z1; ++cz)
+		for (uint32_t cy = y0; cy <= y1; ++cy) {
+			const uint64_t line = nx * (cy + ny * cz);
+			const uint32_t lo = cell_start[line + x0], hi = cell_start[line + x1 + 1];
+			for (uint32_t j = lo; j < hi; ++j) {
+				const float4 p = rows[2 * (size_t)j], q = rows[2 * (size_t)j + 1];      // x y z w0 | w1 w2 . .   (2-D: x y gamma .)
+				// same operations as cell_distance() / spread_particle(), node coordinate hoisted
+				float f = rm_mul(weight(KIND, fabsf(rm_mul(rm_sub(p.x, at[0]), g.rh))), weight(KIND, fabsf(rm_mul(rm_sub(p.y, at[1]), g.rh))));
+				float s[3] = {0.f, 0.f, 0.f};
+				if (D == 3) {
+					f = rm_mul(f, weight(KIND, fabsf(rm_mul(rm_sub(p.z, at[2]), g.rh))));
+					s[0] = rm_mul(p.w, f);
+					s[1] = rm_mul(q.x, f);
+					s[2] = rm_mul(q.y, f);
+				} else {
+					s[0] = rm_mul(p.z, f);
+				}
+				if (s[0] != 0.f || s[1] != 0.f || s[2] != 0.f) {
+					any = true;
+					for (int c = 0; c < COMPS; ++c) acc[c] += (double)s[c];
+				}
+			}
+		}
+	exists[t] = any ? 1u : 0u;
+	if (any) for (int c = 0; c < COMPS; ++c) dense[(size_t)t * COMPS + c] = (float)acc[c];
+}
+
+// Sorted rows padded to two float4 (the dense route reads them with two 16-byte loads).
+template <int D>
+__global__ void __launch_bounds__(kBlock) reorder_rows_padded(const float *__restrict__ rows, const uint32_t *__restrict__ at, long n, float4 *__restrict__ out) {
+	const long j = (long)blockIdx.x * kBlock + threadIdx.x;
+	if (j >= n) return;
+	const float *r = rows + (size_t)at[j] * Layout<D>::ROW;
+	if (D == 3) {
+		out[2 * j] = make_float4(r[0], r[1], r[2], r[3]);
+		out[2 * j + 1] = make_float4(r[4], r[5], r[6], 0.f);
+	} else {
+		out[2 * j] = make_float4(r[0], r[1], r[2], r[3]);
+		out[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+}
+
+template <int D, int KIND>
+void launch_gather(const float4 *rows, const uint32_t *cell_start, const Grid &g, uint32_t domain, uint32_t *exists, float *dense, cudaStream_t st) {
+	gather_nodes<D, KIND><<<(unsigned)(((size_t)domain + 1 + kBlock - 1) / kBlock), kBlock, 0, st>>>(rows, cell_start, g, domain, exists, dense);
+}
+
+template <int COMPS, class K>
+__global__ void __launch_bounds__(kBlock) collect_nodes(const uint32_t *__restrict__ exists, const uint32_t *__restrict__ position, const float *__restrict__ dense,
+                                                       uint32_t domain, K *__restrict__ node_code, float *__restrict__ sums) {
+	const uint32_t t = blockIdx.x * kBlock + threadIdx.x;
+	if (t >= domain || !exists[t]) return;
+	const uint32_t at = position[t];
+	node_code[at] = (K)t;
+	for (int c = 0; c < COMPS; ++c) sums[(size_t)at * COMPS + c] = dense[(size_t)t * COMPS + c];
+}
+
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 // Pinned staging -> the caller's vectors, in parallel pieces; codes are widened to 64
@@ -148,21 +264,105 @@ void fetch_bytes(void *dst, const void *src, size_t bytes) {
 }
 
 enum { ROWS, COUNT, OFFSET, CODE_A, CODE_B, REC_A, REC_B, SHARE, TEMP, FIRST, SUMS,        // node build
-       PARTIAL, STRENGTH, KEEP, POSITION, CODE_C, SUMS_C, HISTOGRAM };                     // device-resident pruning
+       PARTIAL, STRENGTH, KEEP, POSITION, CODE_C, SUMS_C, HISTOGRAM,                       // device-resident pruning
+       CELL_A, CELL_B, ORDER_A, ORDER_B, SORTED_ROWS, CELL_START, EXISTS, DENSE_POS, DENSE };   // cell order, dense route
 
 // Node build on rows that are already on the device.  On return (stream synchronised)
 // node_code[0..n_nodes) and sums[0..n_nodes * COMPS) hold the nodes in ascending code order.
+// Whether the dense route (one thread per grid node) is the better one: the grid must be small
+// enough to enumerate and to index, populated enough that most of its nodes exist, and not
+// crowded (the reference's 2-D benchmark puts 150 particles in a cell: few nodes, long walks --
+// sorting shares is faster there).
+inline bool dense_route(int dim, const Grid &g, int bits, long n, double *cells_out) {
+	double cells = 1.0;
+	for (int a = 0; a < dim; ++a) cells *= (double)g.top[a] + 1.0;
+	*cells_out = cells;
+	const double stencil = dim == 3 ? (2.0 * g.half + 1) * (2.0 * g.half + 1) * (2.0 * g.half + 1) : (2.0 * g.half + 1) * (2.0 * g.half + 1);
+	const bool fits = bits <= 27 && cells <= 67108864.0;
+	// CVTX_B200_REMESH_ROUTE=sort|dense pins the route (benchmarks, tests); dense still needs a grid that fits
+	static const char *pin = std::getenv("CVTX_B200_REMESH_ROUTE");
+	if (pin && !std::strcmp(pin, "sort")) return false;
+	if (pin && !std::strcmp(pin, "dense")) return fits;
+	// populated enough that most nodes exist, not so crowded that a node's thread walks thousands of particles
+	return fits && (double)n * stencil >= 0.25 * cells && (double)n <= 16.0 * cells;
+}
+
 template <int D, class K>
-int build_nodes(Device *d, cudaStream_t st, const float *rows, long n, const Grid &g, int bits, K **node_code_out, float **sums_out, uint32_t *n_nodes_out) {
+int build_nodes(Device *d, cudaStream_t st, const float *rows_in, long n, const Grid &g, int bits, K **node_code_out, float **sums_out, uint32_t *n_nodes_out) {
 	constexpr int COMPS = Layout<D>::COMPS;
 	Buffer *b = d->remesh;
 	*n_nodes_out = 0;
+	size_t temp = 0;
+
+	// particles by cell, then by the caller's index: the order shares are summed in
+	double cells = 0.0;
+	const bool dense = dense_route(D, g, bits, n, &cells);
+	int cell_bits = 1;
+	while (cell_bits < 64 && std::ldexp(1.0, cell_bits) < cells) ++cell_bits;
+	CUDA_TRY(b[CELL_A].reserve(sizeof(uint64_t) * (size_t)n));
+	CUDA_TRY(b[CELL_B].reserve(sizeof(uint64_t) * (size_t)n));
+	CUDA_TRY(b[ORDER_A].reserve(sizeof(uint32_t) * (size_t)n));
+	CUDA_TRY(b[ORDER_B].reserve(sizeof(uint32_t) * (size_t)n));
+	CUDA_TRY(b[SORTED_ROWS].reserve(sizeof(float) * 8 * (size_t)n));
+	uint64_t *cell_a = (uint64_t *)b[CELL_A].p, *cell_b = (uint64_t *)b[CELL_B].p;
+	uint32_t *order_a = (uint32_t *)b[ORDER_A].p, *order_b = (uint32_t *)b[ORDER_B].p;
+	float *rows = (float *)b[SORTED_ROWS].p;
+	cell_keys<D><<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_in, n, g, cell_a, order_a);
+	CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp, cell_a, cell_b, order_a, order_b, (int)n, 0, cell_bits, st));
+	CUDA_TRY(b[TEMP].reserve(temp));
+	CUDA_TRY(cub::DeviceRadixSort::SortPairs(b[TEMP].p, temp, cell_a, cell_b, order_a, order_b, (int)n, 0, cell_bits, st));
+	if (dense) reorder_rows_padded<D><<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_in, order_b, n, (float4 *)rows);
+	else reorder_rows<D><<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_in, order_b, n, rows);
+	count_launches(2);
+
+	if (dense) {
+		const uint32_t n_cells = (uint32_t)cells, domain = 1u << bits;
+		CUDA_TRY(b[CELL_START].reserve(sizeof(uint32_t) * ((size_t)n_cells + 2)));
+		CUDA_TRY(b[EXISTS].reserve(sizeof(uint32_t) * ((size_t)domain + 1)));
+		CUDA_TRY(b[DENSE_POS].reserve(sizeof(uint32_t) * ((size_t)domain + 1)));
+		CUDA_TRY(b[DENSE].reserve(sizeof(float) * COMPS * (size_t)domain));
+		uint32_t *cell_start = (uint32_t *)b[CELL_START].p, *exists = (uint32_t *)b[EXISTS].p, *position = (uint32_t *)b[DENSE_POS].p;
+		float *dense_sums = (float *)b[DENSE].p;
+		// particles per cell -> first particle of each cell (count[] is scanned in place, one slot more than cells)
+		CUDA_TRY(cudaMemsetAsync(cell_start, 0, sizeof(uint32_t) * ((size_t)n_cells + 1), st));
+		count_cells<<<blocks_for((size_t)n), kBlock, 0, st>>>(cell_b, n, cell_start);
+		CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, cell_start, cell_start, (int)n_cells + 1, st));
+		CUDA_TRY(b[TEMP].reserve(temp));
+		CUDA_TRY(cub::DeviceScan::ExclusiveSum(b[TEMP].p, temp, cell_start, cell_start, (int)n_cells + 1, st));
+		const float4 *padded = (const float4 *)rows;
+		switch (g.kind) {
+		case K_LAMBDA0: launch_gather<D, K_LAMBDA0>(padded, cell_start, g, domain, exists, dense_sums, st); break;
+		case K_LAMBDA1: launch_gather<D, K_LAMBDA1>(padded, cell_start, g, domain, exists, dense_sums, st); break;
+		case K_LAMBDA2: launch_gather<D, K_LAMBDA2>(padded, cell_start, g, domain, exists, dense_sums, st); break;
+		case K_LAMBDA3: launch_gather<D, K_LAMBDA3>(padded, cell_start, g, domain, exists, dense_sums, st); break;
+		default: launch_gather<D, K_M4P>(padded, cell_start, g, domain, exists, dense_sums, st); break;
+		}
+		CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, exists, position, (int)domain + 1, st));
+		CUDA_TRY(b[TEMP].reserve(temp));
+		CUDA_TRY(cub::DeviceScan::ExclusiveSum(b[TEMP].p, temp, exists, position, (int)domain + 1, st));
+		uint32_t n_nodes = 0;
+		CUDA_TRY(cudaMemcpyAsync(&n_nodes, position + domain, sizeof(n_nodes), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		count_launches(2);
+		if (n_nodes == 0) return CVTX_B200_OK;
+		CUDA_TRY(b[CODE_A].reserve(sizeof(K) * (size_t)n_nodes));
+		CUDA_TRY(b[SUMS].reserve(sizeof(float) * COMPS * (size_t)n_nodes));
+		collect_nodes<COMPS, K><<<blocks_for(domain), kBlock, 0, st>>>(exists, position, dense_sums, domain, (K *)b[CODE_A].p, (float *)b[SUMS].p);
+		count_launches(1);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaStreamSynchronize(st));
+		*node_code_out = (K *)b[CODE_A].p;
+		*sums_out = (float *)b[SUMS].p;
+		*n_nodes_out = n_nodes;
+		return CVTX_B200_OK;
+	}
+
+	// sort route: every share becomes a record
 	CUDA_TRY(b[COUNT].reserve(sizeof(uint32_t) * (size_t)(n + 1)));
 	CUDA_TRY(b[OFFSET].reserve(sizeof(uint32_t) * (size_t)(n + 1)));
 	uint32_t *count = (uint32_t *)b[COUNT].p, *offset = (uint32_t *)b[OFFSET].p;
 
 	spread_count<D><<<blocks_for((size_t)n + 1), kBlock, 0, st>>>(rows, n, g, count);
-	size_t temp = 0;
 	CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, temp, count, offset, (int)(n + 1), st));
 	CUDA_TRY(b[TEMP].reserve(temp));
 	CUDA_TRY(cub::DeviceScan::ExclusiveSum(b[TEMP].p, temp, count, offset, (int)(n + 1), st));

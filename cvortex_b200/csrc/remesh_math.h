@@ -86,6 +86,7 @@ struct Grid {
 	float h, rh;        // spacing and its FP32 reciprocal
 	float origin[3];
 	int kind, half;     // interpolant and stencil half-width
+	uint32_t top[3];    // largest node index, per axis, that any particle's stencil touches (0 on unused axes)
 };
 
 // Nearest node index along one axis.
@@ -106,6 +107,21 @@ RM_HD float node_coord(uint32_t k, float origin, float h) {       // src/UIntKey
 // Distance, in cells, from a particle coordinate to node k.
 RM_HD float cell_distance(float x, uint32_t k, const Grid &g, int axis) {
 	return fabsf(rm_mul(rm_sub(x, node_coord(k, g.origin[axis], g.h)), g.rh));
+}
+
+// A particle's cell = its nearest node.  Cells are numbered x fastest over the box
+// [0, top]^D.  A node's shares are summed cell by cell in this order and, within a cell, in
+// the order the caller gave the particles -- the one summation order every stage follows
+// (device sort route, device dense route, host), which is what makes their results
+// bit-identical.
+template <int D>
+RM_HD uint64_t cell_of(const float *row, const Grid &g) {
+	uint64_t lin = 0;
+	for (int a = D - 1; a >= 0; --a) {
+		const uint32_t k = D == 3 ? node_index_3d(row[a], g.origin[a], g.rh) : node_index_2d(row[a], g.origin[a], g.rh);
+		lin = lin * ((uint64_t)g.top[a] + 1) + k;
+	}
+	return lin;
 }
 
 // Morton codes: bit b of x lands at D*b, of y at D*b+1, of z at D*b+2.

@@ -34,7 +34,7 @@ struct Device {
 	cudaStream_t stream = nullptr;
 	Buffer d_src, d_tgt, d_out;
 	// work arrays of the grid redistribution (remesh_device.cu)
-	Buffer remesh[24];
+	Buffer remesh[32];
 };
 
 // Library-wide pinned (portable) staging: sources, targets and results of ONE

@@ -63,6 +63,12 @@ def test_gpu_and_host_stage_give_the_same_bits(gpu, dim, name):
         want = on_host(product, lambda: fn_of(product, dim)(p, name, h, negl, max_output=cap))
         assert dev.last_dispatch() == 0
         assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dim, name, negl, cap)
+    # the same particles on a grid 12x finer per axis: too sparse for the dense route, so the device
+    # sorts shares instead (32-bit codes); still the same bits as the host stage
+    fine = h / 12
+    got = fn_of(product, dim)(p, name, fine, 1e-4)
+    want = on_host(product, lambda: fn_of(product, dim)(p, name, fine, 1e-4))
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dim, name, "sparse")
 
 
 def test_gpu_matches_oracle_and_live_reference(gpu, oracle, ref):
