@@ -334,7 +334,10 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	unsigned long long launched = 2;
 	if (plan.gy > 1) {
 		const long n_vals = (long)n_tgt * q.nout;
-		reduce_partials_kernel<<<(unsigned)((n_vals + 255) / 256), 256, 0, st>>>((const double *)d->partial.p, out, n_vals, plan.gy);
+		if (n_vals <= 8192 && plan.gy >= 64)      // few values, many chunks: a warp per value
+			reduce_partials_wide_kernel<<<(unsigned)((n_vals * 32 + 255) / 256), 256, 0, st>>>((const double *)d->partial.p, out, n_vals, plan.gy);
+		else
+			reduce_partials_kernel<<<(unsigned)((n_vals + 255) / 256), 256, 0, st>>>((const double *)d->partial.p, out, n_vals, plan.gy);
 		CUDA_TRY(cudaGetLastError());
 		++launched;
 	}

@@ -131,6 +131,11 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
 	}
 
+	// A warp none of whose target slots is real (the tail of the last target tile; most of the
+	// block in a few-target call) only keeps the tile hand-over in step.  Slot (t = 0, lane 0) is
+	// the warp's lowest target index.
+	const bool idle_warp = (long)blockIdx.x * (B * T) + (tid & ~31) >= (long)args.n_tgt;
+
 	for (int it = 0; it < ntile; ++it) {
 		const int buf = it & 1;
 		if (tid == 0 && it + 1 < ntile) {                          // prefetch the next tile into the other buffer
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 			bulk_g2s(tileA[buf ^ 1], gA + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
 			if (P::NSRC4 == 2) bulk_g2s(tileB[buf ^ 1], gB + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
 		}
+		if (idle_warp) { __syncthreads(); continue; }
 		mbar_wait(&full[buf], (it >> 1) & 1);
 
 		const float4 *sA = tileA[buf];
@@ -193,6 +199,20 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, float
 	double s = 0.0;
 	for (int c = 0; c < n_chunks; ++c) s += partial[(size_t)c * n_vals + i];
 	out[i] = (float)s;
+}
+
+// The same sum for few values and many chunks (a few-target call splits its sources thousands of
+// ways): one warp per value, lane l adds chunks l, l + 32, ... in order, then a fixed shuffle tree.
+__global__ void reduce_partials_wide_kernel(const double *__restrict__ partial, float *__restrict__ out,
+                                            long n_vals, int n_chunks)
+{
+	const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (i >= n_vals) return;
+	double s = 0.0;
+	for (int c = lane; c < n_chunks; c += 32) s += partial[(size_t)c * n_vals + i];
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+	if (lane == 0) out[i] = (float)s;
 }
 
 // Raw rows -> packed float4 records, zero-padded to n_pad (a multiple of kSrcTile).

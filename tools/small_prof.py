@@ -1,0 +1,12 @@
+import os, sys, numpy as np, torch
+sys.path.insert(0, '.')
+from cvortex_b200 import api
+api.initialise(); be = api.backend()
+rng = np.random.default_rng(1); st = torch.cuda.current_stream().cuda_stream
+n = 1_000_000; m = int(sys.argv[1])
+src = torch.from_numpy(rng.uniform(0, 10, (n, 7)).astype(np.float32)).cuda()
+tgt = torch.from_numpy(rng.uniform(0, 10, (m, 3)).astype(np.float32)).cuda()
+out = torch.empty((m, 3), device="cuda")
+for _ in range(3):
+    be.m2m("P3D_M2M_vel", "winckelmans", 0, st, src, n, tgt, m, out, 0.02); torch.cuda.synchronize()
+print(be.last_pair_kernel_ms(0), be.plan('P3D_M2M_vel', 0, n, m))
