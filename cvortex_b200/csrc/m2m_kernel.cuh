@@ -131,10 +131,12 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
 	}
 
-	// A warp none of whose target slots is real (the tail of the last target tile; most of the
-	// block in a few-target call) only keeps the tile hand-over in step.  Slot (t = 0, lane 0) is
-	// the warp's lowest target index.
-	const bool idle_warp = (long)blockIdx.x * (B * T) + (tid & ~31) >= (long)args.n_tgt;
+	// A warp none of whose target slots is real (most of the block in a few-target call) only
+	// keeps the tile hand-over in step.  Slot (t = 0, lane 0) is the warp's lowest target index.
+	// Only the T = 1 geometry, the one the planner gives few-target calls, carries the test: in
+	// the large-problem geometries it would cost the Gaussian kernels 0.8 % for a tail that is
+	// one block in a thousand.
+	const bool idle_warp = T == 1 && (long)blockIdx.x * (B * T) + (tid & ~31) >= (long)args.n_tgt;
 
 	for (int it = 0; it < ntile; ++it) {
 		const int buf = it & 1;
@@ -143,30 +145,31 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 			bulk_g2s(tileA[buf ^ 1], gA + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
 			if (P::NSRC4 == 2) bulk_g2s(tileB[buf ^ 1], gB + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
 		}
-		if (idle_warp) { __syncthreads(); continue; }
-		mbar_wait(&full[buf], (it >> 1) & 1);
+		if (!idle_warp) {
+			mbar_wait(&full[buf], (it >> 1) & 1);
 
-		const float4 *sA = tileA[buf];
-		const float4 *sB = tileB[P::NSRC4 == 2 ? buf : 0];
+			const float4 *sA = tileA[buf];
+			const float4 *sB = tileB[P::NSRC4 == 2 ? buf : 0];
 #pragma unroll 1
-		for (int j0 = 0; j0 < S; j0 += CHAIN) {
-			Vec<W> acc[NV][P::NACC];
+			for (int j0 = 0; j0 < S; j0 += CHAIN) {
+				Vec<W> acc[NV][P::NACC];
 #pragma unroll
-			for (int v = 0; v < NV; ++v)
+				for (int v = 0; v < NV; ++v)
 #pragma unroll
-				for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+					for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
 #pragma unroll UNROLL
-			for (int j = 0; j < CHAIN; ++j) {
-				const float4 a = sA[j0 + j];
-				float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (P::NSRC4 == 2) b = sB[j0 + j];
+				for (int j = 0; j < CHAIN; ++j) {
+					const float4 a = sA[j0 + j];
+					float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (P::NSRC4 == 2) b = sB[j0 + j];
 #pragma unroll
-				for (int v = 0; v < NV; ++v) P::template pair<W>(tg[v], a, b, acc[v], args.k);
+					for (int v = 0; v < NV; ++v) P::template pair<W>(tg[v], a, b, acc[v], args.k);
+				}
+#pragma unroll
+				for (int t = 0; t < T; ++t)
+#pragma unroll
+					for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
 			}
-#pragma unroll
-			for (int t = 0; t < T; ++t)
-#pragma unroll
-				for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
 		}
 		__syncthreads();      // everyone is done with tile[buf] before it is refilled two iterations on
 	}
