@@ -25,6 +25,7 @@ def test_c_caller_links_and_runs_on_the_host_path(product, tmp_path):
     res = subprocess.run([_build(tmp_path), "600"], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "relative L2 difference 0.00e+00" in res.stdout          # same host loops both times
+    assert "give the same particles" in res.stdout                  # and the redistribution ran (host stage)
 
 
 @pytest.mark.gpu
@@ -33,3 +34,4 @@ def test_c_caller_on_the_gpu(gpu, tmp_path):
     print(res.stdout)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "sm_100a kernels" in res.stdout and "NVIDIA" in res.stdout
+    assert "give the same particles" in res.stdout                  # CUDA node build == host stage, bit for bit
