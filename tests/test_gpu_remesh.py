@@ -189,3 +189,42 @@ def test_device_resident_edge_cases(gpu, torch_cuda):
         dev.redistribute(3, "m4p", 0, None, rows, 10, 1e-8, 0.0, out, 100)                # 2^21 nodes per axis exceeded
     fine = dev.redistribute(3, "lambda1", 0, None, rows, 10, 4e-4, 0.0, out, 100)         # 64-bit codes
     assert 10 <= fine <= 80
+
+
+def test_random_configurations_same_bits_as_the_host_stage(gpu, torch_cuda):
+    """The configurations of tests/test_remesh.py's randomized test (1-400 particles, every
+    interpolant, tiny to huge cells, coincident particles, zero and extreme strengths, pruning,
+    small output arrays), signed strengths this time: whatever route and code width the device
+    picks, the host-array call returns the host stage's bits, and the device-pointer call the
+    same particles."""
+    torch = torch_cuda
+    product, dev = gpu
+    rng = np.random.default_rng(7)
+    for trial in range(150):
+        dim = int(rng.choice([2, 3]))
+        n = int(rng.choice([1, 2, 3, 5, 17, 100, 400]))
+        name = str(rng.choice(REDISTS))
+        comps = 3 if dim == 3 else 1
+        box = float(rng.choice([1e-3, 1.0, 50.0]))
+        h = box * float(rng.choice([0.03, 0.2, 1.0, 5.0]))
+        negl = float(rng.choice([0.0, 1e-4, 0.3, 0.9]))
+        p = np.zeros((n, dim + comps + 1), np.float32)
+        p[:, :dim] = float(rng.choice([0.0, -3.0, 1000.0])) + rng.uniform(0, box, (n, dim))
+        if rng.random() < 0.2:
+            p[:, :dim] = p[0, :dim]
+        p[:, dim:dim + comps] = rng.uniform(-1, 1, (n, comps)) * float(rng.choice([1.0, 1e-20, 1e10]))
+        if rng.random() < 0.1:
+            p[: n // 2, dim:dim + comps] = 0
+        cap = None if rng.random() < 0.6 else int(rng.integers(1, 200))
+        what = f"trial {trial}: {dim}D n={n} {name} box={box} h={h} negl={negl} cap={cap}"
+        got = fn_of(product, dim)(p, name, h, negl, max_output=cap)
+        want = on_host(product, lambda: fn_of(product, dim)(p, name, h, negl, max_output=cap))
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), what
+        room = cap if cap is not None else max(len(want), 1)
+        out = torch.full((room, p.shape[1]), float("nan"), device="cuda")
+        k = dev.redistribute(dim, name, 0, None, torch.from_numpy(p).cuda(), n, h, negl, out, room)
+        resident = out[:k].cpu().numpy()
+        if cap is None:
+            assert_same_remesh(resident, want, tol=2e-6, what="device-resident, " + what)
+        else:   # a too-small array: the threshold search may settle one bin apart when a sum differs by an ulp
+            assert abs(k - len(want)) <= max(2, len(want) // 50), what

@@ -210,3 +210,44 @@ def test_relaxation_keeps_strength_and_turns_towards_the_field(oracle):
     assert np.array_equal(oracle.pedrizzetti(p, 0.0, "gaussian", 0.2)[:, 3:6], p[:, 3:6])
     full = oracle.pedrizzetti(p, 1.0, "gaussian", 0.2)                 # fdt = 1: alpha -> |alpha| w/|w|
     assert np.allclose(np.linalg.norm(full[:, 3:6], axis=1), np.linalg.norm(p[:, 3:6], axis=1), rtol=1e-5)
+
+
+def test_random_configurations_against_live_reference(oracle, product, ref):
+    """150 seeded random calls -- 1 to 400 particles, every interpolant, 2-D and 3-D, boxes from
+    1e-3 to 50 wide placed at 0 / -3 / 1000, grid spacings from 3 % to 5x the box, coincident
+    particles, zero strengths, strengths scaled by 1e-20 .. 1e10, pruning on and off, output
+    arrays that are too small -- against the reference compiled here.  Strengths are kept
+    non-negative so that FP32 summation order (which differs in every implementation, the
+    reference's own included) cannot cancel its way above the tolerance."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    enabled = [k for k in range(product.num_accelerators()) if product.accelerator_enabled(k)]
+    for k in enabled:
+        product.accelerator_disable(k)
+    rng = np.random.default_rng(2026)
+    try:
+        for trial in range(150):
+            dim = int(rng.choice([2, 3]))
+            n = int(rng.choice([1, 2, 3, 5, 17, 100, 400]))
+            name = str(rng.choice(REDISTS))
+            comps = 3 if dim == 3 else 1
+            box = float(rng.choice([1e-3, 1.0, 50.0]))
+            h = box * float(rng.choice([0.03, 0.2, 1.0, 5.0]))
+            negl = float(rng.choice([0.0, 1e-4, 0.3, 0.9]))
+            p = np.zeros((n, dim + comps + 1), np.float32)
+            p[:, :dim] = float(rng.choice([0.0, -3.0, 1000.0])) + rng.uniform(0, box, (n, dim))
+            if rng.random() < 0.2:
+                p[:, :dim] = p[0, :dim]
+            p[:, dim:dim + comps] = rng.uniform(0, 1, (n, comps)) * float(rng.choice([1.0, 1e-20, 1e10]))
+            if rng.random() < 0.1:
+                p[: n // 2, dim:dim + comps] = 0
+            cap = None if rng.random() < 0.6 else int(rng.integers(1, 200))
+            what = f"trial {trial}: {dim}D n={n} {name} box={box} h={h} negl={negl} cap={cap}"
+            want = (ref.P3D_redistribute_on_grid if dim == 3 else ref.P2D_redistribute_on_grid)(p, name, h, negl, max_output=cap)
+            got = (product.P3D_redistribute_on_grid if dim == 3 else product.P2D_redistribute_on_grid)(p, name, h, negl, max_output=cap)
+            tol = 2e-6 if cap is None else 5e-5
+            assert_same_remesh(got, want, tol=tol, what="product, " + what)
+            assert_same_remesh(oracle.redistribute(p, name, h, negl, max_output=cap), want, tol=tol, what="oracle, " + what)
+    finally:
+        for k in enabled:
+            product.accelerator_enable(k)
