@@ -226,5 +226,12 @@ def test_random_configurations_same_bits_as_the_host_stage(gpu, torch_cuda):
         resident = out[:k].cpu().numpy()
         if cap is None:
             assert_same_remesh(resident, want, tol=2e-6, what="device-resident, " + what)
-        else:   # a too-small array: the threshold search may settle one bin apart when a sum differs by an ulp
-            assert abs(k - len(want)) <= max(2, len(want) // 50), what
+        else:
+            # a too-small array: a dropped-vorticity sum formed in another order can differ by an ulp,
+            # which moves tied nodes (few particles give many equal strengths) across a histogram
+            # bin and the threshold search to the next bin.  What must hold either way: the array
+            # is respected, nothing is invented, and the total vorticity is what went in.
+            assert k <= room and (k > 0) == (len(want) > 0), what
+            w = slice(dim, dim + comps)
+            scale = np.abs(want[:, w]).sum() + 1e-300
+            assert np.abs(resident[:, w].astype(np.float64).sum(0) - want[:, w].astype(np.float64).sum(0)).max() <= 1e-4 * scale, what
