@@ -14,7 +14,8 @@
 // A redistribution call is two stages.  Stage A turns the particles into the set of grid
 // nodes that receive vorticity, with each node's summed strength: on the first enabled
 // accelerator when the caller passed one of the five built-in interpolants
-// (remesh_device.cu), else on the host (host_nodes below, same arithmetic, same bits).
+// (remesh_device.cu), else on the host (host_nodes_dense / host_nodes below: the same two
+// routes, same arithmetic, same bits).
 // Stage B (prune below) is the reference's post-processing on that node set -- it has to
 // end in the caller's host array anyway: drop nodes weaker than negligible_vort x the mean
 // strength, hand the dropped vorticity back evenly, and if the caller's array is still too
@@ -129,6 +130,19 @@ Grid cvtx::remesh::grid_from_bounds(int dim, int kind, int half, float h, const 
 	return g;
 }
 
+bool cvtx::remesh::dense_route(int dim, const Grid &g, int bits, long n) {
+	double cells = 1.0;
+	for (int a = 0; a < dim; ++a) cells *= (double)g.top[a] + 1.0;
+	const double stencil = dim == 3 ? (2.0 * g.half + 1) * (2.0 * g.half + 1) * (2.0 * g.half + 1) : (2.0 * g.half + 1) * (2.0 * g.half + 1);
+	const bool fits = bits > 0 && bits <= 27 && cells <= 67108864.0;
+	// CVTX_B200_REMESH_ROUTE=sort|dense pins the route (benchmarks, tests); dense still needs a grid that fits
+	static const char *pin = std::getenv("CVTX_B200_REMESH_ROUTE");
+	if (pin && !std::strcmp(pin, "sort")) return false;
+	if (pin && !std::strcmp(pin, "dense")) return fits;
+	// populated enough that most nodes exist, not so crowded that a node walks thousands of particles
+	return fits && (double)n * stencil >= 0.25 * cells && (double)n <= 16.0 * cells;
+}
+
 int cvtx::remesh::code_bits(int dim, uint32_t max_index) {
 	int b = 0;
 	while (b < 32 && (max_index >> b) != 0) ++b;
@@ -189,6 +203,83 @@ void host_nodes(const float *rows, long n, const Grid &g, NodeSet *nodes) {
 		nodes->code.push_back(rec[j].code);
 		for (int c = 0; c < COMPS; ++c) nodes->strength.push_back((float)acc[c]);
 		j = e;
+	}
+}
+
+// Stage A on the host, dense route: what remesh_device.cu's gather_nodes does, one grid node
+// per loop iteration instead of per thread.  Nodes are visited in Morton order; a node's shares
+// come from the particles of the (2R+1)^D cells around it, walked in cell order -- with cells
+// numbered x fastest each x-row of cells is one contiguous run of the cell-sorted particles.
+// Same shares and same summation order as host_nodes() above, so the same bits, without ever
+// materialising a share.
+template <int D, int KIND>
+void host_nodes_dense(const float *rows, long n, const Grid &g, int bits, NodeSet *nodes) {
+	constexpr int ROW = D == 3 ? 7 : 4, COMPS = D == 3 ? 3 : 1, R = kHalfWidth[KIND];
+	const std::vector<uint32_t> order = cell_order<D>(rows, n, g);
+	std::vector<float> sorted((size_t)n * ROW);                 // the particles, physically in cell order
+#pragma omp parallel for schedule(static) num_threads(host_threads())
+	for (long j = 0; j < n; ++j) std::memcpy(&sorted[(size_t)j * ROW], rows + (size_t)order[(size_t)j] * ROW, sizeof(float) * ROW);
+	uint64_t n_cells = 1;
+	for (int a = 0; a < D; ++a) n_cells *= (uint64_t)g.top[a] + 1;
+	std::vector<uint32_t> cell_start(n_cells + 1, 0);
+	for (long j = 0; j < n; ++j) ++cell_start[cell_of<D>(&sorted[(size_t)j * ROW], g) + 1];
+	for (uint64_t c = 0; c < n_cells; ++c) cell_start[c + 1] += cell_start[c];
+
+	// Morton codes in runs of 4096 (a 16^3 brick in 3-D), handed out dynamically: bricks outside
+	// the grid cost nothing, bricks inside differ in how many particles they hold
+	constexpr uint64_t kBrick = 4096;
+	const uint64_t domain = (uint64_t)1 << bits, nx = (uint64_t)g.top[0] + 1, ny = (uint64_t)g.top[1] + 1;
+	const long pieces = (long)((domain + kBrick - 1) / kBrick);
+	std::vector<NodeSet> found((size_t)pieces);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads())
+	for (long p = 0; p < pieces; ++p) {
+		NodeSet &mine = found[(size_t)p];
+		const uint64_t t_end = (uint64_t)(p + 1) * kBrick < domain ? (uint64_t)(p + 1) * kBrick : domain;
+		for (uint64_t t = (uint64_t)p * kBrick; t < t_end; ++t) {
+			uint32_t node[3] = {0, 0, 0};
+			float at[3] = {0.f, 0.f, 0.f};                      // the node's coordinates
+			bool inside = true;
+			for (int a = 0; a < D; ++a) {
+				node[a] = (uint32_t)(D == 3 ? compact3(t >> a) : compact2(t >> a));
+				at[a] = node_coord(node[a], g.origin[a], g.h);
+				inside = inside && node[a] <= g.top[a];
+			}
+			if (!inside) continue;
+			uint32_t lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+			for (int a = 0; a < D; ++a) {
+				lo[a] = node[a] >= (uint32_t)R ? node[a] - (uint32_t)R : 0u;
+				hi[a] = node[a] + (uint32_t)R <= g.top[a] ? node[a] + (uint32_t)R : g.top[a];
+			}
+			double acc[COMPS] = {};
+			bool any = false;
+			for (uint32_t cz = lo[2]; cz <= hi[2]; ++cz)
+				for (uint32_t cy = lo[1]; cy <= hi[1]; ++cy) {
+					const uint64_t line = nx * (cy + ny * cz);
+					for (uint32_t j = cell_start[line + lo[0]]; j < cell_start[line + hi[0] + 1]; ++j) {
+						const float *row = &sorted[(size_t)j * ROW];
+						// cell_distance() with the node coordinate hoisted: same operations
+						float f = weight(KIND, std::fabs((row[0] - at[0]) * g.rh)) * weight(KIND, std::fabs((row[1] - at[1]) * g.rh));
+						if (D == 3) f = f * weight(KIND, std::fabs((row[2] - at[2]) * g.rh));
+						float s[COMPS];
+						bool nz = false;
+						for (int c = 0; c < COMPS; ++c) { s[c] = row[D + c] * f; nz = nz || s[c] != 0.f; }
+						if (nz) {
+							any = true;
+							for (int c = 0; c < COMPS; ++c) acc[c] += (double)s[c];
+						}
+					}
+				}
+			if (any) {
+				mine.code.push_back(t);
+				for (int c = 0; c < COMPS; ++c) mine.strength.push_back((float)acc[c]);
+			}
+		}
+	}
+	nodes->code.clear();
+	nodes->strength.clear();
+	for (const NodeSet &piece : found) {
+		nodes->code.insert(nodes->code.end(), piece.code.begin(), piece.code.end());
+		nodes->strength.insert(nodes->strength.end(), piece.strength.begin(), piece.strength.end());
 	}
 }
 
@@ -428,8 +519,18 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 			std::fprintf(stderr, "cvortex: %s: grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D); aborting.\n", entry);
 			std::abort();
 		}
-		if (kind >= 0) host_nodes<D>(rows.data(), n_in, g, &nodes);
-		else host_nodes_user<D>(rows.data(), n_in, g, rf, &nodes);
+		const int bits = code_bits(D, max_index);
+		if (kind < 0) host_nodes_user<D>(rows.data(), n_in, g, rf, &nodes);
+		else if (dense_route(D, g, bits, n_in)) {
+			switch (kind) {
+			case K_LAMBDA0: host_nodes_dense<D, K_LAMBDA0>(rows.data(), n_in, g, bits, &nodes); break;
+			case K_LAMBDA1: host_nodes_dense<D, K_LAMBDA1>(rows.data(), n_in, g, bits, &nodes); break;
+			case K_LAMBDA2: host_nodes_dense<D, K_LAMBDA2>(rows.data(), n_in, g, bits, &nodes); break;
+			case K_LAMBDA3: host_nodes_dense<D, K_LAMBDA3>(rows.data(), n_in, g, bits, &nodes); break;
+			default: host_nodes_dense<D, K_M4P>(rows.data(), n_in, g, bits, &nodes); break;
+			}
+		}
+		else host_nodes<D>(rows.data(), n_in, g, &nodes);
 	}
 	const double t1 = omp_get_wtime();
 	const size_t n_nodes = nodes.code.size();

@@ -33,6 +33,14 @@ Grid grid_from_bounds(int dim, int kind, int half, float h, const float *lo, con
 // the codes can hold (2^21 nodes per axis in 3-D, 2^31 in 2-D).
 int code_bits(int dim, uint32_t max_index);
 
+// Which of the two node-building routes a call takes (both stages, device and host): the dense
+// route visits every grid node and gathers its shares from the particles of the cells around
+// it; it needs a grid small enough to enumerate and to index (2^27 codes, 2^26 cells),
+// populated enough that most of its nodes exist, and not crowded (the reference's 2-D
+// benchmark puts 150 particles in a cell: few nodes, long walks).  Otherwise every share is
+// written out and sorted by node.  Both give the same bits.
+bool dense_route(int dim, const Grid &g, int bits, long n);
+
 // Device stage: particles (array of pointers to cvtx_P3D / cvtx_P2D) -> node set, on
 // `device`.  Returns a cvtx_b200_status; fills grid and nodes on success.
 int device_nodes(int device, int dim, int kind, float h, const void *const *particles, long n, Grid *grid, NodeSet *nodes);

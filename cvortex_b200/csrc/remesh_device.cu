@@ -269,24 +269,6 @@ enum { ROWS, COUNT, OFFSET, CODE_A, CODE_B, REC_A, REC_B, SHARE, TEMP, FIRST, SU
 
 // Node build on rows that are already on the device.  On return (stream synchronised)
 // node_code[0..n_nodes) and sums[0..n_nodes * COMPS) hold the nodes in ascending code order.
-// Whether the dense route (one thread per grid node) is the better one: the grid must be small
-// enough to enumerate and to index, populated enough that most of its nodes exist, and not
-// crowded (the reference's 2-D benchmark puts 150 particles in a cell: few nodes, long walks --
-// sorting shares is faster there).
-inline bool dense_route(int dim, const Grid &g, int bits, long n, double *cells_out) {
-	double cells = 1.0;
-	for (int a = 0; a < dim; ++a) cells *= (double)g.top[a] + 1.0;
-	*cells_out = cells;
-	const double stencil = dim == 3 ? (2.0 * g.half + 1) * (2.0 * g.half + 1) * (2.0 * g.half + 1) : (2.0 * g.half + 1) * (2.0 * g.half + 1);
-	const bool fits = bits <= 27 && cells <= 67108864.0;
-	// CVTX_B200_REMESH_ROUTE=sort|dense pins the route (benchmarks, tests); dense still needs a grid that fits
-	static const char *pin = std::getenv("CVTX_B200_REMESH_ROUTE");
-	if (pin && !std::strcmp(pin, "sort")) return false;
-	if (pin && !std::strcmp(pin, "dense")) return fits;
-	// populated enough that most nodes exist, not so crowded that a node's thread walks thousands of particles
-	return fits && (double)n * stencil >= 0.25 * cells && (double)n <= 16.0 * cells;
-}
-
 template <int D, class K>
 int build_nodes(Device *d, cudaStream_t st, const float *rows_in, long n, const Grid &g, int bits, K **node_code_out, float **sums_out, uint32_t *n_nodes_out) {
 	constexpr int COMPS = Layout<D>::COMPS;
@@ -295,8 +277,9 @@ int build_nodes(Device *d, cudaStream_t st, const float *rows_in, long n, const 
 	size_t temp = 0;
 
 	// particles by cell, then by the caller's index: the order shares are summed in
-	double cells = 0.0;
-	const bool dense = dense_route(D, g, bits, n, &cells);
+	double cells = 1.0;
+	for (int a = 0; a < D; ++a) cells *= (double)g.top[a] + 1.0;
+	const bool dense = dense_route(D, g, bits, n);
 	int cell_bits = 1;
 	while (cell_bits < 64 && std::ldexp(1.0, cell_bits) < cells) ++cell_bits;
 	CUDA_TRY(b[CELL_A].reserve(sizeof(uint64_t) * (size_t)n));
