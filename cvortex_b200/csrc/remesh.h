@@ -66,7 +66,9 @@ float strength_cut_with(int n, int wanted, MinMax &&minmax, Histogram &&histogra
 	std::vector<float> edge(kCutBins);
 	std::vector<int> count(kCutBins);
 	int k = 0;
-	for (;;) {
+	// every round narrows [lo, hi] to one of 1024 bins, so FP32 strengths are separated after 4
+	// rounds at most; the cap only guards against NaN input, where no comparison ever succeeds
+	for (int round = 0; round < 64; ++round) {
 		const double range = (hi - lo) * 1.05;
 		for (int i = 0; i < kCutBins; ++i) edge[i] = (float)(lo + i * range / (float)(kCutBins - 1));
 		histogram(lo, range, count.data());
