@@ -80,6 +80,7 @@ float strength_cut_with(int n, int wanted, MinMax &&minmax, Histogram &&histogra
 			count[i] = above;
 			if (above > wanted) { k = i + 1; break; }
 		}
+		if (k < 1) break;      // the count never crossed `wanted` (NaN strengths): nothing to refine
 		const float miss = (float)(wanted - count[k]) / (float)wanted;
 		if (lo == hi || count[k] == count[k - 1] || (double)(miss < 0.f ? -miss : miss) < 0.01f * 0.6) break;
 	}
