@@ -265,7 +265,8 @@ void fetch_bytes(void *dst, const void *src, size_t bytes) {
 
 enum { ROWS, COUNT, OFFSET, CODE_A, CODE_B, REC_A, REC_B, SHARE, TEMP, FIRST, SUMS,        // node build
        PARTIAL, STRENGTH, KEEP, POSITION, CODE_C, SUMS_C, HISTOGRAM,                       // device-resident pruning
-       CELL_A, CELL_B, ORDER_A, ORDER_B, SORTED_ROWS, CELL_START, EXISTS, DENSE_POS, DENSE };   // cell order, dense route
+       CELL_A, CELL_B, ORDER_A, ORDER_B, SORTED_ROWS, CELL_START, EXISTS, DENSE_POS, DENSE,     // cell order, dense route
+       RELAX_POINTS, RELAX_FIELD };                                                        // relaxation
 
 // Node build on rows that are already on the device.  On return (stream synchronised)
 // node_code[0..n_nodes) and sums[0..n_nodes * COMPS) hold the nodes in ascending code order.
@@ -747,7 +748,70 @@ int device_redistribute(int device, void *stream, int dim, int kind, const float
 }  // namespace remesh
 }  // namespace cvtx
 
+// ---- Pedrizzetti relaxation on device-resident particles -----------------------------------
+namespace cvtx {
+namespace remesh {
+namespace {
+
+__global__ void __launch_bounds__(kBlock) particle_positions(const float *__restrict__ rows, int n, float *__restrict__ points) {
+	const int i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= n) return;
+	for (int a = 0; a < 3; ++a) points[(size_t)i * 3 + a] = rows[(size_t)i * 7 + a];
+}
+
+// alpha <- (1 - f dt) alpha + f dt |alpha| omega / |omega|, each operation a single rounded FP32
+// op in the reference's order (src/P3D.cpp:687-699); zero where the field is zero.
+__global__ void __launch_bounds__(kBlock) relax_blend(float *__restrict__ rows, const float *__restrict__ field, int n, float fdt) {
+	const int i = blockIdx.x * kBlock + threadIdx.x;
+	if (i >= n) return;
+	float *a = rows + (size_t)i * 7 + 3;
+	const float *w = field + (size_t)i * 3;
+	const float wn = __fsqrt_rn(rm_add(rm_add(rm_mul(w[0], w[0]), rm_mul(w[1], w[1])), rm_mul(w[2], w[2])));
+	const float an = __fsqrt_rn(rm_add(rm_add(rm_mul(a[0], a[0]), rm_mul(a[1], a[1])), rm_mul(a[2], a[2])));
+	const float keep = rm_sub(1.f, fdt), pull = rm_mul(__fdiv_rn(an, wn), fdt);
+	for (int c = 0; c < 3; ++c) {
+		const float r = rm_add(rm_mul(a[c], keep), rm_mul(w[c], pull));
+		a[c] = wn != 0.f ? r : 0.f;
+	}
+}
+
+}  // namespace
+}  // namespace remesh
+}  // namespace cvtx
+
 // ---- thin C ABI (include/cvtx_b200.h) ------------------------------------------------------
+extern "C" CVTX_B200_API int cvtx_b200_pedrizzetti_relaxation(int reg, int device, void *stream, float *rows_dev, int n, float fdt, float sigma) {
+	using namespace cvtx;
+	using namespace cvtx::remesh;
+	if (n < 0) return fail(CVTX_B200_ERR_ARGUMENT, "negative count");
+	if (n == 0) return CVTX_B200_OK;
+	if (!rows_dev) return fail(CVTX_B200_ERR_ARGUMENT, "null particle rows");
+	cudaStream_t own = nullptr;
+	if (int rc = device_stream(device, &own)) return rc;
+	cudaStream_t st = stream ? (cudaStream_t)stream : own;
+	Device *d = get_device(device);
+	float *points = nullptr, *field = nullptr;
+	{
+		std::lock_guard<std::mutex> device_lock(d->mu);
+		CUDA_TRY(cudaSetDevice(device));
+		CUDA_TRY(d->remesh[RELAX_POINTS].reserve(sizeof(float) * 3 * (size_t)n));
+		CUDA_TRY(d->remesh[RELAX_FIELD].reserve(sizeof(float) * 3 * (size_t)n));
+		points = (float *)d->remesh[RELAX_POINTS].p;
+		field = (float *)d->remesh[RELAX_FIELD].p;
+		particle_positions<<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_dev, n, points);
+	}
+	// the vorticity field the particles induce at their own positions: the all-pairs kernel
+	if (int rc = cvtx_b200_m2m(CVTX_B200_P3D_VORT, reg, device, st, rows_dev, n, points, n, field, sigma, 0.f)) return rc;
+	{
+		std::lock_guard<std::mutex> device_lock(d->mu);
+		CUDA_TRY(cudaSetDevice(device));
+		relax_blend<<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_dev, field, n, fdt);
+		CUDA_TRY(cudaGetLastError());
+	}
+	count_launches(2);
+	return CVTX_B200_OK;
+}
+
 extern "C" CVTX_B200_API int cvtx_b200_redistribute(int dim, int kind, int device, void *stream, const float *rows_dev, int n,
                                                     float grid_density, float negligible_vort, float *out_dev, int max_out, int *n_out) {
 	return cvtx::remesh::device_redistribute(device, stream, dim, kind, rows_dev, n, grid_density, negligible_vort, out_dev, max_out, n_out);

@@ -57,6 +57,8 @@ class DeviceBackend:
         lib.cvtx_b200_f3d_inf_mtrx.argtypes = [i, vp, vp, i, vp, vp, i, vp]
         lib.cvtx_b200_redistribute.restype = i
         lib.cvtx_b200_redistribute.argtypes = [i, i, i, vp, vp, i, f, f, vp, i, ip]
+        lib.cvtx_b200_pedrizzetti_relaxation.restype = i
+        lib.cvtx_b200_pedrizzetti_relaxation.argtypes = [i, i, vp, vp, i, f, f]
         lib.cvtx_b200_op_info.restype, lib.cvtx_b200_op_info.argtypes = i, [i, i, ip, ip, ip, ip, ip]
         lib.cvtx_b200_plan.restype, lib.cvtx_b200_plan.argtypes = i, [i, i, i, i, ip, ip, ip, ip]
         lib.cvtx_b200_kernel_launches.restype = C.c_ulonglong
@@ -151,6 +153,13 @@ class DeviceBackend:
         if rc:
             raise BackendError(f"cvtx_b200_redistribute({dim}D, {redist}) failed ({rc}): {self.last_error()}")
         return n_out.value
+
+    def pedrizzetti_relaxation(self, reg: str, device: int, stream, rows, n: int, fdt: float, sigma: float) -> None:
+        """cvtx_P3D_pedrizzetti_relaxation on n cvtx_P3D structs resident on `device`, in place
+        (see cvtx_b200_pedrizzetti_relaxation).  Asynchronous on `stream`."""
+        rc = self.lib.cvtx_b200_pedrizzetti_relaxation(REGS[reg], device, _ptr(stream), _ptr(rows), n, fdt, sigma)
+        if rc:
+            raise BackendError(f"cvtx_b200_pedrizzetti_relaxation({reg}) failed ({rc}): {self.last_error()}")
 
     def m2m_host(self, op: str, reg: str, device: int, src: np.ndarray, tgt: np.ndarray,
                  sigma: float = 1.0, nu: float = 0.0, out: np.ndarray | None = None):

@@ -11,6 +11,7 @@ device-pointer twin of include/cvtx_b200.h:
               (by default both in ONE pass over the pairs: the fused CVTX_B200_P3D_VEL_DVORT op)
     x += u dt;  alpha += d alpha dt                                      (torch, in place)
     every k steps: cvtx_P3D_redistribute_on_grid (M4')                   cvtx_b200_redistribute
+                   cvtx_P3D_pedrizzetti_relaxation (optional)            cvtx_b200_pedrizzetti_relaxation
 
 No particle data crosses PCIe; only the particle count comes back to the host after a
 redistribution.  The script prints the ring's position, the invariants of the motion (total
@@ -60,7 +61,7 @@ def invariants(torch, rows):
     return a.sum(0).cpu().numpy(), 0.5 * torch.cross(x, a, dim=1).sum(0).cpu().numpy()
 
 
-def run(n_particles=20000, steps=20, remesh_every=5, dt=0.05, reg="gaussian", verbose=True, fused=True):
+def run(n_particles=20000, steps=20, remesh_every=5, dt=0.05, reg="gaussian", verbose=True, fused=True, relax=0.0):
     import torch
     from cvortex_b200 import api
 
@@ -102,6 +103,8 @@ def run(n_particles=20000, steps=20, remesh_every=5, dt=0.05, reg="gaussian", ve
         if remesh_every and (step + 1) % remesh_every == 0:
             n = dev.redistribute(3, "m4p", 0, stream, rows, n, h, 1e-3, spare, room)
             rows, spare = spare, rows
+            if relax > 0.0:       # pull the particle strengths back towards the field they represent
+                dev.pedrizzetti_relaxation(reg, 0, stream, rows, n, relax, sigma)
         tock.record()
         tock.synchronize()
         history[-1]["ms"] = tick.elapsed_time(tock)
@@ -115,5 +118,6 @@ if __name__ == "__main__":
     ap.add_argument("--remesh-every", type=int, default=5)
     ap.add_argument("--dt", type=float, default=0.05)
     ap.add_argument("--separate", action="store_true", help="two all-pairs calls per step instead of the fused op")
+    ap.add_argument("--relax", type=float, default=0.0, help="Pedrizzetti relaxation factor f dt applied after each redistribution")
     a = ap.parse_args()
-    run(a.particles, a.steps, a.remesh_every, a.dt, fused=not a.separate)
+    run(a.particles, a.steps, a.remesh_every, a.dt, fused=not a.separate, relax=a.relax)

@@ -127,6 +127,13 @@ enum cvtx_b200_redist {
 CVTX_B200_API int cvtx_b200_redistribute(int dim, int kind, int device, void *stream, const float *rows_dev, int n,
                                          float grid_density, float negligible_vort, float *out_dev, int max_out, int *n_out);
 
+/* cvtx_P3D_pedrizzetti_relaxation (libcvtx.h:259-265, reference src/P3D.cpp:667-707) on n
+ * cvtx_P3D structs resident on the device, in place: the vorticity field at the particles'
+ * own positions comes from the CVTX_B200_P3D_VORT kernel, the blend is the reference's FP32
+ * arithmetic.  Asynchronous on `stream` (NULL: the library's own). */
+CVTX_B200_API int cvtx_b200_pedrizzetti_relaxation(int reg, int device, void *stream, float *rows_dev, int n,
+                                                   float fdt, float sigma);
+
 /* ---- introspection ------------------------------------------------------------ */
 /* Shape and roofline metadata of (op, reg): floats per source / target / output
  * row, and the algorithmic FP32 lane-ops and MUFU ops per pair of the kernel's

@@ -235,3 +235,21 @@ def test_random_configurations_same_bits_as_the_host_stage(gpu, torch_cuda):
             w = slice(dim, dim + comps)
             scale = np.abs(want[:, w]).sum() + 1e-300
             assert np.abs(resident[:, w].astype(np.float64).sum(0) - want[:, w].astype(np.float64).sum(0)).max() <= 1e-4 * scale, what
+
+
+@pytest.mark.parametrize("reg", ["winckelmans", "gaussian", "planetary"])
+def test_device_resident_relaxation(gpu, torch_cuda, oracle, reg):
+    """cvtx_b200_pedrizzetti_relaxation: same kernel for the field, same FP32 blend as the
+    host-array entry point -- the same bits; and within 1e-5 of the reference arithmetic."""
+    torch = torch_cuda
+    product, dev = gpu
+    p = remesh_particles(np.random.default_rng(12), 20000, 3)
+    want = product.P3D_pedrizzetti_relaxation(p, 0.3, reg, 0.05)
+    rows = torch.from_numpy(p).cuda()
+    dev.pedrizzetti_relaxation(reg, 0, torch.cuda.current_stream().cuda_stream, rows, len(p), 0.3, 0.05)
+    torch.cuda.synchronize()
+    got = rows.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    ref = oracle.pedrizzetti(p, 0.3, reg, 0.05)
+    assert np.abs(got[:, 3:6] - ref[:, 3:6]).max() <= 1e-5 * np.abs(ref[:, 3:6]).max()
+    dev.pedrizzetti_relaxation(reg, 0, None, rows, 0, 0.3, 0.05)          # nothing to do
