@@ -1,3 +1,5 @@
+"""Three cvtx_P3D/P2D_redistribute_on_grid calls on the reference benchmark's workload, for ncu launch lists
+(tools/remesh_launch_summary.py) and CVTX_B200_TRACE=1 stage times.  python tools/remesh_prof.py DIM N INTERPOLANT"""
 import sys, numpy as np
 sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 from cvortex_b200 import _native
