@@ -74,10 +74,10 @@ int host_threads() {
 // ---- grid placement (shared with the device stage) -----------------------------------
 Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const void *const *particles, float *rows, long n, int row_floats,
                               uint32_t *max_index) {
-	// bounds and FP64 coordinate sums: fixed-size pieces in parallel, combined in piece order,
-	// so the result does not depend on the thread count (one piece = the reference's plain
-	// sequential loop, src/array_methods.cpp minmax_xyz_posn / mean_xyz_posn)
-	struct Piece { float lo[3], hi[3]; double sum[3]; };
+	// gather (when asked) and bounds in fixed-size pieces, in parallel; the FP64 coordinate sums
+	// in the canonical order of remesh.h, which is also what the device-resident entry point's
+	// bounds kernel produces -- the grid then sits at the same place on every route
+	struct Piece { float lo[3], hi[3]; };
 	const long pieces = (n + kPiece - 1) / kPiece;
 	std::vector<Piece> piece((size_t)pieces);
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
@@ -86,13 +86,12 @@ Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const void *
 		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
 		if (particles)   // gather this piece through the caller's pointer array first
 			for (long i = b; i < e; ++i) std::memcpy(rows + i * row_floats, particles[i], sizeof(float) * (size_t)row_floats);
-		for (int a = 0; a < 3; ++a) { q.lo[a] = q.hi[a] = a < dim ? rows[b * row_floats + a] : 0.f; q.sum[a] = 0.0; }
+		for (int a = 0; a < 3; ++a) q.lo[a] = q.hi[a] = a < dim ? rows[b * row_floats + a] : 0.f;
 		for (long i = b; i < e; ++i)
 			for (int a = 0; a < dim; ++a) {
 				const float x = rows[i * row_floats + a];
 				q.lo[a] = q.lo[a] > x ? x : q.lo[a];
 				q.hi[a] = q.hi[a] < x ? x : q.hi[a];
-				q.sum[a] += (double)x;
 			}
 		piece[(size_t)p] = q;
 	}
@@ -103,8 +102,8 @@ Grid cvtx::remesh::place_grid(int dim, int kind, int half, float h, const void *
 		for (int a = 0; a < dim; ++a) {
 			lo[a] = lo[a] > q.lo[a] ? q.lo[a] : lo[a];
 			hi[a] = hi[a] < q.hi[a] ? q.hi[a] : hi[a];
-			sum[a] += q.sum[a];
 		}
+	for (int a = 0; a < dim; ++a) sum[a] = canonical_sum(n, [&](long i) { return rows[i * row_floats + a]; });
 	return grid_from_bounds(dim, kind, half, h, lo, hi, sum, n, max_index);
 }
 
@@ -353,8 +352,9 @@ float strength_cut(const std::vector<float> &s, int n, int wanted) {
 
 // Which nodes survive a cut: node i stays when strength[i] > cut and i < index_limit; the
 // vorticity of the others is handed back evenly to the survivors (reference
-// src/P3D.cpp:636-665).  The node list is walked in fixed pieces, in parallel; partial sums
-// are combined in piece order, so the result does not depend on the thread count.
+// src/P3D.cpp:636-665).  The node list is walked in fixed pieces, in parallel; the FP64 sums
+// follow the canonical order of remesh.h, so the result does not depend on the thread count
+// and equals the device's.
 template <int COMPS>
 struct Cut {
 	float cut;
@@ -370,28 +370,29 @@ Cut<COMPS> plan_cut(const NodeSet &nodes, const std::vector<float> &strength, lo
 	c.cut = cut;
 	c.index_limit = index_limit;
 	const long pieces = (n + kPiece - 1) / kPiece;
-	struct Tally { long kept; double lost[COMPS]; };
-	std::vector<Tally> tally((size_t)pieces);
+	std::vector<long> tally((size_t)pieces);
 	const float *w = nodes.strength.data();
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
 	for (long p = 0; p < pieces; ++p) {
-		Tally t = {};
+		long kept = 0;
 		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
-		for (long i = b; i < e; ++i) {
-			if (c.keeps(strength[(size_t)i], i)) ++t.kept;
-			else for (int q = 0; q < COMPS; ++q) t.lost[q] += (double)w[(size_t)i * COMPS + q];
-		}
-		tally[(size_t)p] = t;
+		for (long i = b; i < e; ++i) kept += c.keeps(strength[(size_t)i], i) ? 1 : 0;
+		tally[(size_t)p] = kept;
 	}
 	c.kept = 0;
-	double lost[COMPS] = {};
 	c.start.resize((size_t)pieces);
 	for (long p = 0; p < pieces; ++p) {
 		c.start[(size_t)p] = c.kept;
-		c.kept += tally[(size_t)p].kept;
-		for (int q = 0; q < COMPS; ++q) lost[q] += tally[(size_t)p].lost[q];
+		c.kept += tally[(size_t)p];
 	}
-	for (int q = 0; q < COMPS; ++q) c.each[q] = (float)lost[q] / (float)c.kept;
+	// the dropped vorticity, summed in the canonical order over n + 1 slots (the device's keep
+	// kernel covers one slot past the last node)
+	for (int q = 0; q < COMPS; ++q) {
+		const double lost = canonical_sum(n + 1, [&](long i) {
+			return i < n && !c.keeps(strength[(size_t)i], i) ? w[(size_t)i * COMPS + q] : 0.f;
+		});
+		c.each[q] = (float)lost / (float)c.kept;
+	}
 	return c;
 }
 
@@ -413,28 +414,18 @@ void apply_cut(const Cut<COMPS> &c, const NodeSet &nodes, const std::vector<floa
 	}
 }
 
-// |w| per node and, in FP64, their sum.
+// |w| per node and, in FP64 and the canonical order (remesh.h), their sum.
 template <int COMPS>
 double magnitudes(const std::vector<float> &w, int n, std::vector<float> &out) {
 	out.resize((size_t)n);
-	const long pieces = ((long)n + kPiece - 1) / kPiece;
-	std::vector<double> part((size_t)pieces, 0.0);
-#pragma omp parallel for schedule(static) num_threads(host_threads()) if (pieces > 1)
-	for (long p = 0; p < pieces; ++p) {
-		const long b = p * kPiece, e = b + kPiece < n ? b + kPiece : n;
-		double t = 0.0;
-		for (long i = b; i < e; ++i) {
-			float m;
-			if (COMPS == 1) m = std::fabs(w[(size_t)i]);
-			else m = std::sqrt(w[(size_t)i * 3] * w[(size_t)i * 3] + w[(size_t)i * 3 + 1] * w[(size_t)i * 3 + 1] + w[(size_t)i * 3 + 2] * w[(size_t)i * 3 + 2]);
-			out[(size_t)i] = m;
-			t += (double)m;
-		}
-		part[(size_t)p] = t;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n > kPiece)
+	for (long i = 0; i < (long)n; ++i) {
+		float m;
+		if (COMPS == 1) m = std::fabs(w[(size_t)i]);
+		else m = std::sqrt(w[(size_t)i * 3] * w[(size_t)i * 3] + w[(size_t)i * 3 + 1] * w[(size_t)i * 3 + 1] + w[(size_t)i * 3 + 2] * w[(size_t)i * 3 + 2]);
+		out[(size_t)i] = m;
 	}
-	double total = 0.0;
-	for (double t : part) total += t;
-	return total;
+	return canonical_sum(n, [&](long i) { return out[(size_t)i]; });
 }
 
 template <int D, class Particle>
@@ -502,8 +493,14 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 	const std::vector<int> devs = enabled_accelerators();
 	if (kind >= 0 && !devs.empty()) {
 		note_dispatch(1, 1);
-		const int rc = device_nodes(devs[0], D, kind, h, (const void *const *)in, n_in, &g, &nodes);
+		int created = 0;
+		size_t n_nodes = 0;
+		const int rc = device_redistribute_from_host(devs[0], D, kind, h, (const void *const *)in, n_in, negligible, out, max_out, &created, &n_nodes);
 		if (rc != CVTX_B200_OK) gpu_failure(entry, rc);
+		if (trace_on())
+			std::fprintf(stderr, "cvortex trace: %s n=%d -> %zu nodes -> %d particles; %.3f ms (device: nodes + pruning)\n", entry, n_in, n_nodes,
+			             created, (omp_get_wtime() - t0) * 1e3);
+		return created;
 	} else {
 		note_dispatch(0, 0);
 		std::vector<float> rows((size_t)n_in * ROW);
@@ -536,8 +533,8 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 	const size_t n_nodes = nodes.code.size();
 	const int kept = prune_and_write<D>(nodes, g, out, max_out, negligible);
 	if (trace_on())
-		std::fprintf(stderr, "cvortex trace: %s n=%d -> %zu nodes -> %d particles; nodes %.3f ms (%s), prune+write %.3f ms\n", entry, n_in,
-		             n_nodes, kept, (t1 - t0) * 1e3, kind >= 0 && !devs.empty() ? "device" : "host", (omp_get_wtime() - t1) * 1e3);
+		std::fprintf(stderr, "cvortex trace: %s n=%d -> %zu nodes -> %d particles; nodes %.3f ms (host), prune+write %.3f ms\n", entry, n_in,
+		             n_nodes, kept, (t1 - t0) * 1e3, (omp_get_wtime() - t1) * 1e3);
 	return kept;
 }
 

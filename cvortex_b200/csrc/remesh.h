@@ -41,9 +41,42 @@ int code_bits(int dim, uint32_t max_index);
 // written out and sorted by node.  Both give the same bits.
 bool dense_route(int dim, const Grid &g, int bits, long n);
 
-// Device stage: particles (array of pointers to cvtx_P3D / cvtx_P2D) -> node set, on
-// `device`.  Returns a cvtx_b200_status; fills grid and nodes on success.
-int device_nodes(int device, int dim, int kind, float h, const void *const *particles, long n, Grid *grid, NodeSet *nodes);
+// The host-array entry points on `device`: particles (array of pointers to cvtx_P3D / cvtx_P2D)
+// in, created particles out (out_rows may be null: count only).  Node build and pruning both
+// run on the device; the result is the host stage's, bit for bit.  Returns a cvtx_b200_status.
+int device_redistribute_from_host(int device, int dim, int kind, float h, const void *const *particles, long n, float negligible,
+                                  void *out_rows, int max_out, int *n_out, size_t *n_nodes);
+
+// The order in which the pruning stage forms its FP64 sums (mean strength, dropped vorticity),
+// on the device (block_reduce in remesh_device.cu: a shuffle tree per warp, warps in order,
+// blocks in order) and, through this function, on the host: elements in blocks of 256; inside a
+// block eight 32-element trees (a[l] += a[l + o] for o = 16, 8, 4, 2, 1), their results added in
+// order; block sums added in block order.  Elements past n count as 0.  One order everywhere
+// is what lets the device prune for the host-array entry points and still return the host
+// stage's bits.
+template <class Get>
+double canonical_sum(long n, Get &&get) {
+	const long blocks = (n + 255) / 256;
+	std::vector<double> part((size_t)blocks);
+#pragma omp parallel for schedule(static) if (blocks > 64)
+	for (long b = 0; b < blocks; ++b) {
+		double block = 0.0;
+		for (int w = 0; w < 8; ++w) {
+			double a[32];
+			for (int l = 0; l < 32; ++l) {
+				const long i = b * 256 + w * 32 + l;
+				a[l] = i < n ? (double)get(i) : 0.0;
+			}
+			for (int o = 16; o > 0; o >>= 1)
+				for (int l = 0; l < o; ++l) a[l] += a[l + o];
+			block = w == 0 ? a[0] : block + a[0];
+		}
+		part[(size_t)b] = block;
+	}
+	double total = 0.0;
+	for (long b = 0; b < blocks; ++b) total += part[(size_t)b];
+	return total;
+}
 
 // Device-resident redistribution (the additive cvtx_b200_redistribute of cvtx_b200.h): rows_dev
 // in, out_dev (capacity max_out rows, may be null = count only) out, both on `device`.

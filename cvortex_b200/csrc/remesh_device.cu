@@ -241,18 +241,7 @@ __global__ void __launch_bounds__(kBlock) collect_nodes(const uint32_t *__restri
 
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-// Pinned staging -> the caller's vectors, in parallel pieces; codes are widened to 64
-// bits on the way when the device used 32.
-template <class K>
-void fetch_codes(uint64_t *dst, const K *src, size_t n) {
-	const size_t piece = 1 << 18;
-	const long pieces = (long)((n + piece - 1) / piece);
-#pragma omp parallel for schedule(static) num_threads(4) if (pieces > 4)
-	for (long p = 0; p < pieces; ++p) {
-		const size_t lo = (size_t)p * piece, hi = lo + piece < n ? lo + piece : n;
-		for (size_t i = lo; i < hi; ++i) dst[i] = (uint64_t)src[i];
-	}
-}
+// Pinned staging -> the caller's array, in parallel 1 MiB pieces.
 void fetch_bytes(void *dst, const void *src, size_t bytes) {
 	const size_t piece = 1 << 20;
 	const long pieces = (long)((bytes + piece - 1) / piece);
@@ -266,7 +255,7 @@ void fetch_bytes(void *dst, const void *src, size_t bytes) {
 enum { ROWS, COUNT, OFFSET, CODE_A, CODE_B, REC_A, REC_B, SHARE, TEMP, FIRST, SUMS,        // node build
        PARTIAL, STRENGTH, KEEP, POSITION, CODE_C, SUMS_C, HISTOGRAM,                       // device-resident pruning
        CELL_A, CELL_B, ORDER_A, ORDER_B, SORTED_ROWS, CELL_START, EXISTS, DENSE_POS, DENSE,     // cell order, dense route
-       RELAX_POINTS, RELAX_FIELD };                                                        // relaxation
+       RELAX_POINTS, RELAX_FIELD, OUT_ROWS };                                              // relaxation, host-array result
 
 // Node build on rows that are already on the device.  On return (stream synchronised)
 // node_code[0..n_nodes) and sums[0..n_nodes * COMPS) hold the nodes in ascending code order.
@@ -398,44 +387,13 @@ int build_nodes(Device *d, cudaStream_t st, const float *rows_in, long n, const 
 	return CVTX_B200_OK;
 }
 
-// The public-ABI route: rows from pinned host staging, node set back to the host.
-template <int D, class K>
-int run(Device *d, cudaStream_t st, const float *rows_host, long n, const Grid &g, int bits, NodeSet *nodes) {
-	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
-	Buffer *b = d->remesh;
-	CUDA_TRY(b[ROWS].reserve(sizeof(float) * ROW * (size_t)n));
-	float *rows = (float *)b[ROWS].p;
-	CUDA_TRY(cudaMemcpyAsync(rows, rows_host, sizeof(float) * ROW * (size_t)n, cudaMemcpyHostToDevice, st));
-	K *node_code = nullptr;
-	float *sums = nullptr;
-	uint32_t n_nodes = 0;
-	nodes->code.clear();
-	nodes->strength.clear();
-	if (int rc = build_nodes<D, K>(d, st, rows, n, g, bits, &node_code, &sums, &n_nodes)) return rc;
-	if (n_nodes == 0) return CVTX_B200_OK;
-
-	// results: pinned staging first (a pageable destination would be bounced by the driver)
-	HostStage &hs = host_stage();
-	const size_t code_bytes = sizeof(K) * (size_t)n_nodes, sum_bytes = sizeof(float) * COMPS * (size_t)n_nodes;
-	const size_t sums_at = (code_bytes + 15) & ~(size_t)15;
-	CUDA_TRY(hs.out.reserve(sums_at + sum_bytes));
-	CUDA_TRY(cudaMemcpyAsync(hs.out.p, node_code, code_bytes, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + sums_at, sums, sum_bytes, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
-	nodes->code.resize(n_nodes);
-	nodes->strength.resize((size_t)n_nodes * COMPS);
-	fetch_codes<K>(nodes->code.data(), (const K *)hs.out.p, n_nodes);
-	fetch_bytes(nodes->strength.data(), (const char *)hs.out.p + sums_at, sum_bytes);
-	return CVTX_B200_OK;
-}
-
 // ---- device-resident redistribution: bounds and pruning on the device ---------------------
 // Block-level partial results are combined on the host in block order, so a result never
 // depends on scheduling.  FP64 sums are formed in a different (tree) order than the host
 // stage's, which can only matter when a rounded mean falls within an ulp of a threshold.
 
 struct Bounds { float lo[3], hi[3]; double sum[3]; };
-constexpr int kRowsPerBlock = kBlock * 16;
+constexpr int kRowsPerBlock = kBlock;      // one row per thread: the canonical sum order of remesh.h
 
 template <class T, class Op>
 __device__ T block_reduce(T v, Op op, T *scratch /* kBlock / 32 */) {
@@ -602,16 +560,20 @@ int strengths_on_device(Device *d, cudaStream_t st, const float *w, uint32_t n, 
 	return CVTX_B200_OK;
 }
 
+// out: the caller's device array (capacity max_out rows), or -- own_out set -- an internal
+// buffer sized to the result, returned through *own_out (the host-array entry points, which
+// copy it back).  want_rows = false asks for the count only.  *nodes_out: nodes before pruning.
 template <int D, class K>
 int redistribute_resident(Device *d, cudaStream_t st, const float *rows, long n, const Grid &g, int bits, float negligible, float *out,
-                          int max_out, int *n_out) {
-	constexpr int COMPS = Layout<D>::COMPS;
+                          float **own_out, bool want_rows, int max_out, int *n_out, size_t *nodes_out) {
+	constexpr int ROW = Layout<D>::ROW, COMPS = Layout<D>::COMPS;
 	Buffer *b = d->remesh;
 	K *code = nullptr;
 	float *w = nullptr;
 	uint32_t n_nodes = 0;
 	*n_out = 0;
 	if (int rc = build_nodes<D, K>(d, st, rows, n, g, bits, &code, &w, &n_nodes)) return rc;
+	if (nodes_out) *nodes_out = n_nodes;
 	if (n_nodes == 0) return CVTX_B200_OK;
 
 	double total = 0.0;
@@ -621,7 +583,7 @@ int redistribute_resident(Device *d, cudaStream_t st, const float *rows, long n,
 	uint32_t kept = 0;
 	if (int rc = cut_on_device<COMPS>(d, st, w, n_nodes, (float)(total / (double)n_nodes) * negligible, n_nodes, &each, &kept)) return rc;
 	*n_out = (int)kept;
-	if (!out || kept == 0) return CVTX_B200_OK;
+	if (!want_rows || kept == 0) return CVTX_B200_OK;
 
 	if ((long)kept > (long)max_out) {
 		// too many for the caller's array: materialise the survivors, find the strength that fits
@@ -658,6 +620,10 @@ int redistribute_resident(Device *d, cudaStream_t st, const float *rows, long n,
 		*n_out = (int)kept;
 		if (kept == 0) return CVTX_B200_OK;
 	}
+	if (own_out) {
+		CUDA_TRY(b[OUT_ROWS].reserve(sizeof(float) * ROW * (size_t)kept));
+		out = *own_out = (float *)b[OUT_ROWS].p;
+	}
 	const float size = D == 3 ? g.h * g.h * g.h : g.h * g.h;
 	write_rows_kernel<D, K><<<blocks_for(n_nodes), kBlock, 0, st>>>(code, w, (const uint32_t *)b[KEEP].p, (const uint32_t *)b[POSITION].p, n_nodes,
 	                                                                each, g, size, out);
@@ -669,10 +635,13 @@ int redistribute_resident(Device *d, cudaStream_t st, const float *rows, long n,
 
 }  // namespace
 
-int device_nodes(int device, int dim, int kind, float h, const void *const *particles, long n, Grid *grid, NodeSet *nodes) {
+int device_redistribute_from_host(int device, int dim, int kind, float h, const void *const *particles, long n, float negligible,
+                                  void *out_rows, int max_out, int *n_out, size_t *n_nodes) {
 	if (dim != 2 && dim != 3) return fail(CVTX_B200_ERR_ARGUMENT, "dimension must be 2 or 3");
 	if (kind < 0 || kind >= K_COUNT) return fail(CVTX_B200_ERR_ARGUMENT, "unknown redistribution function");
-	if (n <= 0 || n > 0x7ffffff0L) return fail(CVTX_B200_ERR_ARGUMENT, "bad particle count");
+	if (n <= 0 || n > 0x7ffffff0L || !n_out) return fail(CVTX_B200_ERR_ARGUMENT, "bad particle count");
+	*n_out = 0;
+	if (n_nodes) *n_nodes = 0;
 	cudaStream_t st = nullptr;
 	if (int rc = device_stream(device, &st)) return rc;
 	Device *d = get_device(device);
@@ -684,9 +653,8 @@ int device_nodes(int device, int dim, int kind, float h, const void *const *part
 	std::lock_guard<std::mutex> stage_lock(hs.mu);
 	CUDA_TRY(hs.src.reserve(sizeof(float) * row_floats * (size_t)n));
 	const double t0 = omp_get_wtime();
-	const float *rows = (const float *)hs.src.p;
 	uint32_t max_index = 0;
-	*grid = place_grid(dim, kind, kHalfWidth[kind], h, particles, (float *)hs.src.p, n, row_floats, &max_index);
+	const Grid g = place_grid(dim, kind, kHalfWidth[kind], h, particles, (float *)hs.src.p, n, row_floats, &max_index);
 	const int bits = code_bits(dim, max_index);
 	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
 	if ((double)n * (dim == 3 ? 125.0 : 25.0) > 2147483647.0) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles for one redistribution call (2^31 shares)");
@@ -694,12 +662,30 @@ int device_nodes(int device, int dim, int kind, float h, const void *const *part
 	std::lock_guard<std::mutex> device_lock(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	const double t1 = omp_get_wtime();
+	CUDA_TRY(d->remesh[ROWS].reserve(sizeof(float) * row_floats * (size_t)n));
+	float *rows = (float *)d->remesh[ROWS].p, *result = nullptr;
+	CUDA_TRY(cudaMemcpyAsync(rows, hs.src.p, sizeof(float) * row_floats * (size_t)n, cudaMemcpyHostToDevice, st));
+	const bool want = out_rows != nullptr;
 	int rc;
-	if (bits <= 32) rc = dim == 3 ? run<3, uint32_t>(d, st, rows, n, *grid, bits, nodes) : run<2, uint32_t>(d, st, rows, n, *grid, bits, nodes);
-	else rc = dim == 3 ? run<3, uint64_t>(d, st, rows, n, *grid, bits, nodes) : run<2, uint64_t>(d, st, rows, n, *grid, bits, nodes);
-	if (trace) std::fprintf(stderr, "cvortex trace:   gather + grid %.3f ms, H2D + kernels + D2H %.3f ms (%d-bit codes)\n", (t1 - t0) * 1e3,
-	                        (omp_get_wtime() - t1) * 1e3, bits <= 32 ? 32 : 64);
-	return rc;
+	if (bits <= 32)
+		rc = dim == 3 ? redistribute_resident<3, uint32_t>(d, st, rows, n, g, bits, negligible, nullptr, &result, want, max_out, n_out, n_nodes)
+		              : redistribute_resident<2, uint32_t>(d, st, rows, n, g, bits, negligible, nullptr, &result, want, max_out, n_out, n_nodes);
+	else
+		rc = dim == 3 ? redistribute_resident<3, uint64_t>(d, st, rows, n, g, bits, negligible, nullptr, &result, want, max_out, n_out, n_nodes)
+		              : redistribute_resident<2, uint64_t>(d, st, rows, n, g, bits, negligible, nullptr, &result, want, max_out, n_out, n_nodes);
+	if (rc) return rc;
+	const double t2 = omp_get_wtime();
+	if (want && *n_out > 0) {
+		// the created particles: pinned staging first (a pageable destination would be bounced by the driver)
+		const size_t bytes = sizeof(float) * row_floats * (size_t)*n_out;
+		CUDA_TRY(hs.out.reserve(bytes));
+		CUDA_TRY(cudaMemcpyAsync(hs.out.p, result, bytes, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		fetch_bytes(out_rows, hs.out.p, bytes);
+	}
+	if (trace) std::fprintf(stderr, "cvortex trace:   gather + grid %.3f ms, H2D + kernels %.3f ms, D2H + copy out %.3f ms (%d-bit codes)\n", (t1 - t0) * 1e3,
+	                        (t2 - t1) * 1e3, (omp_get_wtime() - t2) * 1e3, bits <= 32 ? 32 : 64);
+	return CVTX_B200_OK;
 }
 
 int device_redistribute(int device, void *stream, int dim, int kind, const float *rows_dev, long n, float h, float negligible, float *out_dev,
@@ -738,11 +724,12 @@ int device_redistribute(int device, void *stream, int dim, int kind, const float
 	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
 	if ((double)n * (dim == 3 ? 125.0 : 25.0) > 2147483647.0) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles for one redistribution call (2^31 shares)");
 
+	const bool want = out_dev != nullptr;
 	if (bits <= 32)
-		return dim == 3 ? redistribute_resident<3, uint32_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out)
-		                : redistribute_resident<2, uint32_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out);
-	return dim == 3 ? redistribute_resident<3, uint64_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out)
-	                : redistribute_resident<2, uint64_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, max_out, n_out);
+		return dim == 3 ? redistribute_resident<3, uint32_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, nullptr, want, max_out, n_out, nullptr)
+		                : redistribute_resident<2, uint32_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, nullptr, want, max_out, n_out, nullptr);
+	return dim == 3 ? redistribute_resident<3, uint64_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, nullptr, want, max_out, n_out, nullptr)
+	                : redistribute_resident<2, uint64_t>(d, st, rows_dev, n, g, bits, negligible, out_dev, nullptr, want, max_out, n_out, nullptr);
 }
 
 }  // namespace remesh
