@@ -344,8 +344,7 @@ float strength_cut(const std::vector<float> &s, int n, int wanted) {
 	    [&](double lo, double range, int *count) {
 		    for (int i = 0; i < kCutBins; ++i) count[i] = 0;
 		    for (int i = 0; i < n; ++i) {
-			    const int b = (int)std::floor((double)(kCutBins - 1) * (s[i] - lo) / range);
-			    ++count[b < 0 ? 0 : (b >= kCutBins ? kCutBins - 1 : b)];
+			    ++count[cut_bin(std::floor((double)(kCutBins - 1) * (s[i] - lo) / range))];
 		    }
 	    });
 }

@@ -87,9 +87,8 @@ int device_redistribute(int device, void *stream, int dim, int kind, const float
 // histograms of [min, max], zooming into the bin where the count from the top crosses
 // `wanted` (reference src/redistribution_helper_funcs.cpp:32-91, same arithmetic).  The
 // data stay with the caller: minmax(&min, &max) and histogram(lo, range, counts[1024]) --
-// bin = floor(1023 (s - lo) / range) in FP64, clamped to [0, 1023] -- are supplied by the
+// bin = cut_bin(floor(1023 (s - lo) / range)) in FP64 (remesh_math.h) -- are supplied by the
 // host stage (a loop) and by the device stage (kernels), so both take the same decisions.
-constexpr int kCutBins = 1024;
 template <class MinMax, class Histogram>
 float strength_cut_with(int n, int wanted, MinMax &&minmax, Histogram &&histogram) {
 	float fmin = 0.f, fmax = 0.f;

@@ -505,8 +505,7 @@ __global__ void __launch_bounds__(kBlock) histogram_kernel(const float *__restri
 	__syncthreads();
 	for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
 		const double t = floor(__ddiv_rn(__dmul_rn((double)(kCutBins - 1), __dsub_rn((double)strength[i], lo)), range));
-		const int b = t < 0.0 ? 0 : (t >= (double)kCutBins ? kCutBins - 1 : (t == t ? (int)t : 0));
-		atomicAdd(&local[b], 1);
+		atomicAdd(&local[cut_bin(t)], 1);
 	}
 	__syncthreads();
 	for (int b = threadIdx.x; b < kCutBins; b += kBlock) if (local[b]) atomicAdd(&count[b], local[b]);

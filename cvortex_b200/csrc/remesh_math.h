@@ -124,6 +124,18 @@ RM_HD uint64_t cell_of(const float *row, const Grid &g) {
 	return lin;
 }
 
+// Bin of the strength-threshold histogram (reference src/redistribution_helper_funcs.cpp:56-61):
+// t = floor(1023 (s - lo) / range) is converted with a C cast there, clamped to [0, 1023]
+// afterwards.  Once the search has zoomed in, strong particles give t far beyond INT_MAX; on
+// x86-64 the cast then yields INT_MIN and they are counted in bin 0, not in the top bin -- which
+// steers the search, so it is reproduced here explicitly (also for NaN) on host and device alike.
+constexpr int kCutBins = 1024;
+RM_HD int cut_bin(double t) {
+	if (!(t >= -2147483648.0 && t < 2147483648.0)) return 0;
+	const int b = (int)t;
+	return b < 0 ? 0 : (b >= kCutBins ? kCutBins - 1 : b);
+}
+
 // Morton codes: bit b of x lands at D*b, of y at D*b+1, of z at D*b+2.
 constexpr int kBits3D = 21;   // 63-bit code
 RM_HD uint64_t spread3(uint64_t v) {   // 21 bits -> every third bit
