@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../../include/cvtx_b200.h"
 #include "m2m_kernel.cuh"
@@ -29,6 +30,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_T{0}, g_force_chunks{0};
+std::atomic<int> g_guarded_only{-1};                           // -1 = not set: CVTX_B200_GUARDED decides, read once
 std::mutex g_devices_mu;
 std::vector<Device *> g_devices;
 int g_device_count = -2;                                       // -2 = not probed yet
@@ -143,6 +145,22 @@ Plan make_plan(int n_src, int n_tgt, int n_out, int sm_count, int pref_T) {
 	return p;
 }
 
+// Chains shorter than this many tiles per target are evaluated in the guarded form straight away:
+// a self-interaction call re-evaluates one chain per target, which is noise among thousands of
+// chains and half the work among two.
+constexpr int kMinTilesOptimistic = 16;
+
+// 0 = by size (the default), 1 = guarded form only, 2 = optimistic form at any size
+int guard_mode() {
+	int v = g_guarded_only.load();
+	if (v < 0) {
+		const char *e = getenv("CVTX_B200_GUARDED");
+		v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+		g_guarded_only = v;
+	}
+	return v;
+}
+
 struct Launcher {
 	M2MArgs args; Plan plan; cudaStream_t st; cudaError_t err;
 	template <class P> void run() {
@@ -255,6 +273,8 @@ unsigned long long cvtx_b200_kernel_launches(void) { return g_launches.load(); }
 
 void cvtx_b200_tune(int force_T, int force_chunks) { g_force_T = force_T; g_force_chunks = force_chunks; }
 
+void cvtx_b200_guarded_only(int mode) { g_guarded_only = (mode == 1 || mode == 2) ? mode : 0; }
+
 const char *cvtx_b200_last_error(void) { return g_err.c_str(); }
 
 float cvtx_b200_last_pair_kernel_ms(int device) {
@@ -324,6 +344,8 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	L.args.out = out;
 	L.args.partial = (double *)d->partial.p;
 	L.args.k = ck.k;
+	const int gm = guard_mode();
+	L.args.exact_only = (gm == 1 || (gm == 0 && n_src_tiles < kMinTilesOptimistic)) ? 1 : 0;
 	L.plan = plan;
 	L.st = st;
 	CUDA_TRY(cudaEventRecord(d->k_start, st));

@@ -18,6 +18,11 @@
 //   running sums are FP32 per chain (a tile, or Policy::CHAIN sources) and
 //   are flushed into FP64 accumulators, matching the reference CPU path's
 //   double accumulation (src/P3D.cpp:237-249) at ~0.1 % extra instructions;
+//   ops whose coincident-pair / non-finite guards only ever replace an inf or a
+//   NaN (Policy::OPTIMISTIC, pair_math.cuh "GUARDS") run the pair loop without
+//   them and check the FP32 running sums once per chain; a chain that comes out
+//   non-finite is evaluated again with the guards (bit-identical results, and
+//   2-6 ALU-pipe instructions fewer per pair);
 //   the epilogue applies Policy::finish() in FP64 and either writes the
 //   final floats (one chunk) or FP64 partials that reduce_partials_kernel
 //   adds in a fixed order (deterministic, no atomics).
@@ -47,6 +52,7 @@ struct M2MArgs {
 	float *out;                // final result, Policy::NOUT floats per target (gridDim.y == 1)
 	double *partial;           // [gridDim.y][n_tgt][NOUT] FP64 partials (gridDim.y > 1)
 	PairConsts k;
+	int exact_only;            // 1: always evaluate the guarded pair form (never the optimistic one)
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 	// the large-problem geometries it would cost the Gaussian kernels 0.8 % for a tail that is
 	// one block in a thousand.
 	const bool idle_warp = T == 1 && (long)blockIdx.x * (B * T) + (tid & ~31) >= (long)args.n_tgt;
+	const bool optimistic = P::OPTIMISTIC && !args.exact_only;
 
 	for (int it = 0; it < ntile; ++it) {
 		const int buf = it & 1;
@@ -157,13 +164,42 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 				for (int v = 0; v < NV; ++v)
 #pragma unroll
 					for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+				bool guarded = true;
+				if (P::OPTIMISTIC && optimistic) {
 #pragma unroll UNROLL
-				for (int j = 0; j < CHAIN; ++j) {
-					const float4 a = sA[j0 + j];
-					float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-					if (P::NSRC4 == 2) b = sB[j0 + j];
+					for (int j = 0; j < CHAIN; ++j) {
+						const float4 a = sA[j0 + j];
+						float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+						if (P::NSRC4 == 2) b = sB[j0 + j];
 #pragma unroll
-					for (int v = 0; v < NV; ++v) P::template pair<W>(tg[v], a, b, acc[v], args.k);
+						for (int v = 0; v < NV; ++v) P::template pair<W, false>(tg[v], a, b, acc[v], args.k);
+					}
+					// inf and NaN survive any further addition, so one sum over this thread's running sums
+					// tells whether a guard would have fired anywhere in the chain (a sum of finite values
+					// that overflows only costs a needless second evaluation)
+					Vec<W> chk = acc[0][0];
+#pragma unroll
+					for (int v = 0; v < NV; ++v)
+#pragma unroll
+						for (int c = (v == 0 ? 1 : 0); c < P::NACC; ++c) chk = vadd(chk, acc[v][c]);
+					const float s = W == 2 ? chk.lane(0) + chk.lane(1) : chk.lane(0);
+					guarded = !(fabsf(s) <= 3.40282346e38f);
+					if (guarded) {
+#pragma unroll
+						for (int v = 0; v < NV; ++v)
+#pragma unroll
+							for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+					}
+				}
+				if (guarded) {
+#pragma unroll UNROLL
+					for (int j = 0; j < CHAIN; ++j) {
+						const float4 a = sA[j0 + j];
+						float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+						if (P::NSRC4 == 2) b = sB[j0 + j];
+#pragma unroll
+						for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+					}
 				}
 #pragma unroll
 				for (int t = 0; t < T; ++t)
@@ -218,13 +254,15 @@ __global__ void reduce_partials_wide_kernel(const double *__restrict__ partial, 
 	if (lane == 0) out[i] = (float)s;
 }
 
-// Raw rows -> packed float4 records, zero-padded to n_pad (a multiple of kSrcTile).
+// Raw rows -> packed float4 records, padded with zero-strength records (pad_source) to n_pad, a
+// multiple of kSrcTile.
 __global__ void pack_sources_kernel(int kind, int cols, const float *__restrict__ rows, int n, int n_pad,
                                     float4 *__restrict__ A, float4 *__restrict__ Bq)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_pad) return;
-	float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+	float4 a, b;
+	pad_source(kind, a, b);
 	if (i < n) {
 		float row[7];
 		for (int c = 0; c < cols; ++c) row[c] = rows[(size_t)i * cols + c];

@@ -42,6 +42,22 @@
 // pair is dropped when r^2 == 0.  For formulas that are regular at r = 0 and
 // carry a factor `rad` the rule holds with no test at all.
 //
+// GUARDS and the optimistic path.  The test costs a compare and one or two
+// selects per pair, and on sm_100 those issue to the 16-lane ALU pipe: measured
+// over all ops, every ALU instruction in the pair loop costs about as much as two
+// FP32 lane-ops.  Where the UNguarded formula is singular
+// -- rsqrt(0) / rcp(0) = inf, so the dropped pair's term comes out as inf or NaN
+// -- the guard is redundant as a detector: pair<W, false>() omits it, the kernel
+// looks at the FP32 running sums once per chain (256 sources) and, if any of
+// them is not finite, discards the chain and evaluates it again with
+// pair<W, true>().  A non-finite value can never be absorbed by later
+// additions, so every chain in which a guard would have fired is re-evaluated,
+// and in all other chains the two forms execute the same instructions on the
+// same values: results are bit-identical with the guarded path (the tests pin
+// this).  Policies advertise it as OPTIMISTIC; guards whose unguarded value is
+// finite (Winckelmans stretching, the viscous ops, the planetary core, the
+// vorticity box cutoff) are real selections and stay in both forms.
+//
 // Each policy exposes
 //   NSRC4   float4 records per packed source (1 or 2)
 //   TCOLS   floats per raw target row in global memory
@@ -60,7 +76,8 @@
 //   LANE_OPS, SFU_OPS   algorithmic FP32 lane-ops / MUFU ops per pair of THIS
 //                       formulation (FMA = 1 lane-op; compares/selects not
 //                       counted) -- the roofline denominators, see DESIGN.md
-//   load_target(row, tg[]), pair<W>(tg, a, b, acc, k), finish(row, acc, out, k)
+//   OPTIMISTIC  pair<W, false>() exists and differs from pair<W, true>() (see GUARDS)
+//   load_target(row, tg[]), pair<W, G>(tg, a, b, acc, k), finish(row, acc, out, k)
 // and is usable from host code too (tests/hostcheck compiles this header with
 // g++ to validate the algebra against the oracle without a GPU; MUFU ops are
 // then replaced by libm and FP32x2 by two scalar lanes).
@@ -109,6 +126,17 @@ CVTX_HD float mufu_ex2(float x) {
 #endif
 }
 
+// max(|a|, |b|, |c|), NaN if any input is: one FMNMX3 on sm_100 instead of three compares, so that
+// `max3_abs(..) < c` is  |a| < c && |b| < c && |c| < c  for every input including NaNs
+CVTX_HD float max3_abs(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+	float y; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(fabsf(a)), "f"(fabsf(b)), "f"(fabsf(c))); return y;
+#else
+	if (a != a || b != b || c != c) return NAN;
+	return fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(c));
+#endif
+}
+
 // ---- Vec<W>: W FP32 lanes -----------------------------------------------------
 template <int W> struct Vec;
 
@@ -140,10 +168,20 @@ template <int W> CVTX_HD Vec<W> bc(float s) {
 
 // fused a*b + c, a*b, a + b, a - b, -a  (FFMA2 / FMUL2 / FADD2 when W = 2;
 // negations fold into the instructions' operand modifiers)
+// (the scalar forms use the _rn intrinsics on the device so that nvcc never contracts a
+// product into a following sum: the guarded and the optimistic pair forms, and the
+// W = 1 and W = 2 forms, must round identically)
+#if defined(__CUDA_ARCH__)
+CVTX_HD Vec<1> vfma(Vec<1> a, Vec<1> b, Vec<1> c) { Vec<1> r; r.x = __fmaf_rn(a.x, b.x, c.x); return r; }
+CVTX_HD Vec<1> vmul(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = __fmul_rn(a.x, b.x); return r; }
+CVTX_HD Vec<1> vadd(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = __fadd_rn(a.x, b.x); return r; }
+CVTX_HD Vec<1> vsub(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = __fsub_rn(a.x, b.x); return r; }
+#else
 CVTX_HD Vec<1> vfma(Vec<1> a, Vec<1> b, Vec<1> c) { Vec<1> r; r.x = fmaf(a.x, b.x, c.x); return r; }
 CVTX_HD Vec<1> vmul(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = a.x * b.x; return r; }
 CVTX_HD Vec<1> vadd(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = a.x + b.x; return r; }
 CVTX_HD Vec<1> vsub(Vec<1> a, Vec<1> b) { Vec<1> r; r.x = a.x - b.x; return r; }
+#endif
 CVTX_HD Vec<1> vneg(Vec<1> a) { Vec<1> r; r.x = -a.x; return r; }
 CVTX_HD Vec<2> vneg(Vec<2> a) { Vec<2> r; r.v.x = -a.v.x; r.v.y = -a.v.y; return r; }
 #if defined(__CUDA_ARCH__)
@@ -178,6 +216,12 @@ template <int W> CVTX_HD Vec<W> keep_if_pos(Vec<W> c, Vec<W> v) {
 	Vec<W> r;
 	for (int i = 0; i < W; ++i) r.set(i, c.lane(i) > 0.0f ? v.lane(i) : 0.0f);
 	return r;
+}
+// the same rule where the unguarded v is inf / NaN whenever the rule would fire: G = false
+// (optimistic path) hands v through and leaves the detection to the kernel
+template <bool G, int W> CVTX_HD Vec<W> drop_if_coincident(Vec<W> c, Vec<W> v) {
+	if (G) return keep_if_pos(c, v);
+	return v;
 }
 // c < thr ? a : b
 template <int W> CVTX_HD Vec<W> pick_if_less(Vec<W> c, float thr, Vec<W> a, Vec<W> b) {
@@ -221,12 +265,13 @@ template <> struct Reg3D<REG_WINCKELMANS> {
 	// c0 = 1/sigma^2, c1 = -3/sigma^4, c2 = -10.5/sigma^2.
 	// A = sigma^3 g/r^3 = g/rho^3.  Bn = -(3 rho^2 + 10.5)(rho^2+1)^-7/2 / sigma^2.
 	static constexpr int A_OPS = 6, AB_OPS = 9, SFU = 1;
-	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
+	static constexpr bool POISONS = false;      // regular at r = 0: nothing to detect, the one guard below is a real selection
+	template <int W, bool G> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
 		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.5f);
 		const Vec<W> ra = vrsqrt(a), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2);
 		return vmul(b, vmul(ra4, ra));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
+	template <int W, bool G> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.5f), b2 = vfma(r2, k.c1, k.c2);
 		const Vec<W> ra = vrsqrt(a), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2), ra5 = vmul(ra4, ra);
 		// the self pair must give exactly 0: c = w_t x w_t formed with FMAs is
@@ -244,14 +289,15 @@ template <> struct Reg3D<REG_WINCKELMANS> {
 template <> struct Reg3D<REG_SINGULAR> {
 	// A = 1/r^3, Bn = -3/r^5; both dropped at r = 0.
 	static constexpr int A_OPS = 2, AB_OPS = 4, SFU = 1;
-	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &) {
+	static constexpr bool POISONS = true;       // unguarded at r = 0: rsqrt(0) = inf in every factor
+	template <int W, bool G> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &) {
 		const Vec<W> ri = vrsqrt(r2);
-		return keep_if_pos(r2, vmul(vmul(ri, ri), ri));
+		return drop_if_coincident<G>(r2, vmul(vmul(ri, ri), ri));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
+	template <int W, bool G> CVTX_HD static void AB(Vec<W> r2, const PairConsts &, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> ri = vrsqrt(r2), ri2 = vmul(ri, ri), ri3 = vmul(ri2, ri);
-		A_ = keep_if_pos(r2, ri3);
-		B1 = keep_if_pos(r2, vmul(ri2, -3.0f));
+		A_ = drop_if_coincident<G>(r2, ri3);
+		B1 = drop_if_coincident<G>(r2, vmul(ri2, -3.0f));
 		B2 = A_;
 	}
 	static void consts(PairConsts &, double) {}
@@ -262,11 +308,12 @@ template <> struct Reg3D<REG_PLANETARY> {
 	// rho < 1: g = rho^3, zeta = 3  ->  A = 1/sigma^3, Bn = 0;  else singular.
 	// c0 = sigma^2, c1 = 1/sigma^3.
 	static constexpr int A_OPS = 2, AB_OPS = 4, SFU = 1;
-	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
+	static constexpr bool POISONS = false;      // the core test is a selection between two finite values
+	template <int W, bool G> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
 		const Vec<W> ri = vrsqrt(r2);
 		return pick_if_less(r2, k.c0, bc<W>(k.c1), vmul(vmul(ri, ri), ri));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
+	template <int W, bool G> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> ri = vrsqrt(r2), ri2 = vmul(ri, ri), ri3 = vmul(ri2, ri);
 		A_ = pick_if_less(r2, k.c0, keep_if_pos(r2, bc<W>(k.c1)), ri3);        // exact 0 for the self pair, as above
 		B1 = pick_if_less(r2, k.c0, bc<W>(0.0f), vmul(ri2, -3.0f));
@@ -280,22 +327,23 @@ template <> struct Reg3D<REG_GAUSSIAN> {
 	// c0 = p/(sqrt2 sigma), c1 = -log2(e)/(2 sigma^2), c2 = sqrt(2/pi)/sigma,
 	// c3 = sqrt(2/pi)/sigma^3.   A = g/r^3,  Bn = (c3 e - 3A)/r^2.
 	static constexpr int A_OPS = 13, AB_OPS = 16, SFU = 3;
-	template <int W> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
+	static constexpr bool POISONS = true;       // unguarded at r = 0: r = 0 * rsqrt(0) = NaN, carried by every factor
+	template <int W, bool G> CVTX_HD static Vec<W> A(Vec<W> r2, const PairConsts &k) {
 		const Vec<W> ri = vrsqrt(r2), r = vmul(r2, ri);
 		const Vec<W> e = vex2(vmul(r2, k.c1));
 		const Vec<W> s = gauss_tail(r, k.c0, k.c2);
 		const Vec<W> g = vfma(vneg(e), s, 1.0f);
-		return keep_if_pos(r2, vmul(g, vmul(vmul(ri, ri), ri)));
+		return drop_if_coincident<G>(r2, vmul(g, vmul(vmul(ri, ri), ri)));
 	}
-	template <int W> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
+	template <int W, bool G> CVTX_HD static void AB(Vec<W> r2, const PairConsts &k, Vec<W> &A_, Vec<W> &B1, Vec<W> &B2) {
 		const Vec<W> ri = vrsqrt(r2), r = vmul(r2, ri), ri2 = vmul(ri, ri);
 		const Vec<W> e = vex2(vmul(r2, k.c1));
 		const Vec<W> s = gauss_tail(r, k.c0, k.c2);
 		const Vec<W> g = vfma(vneg(e), s, 1.0f);
 		const Vec<W> a = vmul(g, vmul(ri2, ri));
-		A_ = keep_if_pos(r2, a);
+		A_ = drop_if_coincident<G>(r2, a);
 		B1 = vfma(A_, -3.0f, vmul(e, k.c3));                                   // from the guarded A: finite at r = 0
-		B2 = keep_if_pos(r2, ri2);
+		B2 = drop_if_coincident<G>(r2, ri2);
 	}
 	static void consts(PairConsts &k, double s) {
 		k.c0 = (float)(0.3275911 * kRecipSqrt2 / s);
@@ -323,10 +371,11 @@ template <int W> CVTX_HD Rad3<W> rad3(const Vec<W> *tg, const f4 a) {
 template <int REG> struct P3DVel {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 15 + Reg3D<REG>::A_OPS, SFU_OPS = Reg3D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // K = inf / NaN meets finite factors: every sum is poisoned
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
-		const Vec<W> K = Reg3D<REG>::A(d.r2, k);
+		const Vec<W> K = Reg3D<REG>::template A<W, G>(d.r2, k);
 		const Vec<W> cx = vfms(d.y, b.z, vmul(d.z, b.y));
 		const Vec<W> cy = vfms(d.z, b.x, vmul(d.x, b.z));
 		const Vec<W> cz = vfms(d.x, b.y, vmul(d.y, b.x));
@@ -356,13 +405,14 @@ template <int REG> struct P3DVel {
 template <int REG> struct P3DDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 22 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // A = inf / NaN enters all three sums through fma(A, c, .)
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
 		Vec<W> A, B1, B2;
-		Reg3D<REG>::AB(d.r2, k, A, B1, B2);
+		Reg3D<REG>::template AB<W, G>(d.r2, k, A, B1, B2);
 		const Vec<W> cx = vfms(tg[4], b.z, vmul(tg[5], b.y));
 		const Vec<W> cy = vfms(tg[5], b.x, vmul(tg[3], b.z));
 		const Vec<W> cz = vfms(tg[3], b.y, vmul(tg[4], b.x));
@@ -397,13 +447,14 @@ template <int REG> struct P3DDvort {
 template <int REG> struct P3DVelDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 6, NOUT = 6, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 31 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
 		Vec<W> A, B1, B2;
-		Reg3D<REG>::AB(d.r2, k, A, B1, B2);
+		Reg3D<REG>::template AB<W, G>(d.r2, k, A, B1, B2);
 		// velocity: A (rad x w_s)          (A is zeroed at r = 0, where rad x w_s = 0 anyway)
 		const Vec<W> ux = vfms(d.y, b.z, vmul(d.z, b.y));
 		const Vec<W> uy = vfms(d.z, b.x, vmul(d.x, b.z));
@@ -459,10 +510,11 @@ template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 template <int REG> struct P3DVisc {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 15 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = false;      // eta(0) is finite: the coincident-pair test is a real selection
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
 	}
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
 		const Vec<W> eta = keep_if_pos(d.r2, Eta3D<REG>::eta(d.r2, k));   // coincident pair contributes nothing
 		// w_s V_t - w_t V_s per pair, one product rounded and one FMA (the reference rounds both
@@ -522,13 +574,14 @@ template <> struct Zeta3D<REG_GAUSSIAN> {     // zeta = sqrt(2/pi) exp(-rho^2/2)
 template <int REG> struct P3DVort {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 9 + Zeta3D<REG>::OPS, SFU_OPS = Zeta3D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = false;      // the box cutoff selects between finite values
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
 		const Vec<W> zeta = Zeta3D<REG>::zeta(d.r2, k);
 		Vec<W> z;
 		for (int i = 0; i < W; ++i) {                          // c3 = 5 sigma: the reference's box cutoff
-			const bool in = fabsf(d.x.lane(i)) < k.c3 && fabsf(d.y.lane(i)) < k.c3 && fabsf(d.z.lane(i)) < k.c3;
+			const bool in = max3_abs(d.x.lane(i), d.y.lane(i), d.z.lane(i)) < k.c3;
 			z.set(i, in ? zeta.lane(i) : 0.0f);
 		}
 		acc[0] = vfma(z, b.x, acc[0]);
@@ -556,13 +609,15 @@ template <int REG> struct P3DVort {
 template <int REG> struct Reg2D;
 template <> struct Reg2D<REG_SINGULAR> {      // K = 1/r^2
 	static constexpr int OPS = 0, SFU = 1;
-	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &) { return keep_if_pos(r2, vrcp(r2)); }
+	static constexpr bool POISONS = true;       // unguarded at r = 0: rcp(0) = inf, times Gamma, times dx = dy = 0
+	template <int W, bool G> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &) { return drop_if_coincident<G>(r2, vrcp(r2)); }
 	static void consts(PairConsts &, double) {}
 	static double scale(double) { return 1.0; }
 };
 template <> struct Reg2D<REG_WINCKELMANS> {   // K = sigma^2 g/r^2 = (rho^2+2)/(rho^2+1)^2
 	static constexpr int OPS = 4, SFU = 1;
-	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
+	static constexpr bool POISONS = false;
+	template <int W, bool G> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
 		const Vec<W> a = vfma(r2, k.c0, 1.0f), b = vfma(r2, k.c0, 2.0f);
 		const Vec<W> ia = vrcp(a);
 		return vmul(b, vmul(ia, ia));
@@ -572,7 +627,8 @@ template <> struct Reg2D<REG_WINCKELMANS> {   // K = sigma^2 g/r^2 = (rho^2+2)/(
 };
 template <> struct Reg2D<REG_PLANETARY> {     // K = rho < 1 ? 1/sigma^2 : 1/r^2
 	static constexpr int OPS = 0, SFU = 1;
-	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
+	static constexpr bool POISONS = false;
+	template <int W, bool G> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
 		return pick_if_less(r2, k.c0, bc<W>(k.c1), vrcp(r2));
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(s * s); k.c1 = (float)(1.0 / (s * s)); }
@@ -580,9 +636,10 @@ template <> struct Reg2D<REG_PLANETARY> {     // K = rho < 1 ? 1/sigma^2 : 1/r^2
 };
 template <> struct Reg2D<REG_GAUSSIAN> {      // K = (1 - exp(-rho^2/2))/r^2
 	static constexpr int OPS = 2, SFU = 2;
-	template <int W> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
+	static constexpr bool POISONS = true;       // unguarded at r = 0: fma(-1, inf, inf) = NaN
+	template <int W, bool G> CVTX_HD static Vec<W> K(Vec<W> r2, const PairConsts &k) {
 		const Vec<W> e = vex2(vmul(r2, k.c0)), ir = vrcp(r2);
-		return keep_if_pos(r2, vfma(vneg(e), ir, ir));
+		return drop_if_coincident<G>(r2, vfma(vneg(e), ir, ir));
 	}
 	static void consts(PairConsts &k, double s) { k.c0 = (float)(-0.5 * kLog2e / (s * s)); }
 	static double scale(double) { return 1.0; }
@@ -591,11 +648,12 @@ template <> struct Reg2D<REG_GAUSSIAN> {      // K = (1 - exp(-rho^2/2))/r^2
 template <int REG> struct P2DVel {
 	static constexpr int NSRC4 = 1, TCOLS = 2, NTGT = 2, NACC = 2, NOUT = 2, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 7 + Reg2D<REG>::OPS, SFU_OPS = Reg2D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = Reg2D<REG>::POISONS;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; }
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
 		const Vec<W> r2 = vfma(dy, dy, vmul(dx, dx));
-		const Vec<W> kg = vmul(Reg2D<REG>::K(r2, k), a.z);
+		const Vec<W> kg = vmul(Reg2D<REG>::template K<W, G>(r2, k), a.z);
 		acc[0] = vfma(kg, dy, acc[0]);
 		acc[1] = vfma(kg, dx, acc[1]);
 	}
@@ -635,8 +693,9 @@ template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFu
 template <int REG> struct P2DVisc {
 	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 2 : 8;
 	static constexpr int LANE_OPS = 7 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
+	static constexpr bool OPTIMISTIC = false;      // eta(0) is finite
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
 		const Vec<W> r2 = vfma(dy, dy, vmul(dx, dx));
 		const Vec<W> eta = keep_if_pos(r2, Eta2D<REG>::eta(r2, k));
@@ -680,8 +739,11 @@ template <int W> CVTX_HD Fil<W> filament_geometry(const Vec<W> *tg, const f4 a, 
 struct F3DVel {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 37, SFU_OPS = 3;
+	// the rule fires when t1 or t2 is inf / NaN; their product is then inf or NaN (inf * 0 = NaN), and so
+	// is every fma(kk, c, acc)
+	static constexpr bool OPTIMISTIC = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
 		const Fil<W> f = filament_geometry(tg, a, b);
 		const Vec<W> cx = vfms(f.py, f.qz, vmul(f.pz, f.qy));
 		const Vec<W> cy = vfms(f.pz, f.qx, vmul(f.px, f.qz));
@@ -690,8 +752,8 @@ struct F3DVel {
 		const Vec<W> t1 = vmul(vrcp(c2), a.w);
 		const Vec<W> t2 = vfms(f.d1, vrsqrt(f.n1), vmul(f.d2, vrsqrt(f.n2)));
 		const Vec<W> kk0 = vmul(t1, t2);
-		Vec<W> kk;
-		for (int i = 0; i < W; ++i) {
+		Vec<W> kk = kk0;
+		if (G) for (int i = 0; i < W; ++i) {
 			const bool ok = (fabsf(t1.lane(i)) <= 3.40282346e38f) && (fabsf(t2.lane(i)) <= 3.40282346e38f);
 			kk.set(i, ok ? kk0.lane(i) : 0.0f);
 		}
@@ -716,8 +778,11 @@ struct F3DVel {
 struct F3DDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 43, SFU_OPS = 3;
+	// the rule fires when A's scalar or B is NaN; a NaN scalar reaches the A sums through fma(sa, r0, acc),
+	// a NaN B reaches the B sum directly
+	static constexpr bool OPTIMISTIC = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
 		const Fil<W> f = filament_geometry(tg, a, b);
 		const Vec<W> xx = vfms(f.py, f.oz, vmul(f.pz, f.oy));                    // X = r1 x r0
 		const Vec<W> xy = vfms(f.pz, f.ox, vmul(f.px, f.oz));
@@ -728,8 +793,8 @@ struct F3DDvort {
 		const Vec<W> sA = vmul(vneg(vmul(t212, a.w)), vmul(rsx, rsx));
 		const Vec<W> t222 = vmul(vmul(x2, rsx), vsub(rs1, rs2));
 		const Vec<W> Bv = vmul(t222, b.w);
-		Vec<W> sa, bv;
-		for (int i = 0; i < W; ++i) {
+		Vec<W> sa = sA, bv = Bv;
+		if (G) for (int i = 0; i < W; ++i) {
 			const bool ok = (sA.lane(i) == sA.lane(i)) && (Bv.lane(i) == Bv.lane(i));
 			sa.set(i, ok ? sA.lane(i) : 0.0f);
 			bv.set(i, ok ? Bv.lane(i) : 0.0f);

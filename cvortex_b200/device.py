@@ -64,6 +64,7 @@ class DeviceBackend:
         lib.cvtx_b200_kernel_launches.restype = C.c_ulonglong
         lib.cvtx_b200_last_pair_kernel_ms.restype, lib.cvtx_b200_last_pair_kernel_ms.argtypes = f, [i]
         lib.cvtx_b200_tune.restype, lib.cvtx_b200_tune.argtypes = None, [i, i]
+        lib.cvtx_b200_guarded_only.restype, lib.cvtx_b200_guarded_only.argtypes = None, [i]
         lib.cvtx_b200_last_dispatch.restype = i
         lib.cvtx_b200_last_devices_used.restype = i
         lib.cvtx_b200_last_error.restype = C.c_char_p
@@ -113,6 +114,11 @@ class DeviceBackend:
 
     def tune(self, tgt_per_thread: int = 0, chunks: int = 0) -> None:
         self.lib.cvtx_b200_tune(tgt_per_thread, chunks)
+
+    def guarded_only(self, mode: int) -> None:
+        """Tests / experiments (cvtx_b200_guarded_only): 1 = every chain in the guarded pair form,
+        2 = the optimistic form at any size, 0 = the default (optimistic from 16 source tiles up)."""
+        self.lib.cvtx_b200_guarded_only(int(mode))
 
     def last_dispatch(self) -> int:
         return int(self.lib.cvtx_b200_last_dispatch())

@@ -153,6 +153,15 @@ CVTX_B200_API float cvtx_b200_last_pair_kernel_ms(int device);
 /* Experiments only: force targets-per-thread (1, 2, 4; 0 = planner) and the
  * number of source chunks (0 = planner). */
 CVTX_B200_API void cvtx_b200_tune(int force_tgt_per_thread, int force_chunks);
+/* Experiments and tests only.  Ops whose coincident-pair / non-finite tests can
+ * only ever replace an inf or a NaN run the pair loop without them and evaluate
+ * again, with the tests, any 256-source chain whose running sums come out
+ * non-finite (same bits either way).  mode = 1 makes every
+ * chain take the tested form directly, mode = 2 uses the untested form even for
+ * source sets of a few tiles (where the default does not bother), mode = 0
+ * restores the default; CVTX_B200_GUARDED=0|1|2 in the environment sets the
+ * initial mode. */
+CVTX_B200_API void cvtx_b200_guarded_only(int mode);
 /* Which route the most recent cvtx_*_M2M_* call of the public ABI took:
  * 1 = the CUDA kernels, 0 = the host loops (every accelerator disabled, or a
  * user-defined cvtx_VortFunc), -1 = no call yet; and on how many devices. */

@@ -79,4 +79,7 @@ def hostcheck():
     lib.hostcheck_m2m.restype = C.c_int
     lib.hostcheck_meta.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.hostcheck_meta.restype = C.c_int
+    lib.hostcheck_guarded_only.argtypes, lib.hostcheck_guarded_only.restype = [C.c_int], None
+    lib.hostcheck_reevaluated.argtypes, lib.hostcheck_reevaluated.restype = [C.c_int], C.c_long
+    lib.hostcheck_optimistic.argtypes, lib.hostcheck_optimistic.restype = [C.c_int, C.c_int], C.c_int
     return lib

@@ -16,6 +16,8 @@
 using namespace cvtx;
 
 namespace {
+int g_guarded_only = 0;      // 1: every chain in the guarded form (what cvtx_b200_guarded_only(1) does on the device)
+long g_reevaluated = 0;      // chains the optimistic form had to hand back
 // W = lanes per Vec: 1 = scalar FP32, 2 = the packed FP32x2 form the kernel uses for even T
 template <int W> struct Runner {
 	const float *src; int n; const float *tgt; int m; float *out; int op; float sigma, nu;
@@ -24,8 +26,7 @@ template <int W> struct Runner {
 		const int kind = src_kind(op), cols = src_cols(op);
 		const long npad = ((long)n + S - 1) / S * S;
 		std::vector<f4> A(npad), B(npad);
-		std::memset(A.data(), 0, sizeof(f4) * npad);
-		std::memset(B.data(), 0, sizeof(f4) * npad);
+		for (long j = n; j < npad; ++j) pad_source(kind, A[j], B[j]);
 		for (long j = 0; j < n; ++j) pack_source(kind, src + cols * j, A[j], B[j]);
 		const PairConsts k = P::make_consts(sigma, nu);
 #pragma omp parallel for schedule(static)
@@ -49,7 +50,23 @@ template <int W> struct Runner {
 			for (long t0 = 0; t0 < npad; t0 += chain) {
 				Vec<W> acc[P::NACC];
 				for (int c = 0; c < P::NACC; ++c) acc[c] = bc<W>(0.0f);
-				for (long j = t0; j < t0 + chain; ++j) P::template pair<W>(tg, A[j], B[j], acc, k);
+				// the kernel's optimistic chain (m2m_kernel.cuh): unguarded pair form, one finiteness
+				// check over the running sums, guarded re-evaluation of the chain if it fails
+				bool guarded = true;
+				if (P::OPTIMISTIC && !g_guarded_only) {
+					for (long j = t0; j < t0 + chain; ++j) P::template pair<W, false>(tg, A[j], B[j], acc, k);
+					Vec<W> chk = acc[0];
+					for (int c = 1; c < P::NACC; ++c) chk = vadd(chk, acc[c]);
+					const float s = W == 2 ? chk.lane(0) + chk.lane(1) : chk.lane(0);
+					guarded = !(fabsf(s) <= 3.40282346e38f);
+					if (guarded) {
+						for (int c = 0; c < P::NACC; ++c) acc[c] = bc<W>(0.0f);
+#pragma omp atomic
+						++g_reevaluated;
+					}
+				}
+				if (guarded)
+					for (long j = t0; j < t0 + chain; ++j) P::template pair<W, true>(tg, A[j], B[j], acc, k);
 				for (int l = 0; l < W; ++l) for (int c = 0; c < P::NACC; ++c) dacc[l][c] += (double)acc[c].lane(l);
 			}
 			for (int l = 0; l < W && i0 + l < m; ++l) {
@@ -63,6 +80,10 @@ template <int W> struct Runner {
 struct Meta {
 	int *v;
 	template <class P> void run() { v[0] = P::LANE_OPS; v[1] = P::SFU_OPS; v[2] = P::TCOLS; v[3] = P::NOUT; v[4] = P::NACC; v[5] = P::NSRC4; }
+};
+struct Optimistic {
+	int v;
+	template <class P> void run() { v = P::OPTIMISTIC ? 1 : 0; }
 };
 }  // namespace
 
@@ -78,6 +99,19 @@ extern "C" int hostcheck_m2m_scalar(int op, int reg, const float *src, int n, co
 {
 	Runner<1> r = {src, n, tgt, m, out, op, sigma, nu};
 	return dispatch_op(op, reg, r) ? 0 : -1;
+}
+
+extern "C" void hostcheck_guarded_only(int on) { g_guarded_only = on; }
+extern "C" long hostcheck_reevaluated(int reset)
+{
+	const long v = g_reevaluated;
+	if (reset) g_reevaluated = 0;
+	return v;
+}
+extern "C" int hostcheck_optimistic(int op, int reg)
+{
+	Optimistic q = {0};
+	return dispatch_op(op, reg, q) ? q.v : -1;
 }
 
 extern "C" int hostcheck_meta(int op, int reg, int *six)

@@ -5,7 +5,7 @@ are a lower bound of what the GPU tests see."""
 import numpy as np
 import pytest
 
-from util import SHAPES, make_case, op_cases, rel_l2
+from util import SHAPES, make_case, nasty_case, op_cases, rel_l2
 
 OPS = {"P3D_M2M_vel": 0, "P3D_M2M_dvort": 1, "P3D_M2M_visc_dvort": 2, "P3D_M2M_vort": 3,
        "P2D_M2M_vel": 4, "P2D_M2M_visc_dvort": 5, "F3D_M2M_vel": 6, "F3D_M2M_dvort": 7}
@@ -99,3 +99,54 @@ def test_length_scale_robustness(hostcheck, oracle, scale):
         assert np.all(np.isfinite(got)), (op, reg, scale)
         e_par, e_ref = rel_l2(got, f32), rel_l2(f32, f64)
         assert e_par <= 1e-5 or e_par <= 3.0 * e_ref + 1e-6, (op, reg, scale, e_par, e_ref)
+
+
+ALL_OPS = op_cases() + [("P3D_M2M_vort", r) for r in ("winckelmans", "planetary", "gaussian")]
+
+
+@pytest.mark.parametrize("op,reg", ALL_OPS + [("fused", r) for r in REG])
+def test_optimistic_chains_give_the_bits_of_the_guarded_form(hostcheck, op, reg):
+    """pair<W, false> + one finiteness test per chain + guarded re-evaluation (the kernel's default
+    route for OPTIMISTIC policies) against the guarded form everywhere, on inputs where guards fire."""
+    rng = np.random.default_rng(11)
+    opid = 8 if op == "fused" else OPS[op]
+    base = "P3D_M2M_dvort" if op == "fused" else op
+    n, m = 1100, 259                             # 4.3 chains, an odd target count
+    src, tgt = nasty_case(base, rng, n, m)
+    nout = 6 if op == "fused" else SHAPES[op][2]
+    outs = []
+    with np.errstate(all="ignore"):
+        for guarded in (1, 0):
+            hostcheck.hostcheck_guarded_only(guarded)
+            hostcheck.hostcheck_reevaluated(1)
+            out = np.full((m, nout), 7.0, np.float32)
+            try:
+                assert hostcheck.hostcheck_m2m(opid, REG[reg], src, n, tgt, m, out, 0.3, 0.1) == 0
+            finally:
+                hostcheck.hostcheck_guarded_only(0)
+            outs.append((out, hostcheck.hostcheck_reevaluated(1)))
+    (g, redo_g), (o, redo_o) = outs
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), (op, reg)
+    assert redo_g == 0
+    if hostcheck.hostcheck_optimistic(opid, REG[reg]):
+        assert 0 < redo_o < 0.6 * ((m + 1) // 2) * 5, redo_o      # handed back where needed, not everywhere
+    else:
+        assert redo_o == 0
+
+
+def test_optimistic_policies_are_the_documented_set(hostcheck):
+    got = {(op, reg) for op in range(9) for reg in range(4) if hostcheck.hostcheck_optimistic(op, reg) == 1}
+    sing_gauss = {(op, reg) for op in (0, 1, 4, 8) for reg in (0, 3)}
+    assert got == sing_gauss | {(6, r) for r in range(4)} | {(7, r) for r in range(4)}
+
+
+def test_padding_filament_contributes_finite_zeros(hostcheck):
+    """One real filament + 255 padding records: off the x axis nothing is re-evaluated."""
+    rng = np.random.default_rng(12)
+    src, tgt = make_case("F3D_M2M_vel", rng, 1, 64)
+    for op in ("F3D_M2M_vel", "F3D_M2M_dvort"):
+        s, t = make_case(op, rng, 1, 64)
+        hostcheck.hostcheck_reevaluated(1)
+        out = run(hostcheck, op, "singular", s, t, 0.3, 0.1)
+        assert hostcheck.hostcheck_reevaluated(1) == 0
+        assert np.all(np.isfinite(out)) and np.any(out != 0)

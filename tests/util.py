@@ -85,6 +85,35 @@ def make_case(op, rng, n, m, box=10.0, self_targets=False):
     return src, tgt
 
 
+def nasty_case(op, rng, n, m, nonfinite=True):
+    """Self-interaction plus everything that makes a guard fire: duplicated positions with different
+    strengths, targets sitting on sources, on filament end points and on filament axes, a zero-length
+    filament, a target at the origin (= the padding records), sub-underflow separations, one NaN and
+    one inf coordinate."""
+    base = "P3D_M2M_vel" if op == "P3D_M2M_vort" else op
+    src, tgt = make_case(base, rng, n, m, self_targets=True)
+    d = 2 if op.startswith("P2D") else 3
+    src[5, :d] = src[4, :d]                      # two sources at one position, different strengths
+    src[300, :d] = src[4, :d]                    # ... and a third one in the next chain
+    if op.startswith("F3D"):
+        src[7, 3:6] = src[7, 0:3]                # zero-length filament
+        tgt[0, :3] = src[9, 0:3]                 # target on a start point
+        tgt[1, :3] = src[9, 3:6]                 # target on an end point
+        tgt[2, :3] = 0.5 * (src[11, 0:3] + src[11, 3:6])          # on the segment
+        tgt[3, :3] = src[12, 0:3] + 3.0 * (src[12, 3:6] - src[12, 0:3])   # on the axis, outside
+        tgt[4, :3] = (0.37, 0.0, 0.0)            # on the padding filament's axis
+    else:
+        tgt[0, :d] = src[4, :d]
+        tgt[1, :d] = src[400, :d]
+        tgt[2, :d] = src[n - 1, :d]
+        tgt[6, :d] = src[20, :d] + 1e-30         # separation whose square underflows
+    tgt[5, :d] = 0.0                             # the origin: coincides with the particle padding
+    if nonfinite:                                # (the reference turns every target into NaN for these)
+        src[30, 0] = np.nan
+        src[600, 1] = np.inf
+    return src, tgt
+
+
 def op_cases():
     """Every (op, regularisation) the reference accelerates."""
     out = []
