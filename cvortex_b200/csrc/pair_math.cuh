@@ -777,9 +777,9 @@ struct F3DVel {
 // ===========================================================================
 struct F3DDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
-	static constexpr int LANE_OPS = 43, SFU_OPS = 3;
+	static constexpr int LANE_OPS = 42, SFU_OPS = 3;
 	// the rule fires when A's scalar or B is NaN; a NaN scalar reaches the A sums through fma(sa, r0, acc),
-	// a NaN B reaches the B sum directly
+	// a NaN B reaches the B sum through its fma
 	static constexpr bool OPTIMISTIC = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
@@ -792,17 +792,22 @@ struct F3DDvort {
 		const Vec<W> t212 = vfms(f.d1, rs1, vmul(f.d2, rs2));
 		const Vec<W> sA = vmul(vneg(vmul(t212, a.w)), vmul(rsx, rsx));
 		const Vec<W> t222 = vmul(vmul(x2, rsx), vsub(rs1, rs2));
-		const Vec<W> Bv = vmul(t222, b.w);
-		Vec<W> sa = sA, bv = Bv;
-		if (G) for (int i = 0; i < W; ++i) {
-			const bool ok = (sA.lane(i) == sA.lane(i)) && (Bv.lane(i) == Bv.lane(i));
-			sa.set(i, ok ? sA.lane(i) : 0.0f);
-			bv.set(i, ok ? Bv.lane(i) : 0.0f);
+		// B = t222 * b.w enters its sum through ONE fused multiply-add in both forms (a separate
+		// product and sum would be contracted by nvcc in the plain form only, and the two forms
+		// must round identically); the guarded form forms B once more just to test it
+		Vec<W> sa = sA, nb = vfma(t222, b.w, acc[3]);
+		if (G) {
+			const Vec<W> Bv = vmul(t222, b.w);
+			for (int i = 0; i < W; ++i) {
+				const bool ok = (sA.lane(i) == sA.lane(i)) && (Bv.lane(i) == Bv.lane(i));
+				sa.set(i, ok ? sA.lane(i) : 0.0f);
+				nb.set(i, ok ? nb.lane(i) : acc[3].lane(i));
+			}
 		}
 		acc[0] = vfma(sa, f.ox, acc[0]);
 		acc[1] = vfma(sa, f.oy, acc[1]);
 		acc[2] = vfma(sa, f.oz, acc[2]);
-		acc[3] = vadd(acc[3], bv);
+		acc[3] = nb;
 	}
 	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &) {
 		const double wx = row[3], wy = row[4], wz = row[5];

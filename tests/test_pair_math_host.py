@@ -53,7 +53,7 @@ def test_lane_op_metadata_is_consistent(hostcheck):
     import ctypes as C
     v = (C.c_int * 6)()
     expect = {(0, 1): (21, 1), (0, 0): (17, 1), (0, 3): (28, 3), (1, 1): (31, 1), (1, 3): (38, 3), (2, 1): (20, 1),
-              (2, 3): (16, 1), (4, 3): (9, 2), (4, 1): (11, 1), (5, 3): (8, 1), (5, 1): (13, 2), (6, 0): (37, 3), (7, 0): (43, 3)}
+              (2, 3): (16, 1), (4, 3): (9, 2), (4, 1): (11, 1), (5, 3): (8, 1), (5, 1): (13, 2), (6, 0): (37, 3), (7, 0): (42, 3)}
     for (op, reg), (lane, sfu) in expect.items():
         assert hostcheck.hostcheck_meta(op, reg, v) == 0
         assert (v[0], v[1]) == (lane, sfu), (op, reg, v[0], v[1])

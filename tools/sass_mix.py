@@ -2,11 +2,12 @@
 
     make -C cvortex_b200/csrc sass && python tools/sass_mix.py [filter]
 
-For every `m2m_kernel<Policy, T, B, MINB>` it finds the innermost loop (the backward branch whose body
-holds the most MUFU instructions per byte), counts opcodes in it, and prints them per (source, target)
-pair: packed FP32x2 instructions count two lane-ops, so `lane-ops/pair` is directly comparable with the
-L column of DESIGN.md section 4, `MUFU/pair` with S, and `issue/pair` (all instructions) with the
-issue bound of 4 warp instructions per clock and SM.
+For every `m2m_kernel<Policy, T, B, MINB>` it finds the innermost pair loops (an OPTIMISTIC policy has
+two: the plain one and the guarded one that re-evaluates a chain, pair_math.cuh "GUARDS"), counts the
+opcodes in each and prints them per (source, target) pair: packed FP32x2 instructions count two
+lane-ops, so `lane-ops` is directly comparable with the L column of DESIGN.md section 4, `MUFU` with
+S; `ALU` are the compares / selects / min-max (FSETP, FSEL, FMNMX*: 16-lane ALU pipe) and `issue` all
+instructions, against the issue bound of one warp instruction per clock and SM sub-partition.
 """
 import collections
 import re
@@ -34,55 +35,60 @@ def functions(text):
 		yield name, body
 
 
-def inner_loop(body):
-	"""The backward branch whose span is smallest among those that contain MUFU instructions."""
-	best = None
-	for k, (addr, op, args) in enumerate(body):
+def inner_loops(body):
+	"""Innermost loops (backward branches with no other backward branch inside) that do FP32 work."""
+	spans = []
+	for addr, op, args in body:
 		if not op.startswith("BRA"):
 			continue
 		m = re.search(r"0x([0-9a-f]+)", args)
+		if m and int(m.group(1), 16) < addr:
+			spans.append((int(m.group(1), 16), addr))
+	out = []
+	for lo, hi in spans:
+		if any((l2, h2) != (lo, hi) and lo <= l2 and h2 <= hi for l2, h2 in spans):
+			continue
+		span = [i for i in body if lo <= i[0] <= hi]
+		if sum(1 for i in span if re.match(r"F(FMA|MUL|ADD)", i[1])) >= 16 and any(i[1].startswith("LDS") for i in span):
+			out.append(span)
+	return out
+
+
+def loop_table(text):
+	"""One dict per innermost pair loop of every m2m_kernel instantiation in a cuobjdump -sass dump."""
+	fns = list(functions(text))
+	dem = subprocess.run(["c++filt"], input="\n".join(n for n, _ in fns), capture_output=True, text=True).stdout.splitlines()
+	rows = []
+	for (name, body), d in zip(fns, dem):
+		m = re.search(r"m2m_kernel<cvtx::(\w+(?:<\d+>)?), (\d+), (\d+), (\d+)>", d)
 		if not m:
 			continue
-		tgt = int(m.group(1), 16)
-		if tgt >= addr:
-			continue
-		span = [i for i in body if tgt <= i[0] <= addr]
-		if not any(i[1].startswith("MUFU") for i in span):
-			continue
-		if best is None or len(span) < len(best):
-			best = span
-	return best or []
+		pol, T = m.group(1), int(m.group(2))
+		for loop in inner_loops(body):
+			c = collections.Counter(op for _, op, _ in loop)
+			mufu = sum(v for k, v in c.items() if k.startswith("MUFU"))
+			lds = sum(v for k, v in c.items() if k.startswith("LDS"))
+			packed = sum(v for k, v in c.items() if re.match(r"F(FMA|MUL|ADD)2", k))
+			scalar = sum(v for k, v in c.items() if re.match(r"F(FMA|MUL|ADD)(\.|$)", k))
+			per_src = 1 if pol.startswith("P2D") else 2            # LDS.128 per packed source record
+			pairs = max(lds // per_src, 1) * T
+			alu = sum(v for k, v in c.items() if re.match(r"(FSETP|FSET|FSEL|FMNMX)", k))
+			total = len(loop)
+			rest = collections.Counter({k: v for k, v in c.items() if not re.match(r"F(FMA|MUL|ADD)", k) and not k.startswith(("MUFU", "LDS"))})
+			rows.append({"kernel": d, "policy": pol, "T": T, "form": "guarded" if alu else "plain", "pairs": pairs,
+			             "lane_ops": (packed * 2 + scalar) / pairs, "mufu": mufu / pairs, "alu": alu / pairs, "lds": lds / pairs,
+			             "other": (total - packed - scalar - mufu - lds - alu) / pairs, "issue": total / pairs,
+			             "tops": ", ".join(f"{k}x{v}" for k, v in rest.most_common(4))})
+	return rows
 
 
 def main():
 	flt = sys.argv[1] if len(sys.argv) > 1 else ""
-	text = SASS.read_text()
-	names = [n for n, _ in functions(text)]
-	dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
-	print(f"{'kernel':44s} {'pairs':>5s} {'lane-ops':>8s} {'MUFU':>5s} {'LDS':>5s} {'other':>6s} {'issue':>6s}   (per pair)   top non-FP32 opcodes")
-	for (name, body), d in zip(functions(text), dem):
-		m = re.search(r"m2m_kernel<cvtx::(\w+(?:<\d+>)?), (\d+), (\d+), (\d+)>", d)
-		if not m or flt not in d:
-			continue
-		pol, T = m.group(1), int(m.group(2))
-		loop = inner_loop(body)
-		if not loop:
-			continue
-		c = collections.Counter(op for _, op, _ in loop)
-		mufu = sum(v for k, v in c.items() if k.startswith("MUFU"))
-		lds = sum(v for k, v in c.items() if k.startswith("LDS"))
-		packed = sum(v for k, v in c.items() if re.match(r"F(FMA|MUL|ADD)2", k))
-		scalar = sum(v for k, v in c.items() if re.match(r"F(FMA|MUL|ADD)(\.|$)", k) and not re.match(r"F(FMA|MUL|ADD)2", k))
-		# sources per trip: one LDS.128 per record
-		per_src = 2 if any(p in pol for p in ("P3DVel", "P3DDvort", "P3DVort", "P3DVisc", "F3D")) else 1
-		srcs = max(lds // per_src, 1)
-		pairs = srcs * T
-		lane = packed * 2 + scalar
-		total = len(loop)
-		other = total - packed - scalar - mufu - lds
-		rest = collections.Counter({k: v for k, v in c.items() if not re.match(r"F(FMA|MUL|ADD)", k) and not k.startswith(("MUFU", "LDS"))})
-		tops = ", ".join(f"{k}x{v}" for k, v in rest.most_common(5))
-		print(f"{pol + f' T={T}':44s} {pairs:5d} {lane / pairs:8.2f} {mufu / pairs:5.2f} {lds / pairs:5.2f} {other / pairs:6.2f} {total / pairs:6.2f}   {tops}")
+	print(f"{'kernel':26s} {'loop':8s} {'pairs':>5s} {'lane-ops':>8s} {'MUFU':>5s} {'ALU':>5s} {'LDS':>5s} {'other':>6s} {'issue':>6s}   (per pair)   top non-FP32 opcodes")
+	for r in loop_table(SASS.read_text()):
+		if flt in r["kernel"]:
+			print(f"{r['policy'] + ' T=' + str(r['T']):26s} {r['form']:8s} {r['pairs']:5d} {r['lane_ops']:8.2f} {r['mufu']:5.2f} {r['alu']:5.2f} "
+			      f"{r['lds']:5.2f} {r['other']:6.2f} {r['issue']:6.2f}   {r['tops']}")
 
 
 if __name__ == "__main__":
