@@ -146,7 +146,7 @@ int main(int argc, char **argv) {
 	auto rnd = []() { return 10.0f * (float)rand() / (float)RAND_MAX; };
 	for (int i = 0; i < n; ++i) {
 		hA[i] = make_float4(rnd(), rnd(), rnd(), 0.01f);
-		hB[i] = make_float4(rnd(), rnd(), rnd(), 0.f);
+		hB[i] = make_float4(rnd(), rnd(), rnd(), 0.1f * rnd());      // w: only the filament ops read it ((3/|r0|) t1)
 		for (int c = 0; c < 6; ++c) hp[(size_t)i * 7 + c] = rnd();
 		hp[(size_t)i * 7 + 6] = 0.01f;
 		hs[(size_t)i * 7 + 0] = hA[i].x; hs[(size_t)i * 7 + 1] = hA[i].y; hs[(size_t)i * 7 + 2] = hA[i].z;
