@@ -403,7 +403,8 @@ template <int REG> struct P3DVel {
 // parallel vorticity, and the hoisted sum would cancel catastrophically there.
 // ===========================================================================
 template <int REG> struct P3DDvort {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
+	// (singular: 4 targets per thread measured 2 % faster than 8 once the guards left the loop, profiles/sweep_ops_r1b.txt)
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = REG == REG_SINGULAR ? 4 : 8;
 	static constexpr int LANE_OPS = 22 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // A = inf / NaN enters all three sums through fma(A, c, .)
 	CVTX_HD static void load_target(const float *row, float *tg) {
