@@ -391,7 +391,7 @@ int cvtx_b200_f3d_inf_mtrx(int device, void *stream_, const float *fil, int n_fi
 	int rows_per_block = (n_mes + gy - 1) / gy;
 	rows_per_block = (rows_per_block + 127) / 128 * 128;
 	gy = (n_mes + rows_per_block - 1) / rows_per_block;
-	f3d_inf_mtrx_kernel<W, B><<<dim3(gx, gy), B, 0, (cudaStream_t)stream_>>>(fil, n_fil, mes, dir, 0, n_mes, rows_per_block, out);
+	f3d_inf_mtrx_kernel<W, B><<<dim3(gx, gy), B, 0, (cudaStream_t)stream_>>>(fil, n_fil, mes, dir, 0, n_mes, rows_per_block, out, 1.0f);
 	CUDA_TRY(cudaGetLastError());
 	g_launches += 1;
 	return CVTX_B200_OK;

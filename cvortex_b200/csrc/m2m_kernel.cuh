@@ -278,14 +278,15 @@ __global__ void pack_sources_kernel(int kind, int cols, const float *__restrict_
 // m points.  Nothing is reduced, every pair is an output, so the roles flip against m2m_kernel:
 // a THREAD owns W filaments (lanes of Vec<W>, registers) so that a warp writes 32 consecutive
 // columns of a row (coalesced 128-byte stores), and the POINTS of a row tile are broadcast from
-// shared memory.  37 lane-ops + 4 for the projection per element and 4 bytes written: at the
-// ~800 G elements/s the FP32 pipe allows that is 3.2 TB/s of stores, so the kernel sits near both
+// shared memory.  40 lane-ops + 4 for the projection per element and 4 bytes written: at the
+// ~750 G elements/s the FP32 pipe allows that is 3.0 TB/s of stores, so the kernel sits near both
 // roofs at once.
 template <int W, int B>
 __global__ void __launch_bounds__(B) f3d_inf_mtrx_kernel(const float *__restrict__ fil, int n,
                                                           const float *__restrict__ mes, const float *__restrict__ dir,
                                                           int row0, int row1, int rows_per_block,
-                                                          float *__restrict__ out /* row `row0` of the matrix */)
+                                                          float *__restrict__ out /* row `row0` of the matrix */,
+                                                          float one /* 1.0f at run time, see cross_rounded() */)
 {
 	constexpr int TILE = 128;
 	__shared__ float4 sx[TILE], sd[TILE];
@@ -320,9 +321,8 @@ __global__ void __launch_bounds__(B) f3d_inf_mtrx_kernel(const float *__restrict
 			const Vec<W> px = vsub(x.x, ax), py = vsub(x.y, ay), pz = vsub(x.z, az);      // r1 = x - a
 			const Vec<W> qx = vsub(x.x, bx), qy = vsub(x.y, by), qz = vsub(x.z, bz);      // r2 = x - b
 			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);         // r0 = r1 - r2
-			const Vec<W> cx = vfms(py, qz, vmul(pz, qy));
-			const Vec<W> cy = vfms(pz, qx, vmul(px, qz));
-			const Vec<W> cz = vfms(px, qy, vmul(py, qx));
+			Vec<W> cx, cy, cz;
+			cross_rounded(px, py, pz, qx, qy, qz, one, cx, cy, cz);
 			const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
 			const Vec<W> n1 = vfma(pz, pz, vfma(py, py, vmul(px, px)));
 			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));

@@ -724,6 +724,23 @@ template <int REG> struct P2DVisc {
 // (|r1| ~ |r2|), so r0 stays consistent with the rounded r1, r2 and the
 // cancelling difference r1.r0/|r1| - r2.r0/|r2| keeps the reference's accuracy.
 // ===========================================================================
+// u x v the way the reference's bsv_V3f_cross rounds it: both products rounded, then one rounded
+// subtraction (9 lane-ops, not the 6 of fma(uy, vz, -(uz vy))).  The filament formulas divide by
+// |r1 x r2|^2 (|r1 x r0|^2) and drop the pair when that is 0, and whether it IS 0 for a point on the
+// filament's own line -- a segment's midpoint, the next node of a straight vortex line -- is decided
+// by this rounding: with equal products the reference gets an exact 0 and drops the pair, while a
+// fused cross product returns the rounding residue of one product (1e-9 ... 1e-16 relative), i.e. a
+// finite 1/|c|^2 of 1e18+ and a "velocity" of 1e8 where the reference returns 0.
+// `one` must be a RUN-TIME 1.0f: ptxas (12.9) fuses a packed product into a following packed sum or
+// difference even when both carry .rn (and folds a literal 1.0 first), so the subtraction is issued
+// as fma(p, one, -m), which it cannot take apart.
+template <int W> CVTX_HD void cross_rounded(Vec<W> ux, Vec<W> uy, Vec<W> uz, Vec<W> vx, Vec<W> vy, Vec<W> vz, float one,
+                                            Vec<W> &cx, Vec<W> &cy, Vec<W> &cz) {
+	cx = vfma(vmul(uy, vz), one, vneg(vmul(uz, vy)));
+	cy = vfma(vmul(uz, vx), one, vneg(vmul(ux, vz)));
+	cz = vfma(vmul(ux, vy), one, vneg(vmul(uy, vx)));
+}
+
 template <int W> struct Fil { Vec<W> px, py, pz, qx, qy, qz, ox, oy, oz, n1, n2, d1, d2; };
 template <int W> CVTX_HD Fil<W> filament_geometry(const Vec<W> *tg, const f4 a, const f4 b) {   // 21 lane-ops
 	Fil<W> f;
@@ -739,16 +756,15 @@ template <int W> CVTX_HD Fil<W> filament_geometry(const Vec<W> *tg, const f4 a, 
 
 struct F3DVel {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
-	static constexpr int LANE_OPS = 37, SFU_OPS = 3;
+	static constexpr int LANE_OPS = 40, SFU_OPS = 3;
 	// the rule fires when t1 or t2 is inf / NaN; their product is then inf or NaN (inf * 0 = NaN), and so
 	// is every fma(kk, c, acc)
 	static constexpr bool OPTIMISTIC = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Fil<W> f = filament_geometry(tg, a, b);
-		const Vec<W> cx = vfms(f.py, f.qz, vmul(f.pz, f.qy));
-		const Vec<W> cy = vfms(f.pz, f.qx, vmul(f.px, f.qz));
-		const Vec<W> cz = vfms(f.px, f.qy, vmul(f.py, f.qx));
+		Vec<W> cx, cy, cz;
+		cross_rounded(f.px, f.py, f.pz, f.qx, f.qy, f.qz, k.c0, cx, cy, cz);      // c = r1 x r2
 		const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
 		const Vec<W> t1 = vmul(vrcp(c2), a.w);
 		const Vec<W> t2 = vfms(f.d1, vrsqrt(f.n1), vmul(f.d2, vrsqrt(f.n2)));
@@ -765,7 +781,7 @@ struct F3DVel {
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &) {
 		out[0] = acc[0]; out[1] = acc[1]; out[2] = acc[2];
 	}
-	static PairConsts make_consts(float, float) { PairConsts k = {}; k.s0 = 1.0; return k; }
+	static PairConsts make_consts(float, float) { PairConsts k = {}; k.c0 = 1.0f; k.s0 = 1.0; return k; }   // c0: cross_rounded's `one`
 };
 
 // ===========================================================================
@@ -778,16 +794,15 @@ struct F3DVel {
 // ===========================================================================
 struct F3DDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
-	static constexpr int LANE_OPS = 42, SFU_OPS = 3;
+	static constexpr int LANE_OPS = 45, SFU_OPS = 3;
 	// the rule fires when A's scalar or B is NaN; a NaN scalar reaches the A sums through fma(sa, r0, acc),
 	// a NaN B reaches the B sum through its fma
 	static constexpr bool OPTIMISTIC = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &) {
+	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Fil<W> f = filament_geometry(tg, a, b);
-		const Vec<W> xx = vfms(f.py, f.oz, vmul(f.pz, f.oy));                    // X = r1 x r0
-		const Vec<W> xy = vfms(f.pz, f.ox, vmul(f.px, f.oz));
-		const Vec<W> xz = vfms(f.px, f.oy, vmul(f.py, f.ox));
+		Vec<W> xx, xy, xz;
+		cross_rounded(f.px, f.py, f.pz, f.ox, f.oy, f.oz, k.c0, xx, xy, xz);      // X = r1 x r0
 		const Vec<W> x2 = vfma(xz, xz, vfma(xy, xy, vmul(xx, xx)));
 		const Vec<W> rs1 = vrsqrt(f.n1), rs2 = vrsqrt(f.n2), rsx = vrsqrt(x2);
 		const Vec<W> t212 = vfms(f.d1, rs1, vmul(f.d2, rs2));
@@ -816,7 +831,7 @@ struct F3DDvort {
 		out[1] = acc[3] * wy + (acc[2] * wx - acc[0] * wz);
 		out[2] = acc[3] * wz + (acc[0] * wy - acc[1] * wx);
 	}
-	static PairConsts make_consts(float, float) { PairConsts k = {}; k.s0 = 1.0; return k; }
+	static PairConsts make_consts(float, float) { PairConsts k = {}; k.c0 = 1.0f; k.s0 = 1.0; return k; }   // c0: cross_rounded's `one`
 };
 
 }  // namespace cvtx

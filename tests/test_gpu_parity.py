@@ -256,3 +256,29 @@ def test_accelerator_switch(gpu, oracle):
     assert np.array_equal(off, oracle.m2m("P3D_M2M_vel", P, X, "planetary", 0.3))
     assert upstream_per_target_ok(on, off)                       # the reference's own acceptance test
     assert lib.accelerator_name(0) and lib.accelerator_name(lib.num_accelerators()) is None
+
+
+@pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
+def test_points_on_a_vortex_line_follow_the_reference(gpu, oracle, op):
+    """Nodes and midpoints of a straight vortex line (see tests/test_pair_math_host.py): |r1 x r2| must
+    round like the reference's, or a point on a filament's own line gets 1e8 where the reference gives 0."""
+    from util import LINE_DIRECTIONS, vortex_line
+    lib, dev = gpu
+    for d in LINE_DIRECTIONS:
+        fil, tgt = vortex_line(d, as_particles=op.endswith("dvort"))
+        got = call_abi(lib, op, fil, tgt, "singular", 0.3, 0.1)
+        assert dev.last_dispatch() == 1
+        want = oracle.m2m(op, fil, tgt)
+        assert np.all(np.isfinite(got))
+        e = rel_l2(got, want)
+        print(f"{op} on a line along {d}: gpu-vs-ref {e:.2e}, max |gpu| {np.abs(got).max():.3e}, max |ref| {np.abs(want).max():.3e}")
+        assert e <= 1e-3 and np.abs(got).max() <= 1.05 * np.abs(want).max(), (op, d, e)      # (a fused cross product: e ~ 1e2)
+    fil = np.zeros((1, 7), np.float32)
+    fil[0, 0:3], fil[0, 3:6], fil[0, 6] = (0.1, 0.1, 0.0), (0.7, 0.7, 0.0), 2.0
+    pts = np.float32([[0.4, 0.4, 0.0], [0.25, 0.25, 0.0], [1.3, 1.3, 0.0], [-2.0, -2.0, 0.0]])
+    tgt = np.concatenate([pts, np.float32([[0.3, 0.1, 0.7, 0.01]] * 4)], axis=1) if op.endswith("dvort") else pts
+    tgt = np.ascontiguousarray(tgt, np.float32)
+    assert np.all(oracle.m2m(op, fil, tgt) == 0)
+    assert np.all(call_abi(lib, op, fil, tgt, "singular", 0.3, 0.1) == 0)
+    if op == "F3D_M2M_vel":
+        assert np.all(lib.F3D_inf_mtrx(fil, pts, np.ones((4, 3), np.float32)) == 0)

@@ -5,7 +5,7 @@ are a lower bound of what the GPU tests see."""
 import numpy as np
 import pytest
 
-from util import SHAPES, make_case, nasty_case, op_cases, rel_l2
+from util import LINE_DIRECTIONS, SHAPES, make_case, nasty_case, op_cases, rel_l2, vortex_line
 
 OPS = {"P3D_M2M_vel": 0, "P3D_M2M_dvort": 1, "P3D_M2M_visc_dvort": 2, "P3D_M2M_vort": 3,
        "P2D_M2M_vel": 4, "P2D_M2M_visc_dvort": 5, "F3D_M2M_vel": 6, "F3D_M2M_dvort": 7}
@@ -53,7 +53,7 @@ def test_lane_op_metadata_is_consistent(hostcheck):
     import ctypes as C
     v = (C.c_int * 6)()
     expect = {(0, 1): (21, 1), (0, 0): (17, 1), (0, 3): (28, 3), (1, 1): (31, 1), (1, 3): (38, 3), (2, 1): (20, 1),
-              (2, 3): (16, 1), (4, 3): (9, 2), (4, 1): (11, 1), (5, 3): (8, 1), (5, 1): (13, 2), (6, 0): (37, 3), (7, 0): (42, 3)}
+              (2, 3): (16, 1), (4, 3): (9, 2), (4, 1): (11, 1), (5, 3): (8, 1), (5, 1): (13, 2), (6, 0): (40, 3), (7, 0): (45, 3)}
     for (op, reg), (lane, sfu) in expect.items():
         assert hostcheck.hostcheck_meta(op, reg, v) == 0
         assert (v[0], v[1]) == (lane, sfu), (op, reg, v[0], v[1])
@@ -150,3 +150,26 @@ def test_padding_filament_contributes_finite_zeros(hostcheck):
         out = run(hostcheck, op, "singular", s, t, 0.3, 0.1)
         assert hostcheck.hostcheck_reevaluated(1) == 0
         assert np.all(np.isfinite(out)) and np.any(out != 0)
+
+
+@pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
+def test_points_on_a_vortex_line_follow_the_reference(hostcheck, oracle, op):
+    """Nodes and midpoints of a straight vortex line: the pair terms divide by |r1 x r2|^2, which the
+    reference forms from two rounded products per component.  A fused cross product (what this kernel
+    used first) leaves a 1e-9 ... 1e-16 residue where the reference gets an exact 0 and drops the pair,
+    and returned 4e9 where the reference returns 2e7 -- or 1e8 where it returns 0."""
+    for d in LINE_DIRECTIONS:
+        fil, tgt = vortex_line(d, as_particles=op.endswith("dvort"))
+        got = run(hostcheck, op, "singular", fil, tgt, 0.3, 0.1)
+        want = oracle.m2m(op, fil, tgt)
+        assert np.all(np.isfinite(got)) and np.all(np.isfinite(want))
+        assert rel_l2(got, want) <= 1e-5, (op, d, rel_l2(got, want))
+        assert np.abs(got).max() <= 1.001 * np.abs(want).max()
+    # one diagonal segment with inexact coordinate products, points on its line: exactly 0, like the reference
+    fil = np.zeros((1, 7), np.float32)
+    fil[0, 0:3], fil[0, 3:6], fil[0, 6] = (0.1, 0.1, 0.0), (0.7, 0.7, 0.0), 2.0
+    pts = np.float32([[0.4, 0.4, 0.0], [0.25, 0.25, 0.0], [1.3, 1.3, 0.0], [-2.0, -2.0, 0.0]])
+    tgt = np.concatenate([pts, np.float32([[0.3, 0.1, 0.7, 0.01]] * 4)], axis=1) if op.endswith("dvort") else pts
+    tgt = np.ascontiguousarray(tgt, np.float32)
+    assert np.all(oracle.m2m(op, fil, tgt) == 0)
+    assert np.all(run(hostcheck, op, "singular", fil, tgt, 0.3, 0.1) == 0)

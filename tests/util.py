@@ -114,6 +114,27 @@ def nasty_case(op, rng, n, m, nonfinite=True):
     return src, tgt
 
 
+LINE_DIRECTIONS = ((1, 0, 0), (1, 1, 0), (1, 1, 1), (1, 2, 0), (0.6, 0.8, 0), (0.3, 0.5, 0.81), (0.1, 0.9, 0.4))
+
+
+def vortex_line(direction, n=40, as_particles=False):
+    """A straight vortex line cut into n filaments (nodes p0 + k h d evaluated in FP32) and the points
+    a filament code evaluates on it: every node and every segment midpoint.  All of them lie on the
+    axes of all n filaments, where |r1 x r2| is zero or rounding noise and the reference's result is
+    decided by how its cross product rounds (cvortex_b200/csrc/pair_math.cuh, cross_rounded)."""
+    d = np.asarray(direction, np.float32)
+    p0, h = np.float32([0.3, 0.7, 0.2]), np.float32(0.125)
+    nodes = np.stack([p0 + np.float32(k) * h * d for k in range(n + 1)]).astype(np.float32)
+    fil = np.zeros((n, 7), np.float32)
+    fil[:, 0:3], fil[:, 3:6], fil[:, 6] = nodes[:-1], nodes[1:], 1.0
+    pts = np.concatenate([nodes, (0.5 * (nodes[:-1] + nodes[1:])).astype(np.float32)]).astype(np.float32)
+    if as_particles:
+        tgt = np.zeros((len(pts), 7), np.float32)
+        tgt[:, :3], tgt[:, 3:6], tgt[:, 6] = pts, np.float32([0.2, -0.4, 0.9]), 0.01
+        return fil, tgt
+    return fil, pts
+
+
 def op_cases():
     """Every (op, regularisation) the reference accelerates."""
     out = []
