@@ -30,7 +30,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_T{0}, g_force_chunks{0};
-std::atomic<int> g_guarded_only{-1};                           // -1 = not set: CVTX_B200_GUARDED decides, read once
+std::atomic<int> g_guard_mode{-1};                           // -1 = not set: CVTX_B200_GUARDED decides, read once
 std::mutex g_devices_mu;
 std::vector<Device *> g_devices;
 int g_device_count = -2;                                       // -2 = not probed yet
@@ -152,11 +152,11 @@ constexpr int kMinTilesOptimistic = 16;
 
 // 0 = by size (the default), 1 = guarded form only, 2 = optimistic form at any size
 int guard_mode() {
-	int v = g_guarded_only.load();
+	int v = g_guard_mode.load();
 	if (v < 0) {
 		const char *e = getenv("CVTX_B200_GUARDED");
 		v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
-		g_guarded_only = v;
+		g_guard_mode = v;
 	}
 	return v;
 }
@@ -273,7 +273,7 @@ unsigned long long cvtx_b200_kernel_launches(void) { return g_launches.load(); }
 
 void cvtx_b200_tune(int force_T, int force_chunks) { g_force_T = force_T; g_force_chunks = force_chunks; }
 
-void cvtx_b200_guarded_only(int mode) { g_guarded_only = (mode == 1 || mode == 2) ? mode : 0; }
+void cvtx_b200_guarded_only(int mode) { g_guard_mode = (mode == 1 || mode == 2) ? mode : 0; }
 
 const char *cvtx_b200_last_error(void) { return g_err.c_str(); }
 
