@@ -8,6 +8,11 @@
 // instruction costs k FP32 lane-ops".  Part 2 runs the production pair kernel of the ops that have
 // an optimistic form (pair_math.cuh, GUARDS) with M2MArgs::exact_only = 1 and 0 on the same
 // inputs, independent targets and self-interaction, and checks that the outputs are the same bits.
+// Part 3 is an EXPERIMENT that exists only here (queued experiment 1): the ops whose
+// guard is a real selection (viscous ops, Winckelmans stretching: eta(0), A(0) are finite, so nothing
+// poisons the sums) run the pair loop unguarded while keeping a running min(r^2) per target lane -- one
+// FMNMX per pair instead of FSETP + FSEL -- and re-evaluate the chain with the production guarded form
+// when the minimum is 0.  Timed against the production kernel on the same inputs, bits compared.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,10 +60,154 @@ __global__ void __launch_bounds__(256) guard_mix(float *out, int iters, float a,
 	if (s == 123.456f) out[0] = s;
 }
 
+
+// ---- part 3: running-min detection of coincident pairs (experiment) -------------------------------
+template <int W> __device__ __forceinline__ Vec<W> vmin(Vec<W> a, Vec<W> b) {
+	Vec<W> r;
+#pragma unroll
+	for (int i = 0; i < W; ++i) r.set(i, fminf(a.lane(i), b.lane(i)));
+	return r;
+}
+
+template <int REG> struct P3DViscMin : P3DVisc<REG> {
+	template <int W> __device__ __forceinline__ static void pair_min(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, Vec<W> &rmin, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		const Vec<W> eta = Eta3D<REG>::eta(d.r2, k);
+		rmin = vmin(rmin, d.r2);
+		acc[0] = vfma(eta, vfms(tg[6], b.x, vmul(tg[3], a.w)), acc[0]);
+		acc[1] = vfma(eta, vfms(tg[6], b.y, vmul(tg[4], a.w)), acc[1]);
+		acc[2] = vfma(eta, vfms(tg[6], b.z, vmul(tg[5], a.w)), acc[2]);
+	}
+};
+
+template <int REG> struct P2DViscMin : P2DVisc<REG> {
+	template <int W> __device__ __forceinline__ static void pair_min(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, Vec<W> &rmin, const PairConsts &k) {
+		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
+		const Vec<W> r2 = vfma(dy, dy, vmul(dx, dx));
+		const Vec<W> eta = Eta2D<REG>::eta(r2, k);
+		rmin = vmin(rmin, r2);
+		acc[0] = vfma(eta, vfms(tg[3], a.z, vmul(tg[2], a.w)), acc[0]);
+	}
+};
+
+struct P3DDvortWMin : P3DDvort<REG_WINCKELMANS> {
+	template <int W> __device__ __forceinline__ static void pair_min(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, Vec<W> &rmin, const PairConsts &k) {
+		const Rad3<W> d = rad3(tg, a);
+		rmin = vmin(rmin, d.r2);
+		// Reg3D<REG_WINCKELMANS>::AB without the selection on A
+		const Vec<W> a1 = vfma(d.r2, k.c0, 1.0f), b1 = vfma(d.r2, k.c0, 2.5f), b2 = vfma(d.r2, k.c1, k.c2);
+		const Vec<W> ra = vrsqrt(a1), ra2 = vmul(ra, ra), ra4 = vmul(ra2, ra2), ra5 = vmul(ra4, ra);
+		const Vec<W> A = vmul(b1, ra5), B1 = b2, B2 = vmul(ra5, ra2);
+		const Vec<W> cx = vfms(tg[4], b.z, vmul(tg[5], b.y));
+		const Vec<W> cy = vfms(tg[5], b.x, vmul(tg[3], b.z));
+		const Vec<W> cz = vfms(tg[3], b.y, vmul(tg[4], b.x));
+		const Vec<W> trip = vfma(d.z, cz, vfma(d.y, cy, vmul(d.x, cx)));
+		const Vec<W> s = vmul(vmul(B1, trip), B2);
+		acc[0] = vfma(s, d.x, vfma(A, cx, acc[0]));
+		acc[1] = vfma(s, d.y, vfma(A, cy, acc[1]));
+		acc[2] = vfma(s, d.z, vfma(A, cz, acc[2]));
+	}
+};
+
+// m2m_kernel (cvortex_b200/csrc/m2m_kernel.cuh) with the chain test replaced: P::pair_min() over the
+// chain, then "is any lane's min(r^2) zero?" -> the production guarded form P::pair<W, true>().
+template <class P, int T, int B, int MINB>
+__global__ void __launch_bounds__(B, MINB) m2m_kernel_min(const M2MArgs args)
+{
+	constexpr int S = kSrcTile;
+	constexpr uint32_t kTileBytes = S * sizeof(float4);
+	__shared__ __align__(128) float4 tileA[2][S];
+	__shared__ __align__(128) float4 tileB[2][P::NSRC4 == 2 ? S : 1];
+	__shared__ __align__(8) uint64_t full[2];
+	const int tid = threadIdx.x;
+	const int tile0 = blockIdx.y * args.tiles_per_chunk;
+	const int ntile = min(args.tiles_per_chunk, args.n_src_tiles - tile0);
+	const float4 *gA = args.srcA + (size_t)tile0 * S;
+	const float4 *gB = args.srcB + (size_t)tile0 * S;
+	if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+	__syncthreads();
+	if (tid == 0 && ntile > 0) {
+		mbar_expect_tx(&full[0], kTileBytes * P::NSRC4);
+		bulk_g2s(tileA[0], gA, kTileBytes, &full[0]);
+		if (P::NSRC4 == 2) bulk_g2s(tileB[0], gB, kTileBytes, &full[0]);
+	}
+	constexpr int W = 2, NV = T / W;
+	static_assert(T % 2 == 0, "packed lanes only");
+	const long base = (long)blockIdx.x * (B * T) + tid;
+	Vec<W> tg[NV][P::NTGT];
+	double dacc[T][P::NACC];
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		long i = base + (long)t * B;
+		i = i < args.n_tgt ? i : (long)args.n_tgt - 1;
+		float one[P::NTGT];
+		P::load_target(args.tgt + i * P::TCOLS, one);
+#pragma unroll
+		for (int c = 0; c < P::NTGT; ++c) tg[t / W][c].set(t % W, one[c]);
+#pragma unroll
+		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
+	}
+	for (int it = 0; it < ntile; ++it) {
+		const int buf = it & 1;
+		if (tid == 0 && it + 1 < ntile) {
+			mbar_expect_tx(&full[buf ^ 1], kTileBytes * P::NSRC4);
+			bulk_g2s(tileA[buf ^ 1], gA + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
+			if (P::NSRC4 == 2) bulk_g2s(tileB[buf ^ 1], gB + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
+		}
+		mbar_wait(&full[buf], (it >> 1) & 1);
+		const float4 *sA = tileA[buf];
+		const float4 *sB = tileB[P::NSRC4 == 2 ? buf : 0];
+		Vec<W> acc[NV][P::NACC], rmin = bc<W>(3.0e38f);
+#pragma unroll
+		for (int v = 0; v < NV; ++v)
+#pragma unroll
+			for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+#pragma unroll 8
+		for (int j = 0; j < S; ++j) {
+			const float4 a = sA[j];
+			float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (P::NSRC4 == 2) b = sB[j];
+#pragma unroll
+			for (int v = 0; v < NV; ++v) P::template pair_min<W>(tg[v], a, b, acc[v], rmin, args.k);
+		}
+		// (one running minimum for all of the thread's targets: any coincidence re-evaluates the chain)
+		if (!(fminf(rmin.lane(0), rmin.lane(1)) > 0.0f)) {
+#pragma unroll
+			for (int v = 0; v < NV; ++v)
+#pragma unroll
+				for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+#pragma unroll 8
+			for (int j = 0; j < S; ++j) {
+				const float4 a = sA[j];
+				float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (P::NSRC4 == 2) b = sB[j];
+#pragma unroll
+				for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+			}
+		}
+#pragma unroll
+		for (int t = 0; t < T; ++t)
+#pragma unroll
+			for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
+		__syncthreads();
+	}
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		const long i = base + (long)t * B;
+		if (i < args.n_tgt) {
+			double res[P::NOUT];
+			P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
+			double *dst = args.partial + ((size_t)blockIdx.y * args.n_tgt + i) * P::NOUT;
+#pragma unroll
+			for (int c = 0; c < P::NOUT; ++c) dst[c] = res[c];
+		}
+	}
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
 struct Bench {
-	float4 *A, *B; float *tgt_pts, *tgt_self; float *out[2]; double *partial; int n; double peak_lane;
+	float4 *A, *B; float *tgt_pts, *tgt_self, *tgt_self4; float *out[2]; double *partial; int n; double peak_lane;
 	cudaEvent_t e0, e1;
 };
 
@@ -98,6 +247,49 @@ static void guarded_vs_optimistic(Bench &b, const char *name, bool self) {
 	double r[2];
 	for (int m = 0; m < 2; ++m) r[m] = pairs / (best[m] * 1e-3);
 	printf("%-22s %-5s T=%d  guarded %8.3f ms %7.1f Gpair/s %5.1f%%   optimistic %8.3f ms %7.1f Gpair/s %5.1f%%   x%.3f  bits %s\n",
+	       name, self ? "self" : "indep", T, best[0], r[0] * 1e-9, 100.0 * r[0] * P::LANE_OPS / b.peak_lane,
+	       best[1], r[1] * 1e-9, 100.0 * r[1] * P::LANE_OPS / b.peak_lane, best[0] / best[1], same ? "identical" : "DIFFER");
+	fflush(stdout);
+}
+
+
+// production kernel (guard = FSETP + FSEL per pair) vs m2m_kernel_min on the same inputs
+template <class P, class PMIN, int T, int BLK, int MINB>
+static void guard_vs_running_min(Bench &b, const char *name, bool self) {
+	const int n = b.n, chunks = 8;
+	const int n_tiles = n / kSrcTile;
+	M2MArgs a = {};
+	a.srcA = b.A; a.srcB = b.B; a.n_src_tiles = n_tiles;
+	a.tiles_per_chunk = (n_tiles + chunks - 1) / chunks;
+	const int gy = (n_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+	a.tgt = self ? (P::TCOLS == 4 ? b.tgt_self4 : b.tgt_self) : b.tgt_pts; a.n_tgt = n; a.partial = b.partial;
+	a.k = P::make_consts(0.02f, 1.0f);
+	const dim3 grid((n + BLK * T - 1) / (BLK * T), gy);
+	float best[2] = {1e30f, 1e30f};
+	const size_t nvals = (size_t)n * P::NOUT;
+	for (int mode = 0; mode < 2; ++mode) {
+		a.out = b.out[mode];
+		for (int rep = 0; rep < 3; ++rep) {
+			CK(cudaEventRecord(b.e0));
+			if (mode == 0) m2m_kernel<P, T, BLK, MINB><<<grid, BLK>>>(a);
+			else m2m_kernel_min<PMIN, T, BLK, MINB><<<grid, BLK>>>(a);
+			CK(cudaEventRecord(b.e1));
+			CK(cudaEventSynchronize(b.e1));
+			CK(cudaGetLastError());
+			const float ms = time_ms(b.e0, b.e1);
+			if (ms < best[mode]) best[mode] = ms;
+		}
+		reduce_partials_kernel<<<(unsigned)((nvals + 255) / 256), 256>>>(b.partial, b.out[mode], (long)nvals, gy);
+		CK(cudaDeviceSynchronize());
+	}
+	std::vector<float> h0(nvals), h1(nvals);
+	CK(cudaMemcpy(h0.data(), b.out[0], sizeof(float) * nvals, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(h1.data(), b.out[1], sizeof(float) * nvals, cudaMemcpyDeviceToHost));
+	const bool same = memcmp(h0.data(), h1.data(), sizeof(float) * nvals) == 0;
+	const double pairs = (double)n * n;
+	double r[2];
+	for (int m = 0; m < 2; ++m) r[m] = pairs / (best[m] * 1e-3);
+	printf("%-22s %-5s T=%d  select/pair %8.3f ms %7.1f Gpair/s %5.1f%%   running min %8.3f ms %7.1f Gpair/s %5.1f%%   x%.3f  bits %s\n",
 	       name, self ? "self" : "indep", T, best[0], r[0] * 1e-9, 100.0 * r[0] * P::LANE_OPS / b.peak_lane,
 	       best[1], r[1] * 1e-9, 100.0 * r[1] * P::LANE_OPS / b.peak_lane, best[0] / best[1], same ? "identical" : "DIFFER");
 	fflush(stdout);
@@ -163,6 +355,8 @@ int main(int argc, char **argv) {
 	CK(cudaMemcpy(b.B, hB.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(b.tgt_pts, hp.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(b.tgt_self, hs.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
+	CK(cudaMalloc(&b.tgt_self4, sizeof(float4) * n));                       // the packed P2D records are their own target rows
+	CK(cudaMemcpy(b.tgt_self4, hA.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
 
 	printf("\n== part 2: pair kernel, guarded form only vs optimistic chains, n = m = %d, 8 source chunks\n", n);
 	// (rows of 7 floats serve every op: 3-column ops read a prefix with a stride of their own, so `self`
@@ -179,6 +373,13 @@ int main(int argc, char **argv) {
 	guarded_vs_optimistic<F3DDvort, 8, 128, 2>(b, "F3D dvort", true);
 	guarded_vs_optimistic<P3DDvort<REG_GAUSSIAN>, 4, 256, 2>(b, "P3D dvort gaussian", true);
 	guarded_vs_optimistic<P3DVel<REG_GAUSSIAN>, 4, 256, 2>(b, "P3D vel gaussian", false);
+
+	printf("\n== part 3 (experiment): guard as a select per pair (production) vs running min(r^2) + guarded re-evaluation\n");
+	guard_vs_running_min<P3DVisc<REG_WINCKELMANS>, P3DViscMin<REG_WINCKELMANS>, 8, 128, 2>(b, "P3D visc winckelmans", true);
+	guard_vs_running_min<P3DVisc<REG_GAUSSIAN>, P3DViscMin<REG_GAUSSIAN>, 8, 128, 2>(b, "P3D visc gaussian", true);
+	guard_vs_running_min<P3DDvort<REG_WINCKELMANS>, P3DDvortWMin, 8, 128, 2>(b, "P3D dvort winckelmans", true);
+	guard_vs_running_min<P2DVisc<REG_GAUSSIAN>, P2DViscMin<REG_GAUSSIAN>, 8, 128, 2>(b, "P2D visc gaussian", true);
+	guard_vs_running_min<P2DVisc<REG_WINCKELMANS>, P2DViscMin<REG_WINCKELMANS>, 2, 256, 3>(b, "P2D visc winckelmans", true);
 	printf("done\n");
 	return 0;
 }
