@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from util import call_abi, make_case, op_cases, rel_l2
+from util import call_abi, make_case, op_cases
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -10,7 +10,7 @@ reference is.
 import numpy as np
 import pytest
 
-from util import (REGS, VISC_REGS, SHAPES, call_abi, filaments, make_case, op_cases, particles2d,
+from util import (REGS, VISC_REGS, SHAPES, call_abi, filaments, make_case, op_cases,
                   particles3d, points, rel_l2, upstream_per_target_ok, vort_cases)
 
 pytestmark = pytest.mark.gpu

@@ -1,6 +1,6 @@
 """One few-target call (1M sources on M targets) for `ncu --metrics gpu__time_duration.sum`: shows the split
 between pack_sources, the pair kernel and the reduction of the FP64 partials.  python tools/small_prof.py M"""
-import os, sys, numpy as np, torch
+import sys, numpy as np, torch
 sys.path.insert(0, '.')
 from cvortex_b200 import api
 api.initialise(); be = api.backend()
