@@ -30,7 +30,8 @@ namespace {
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_T{0}, g_force_chunks{0};
-std::atomic<int> g_guard_mode{-1};                           // -1 = not set: CVTX_B200_GUARDED decides, read once
+std::atomic<int> g_guard_mode{-1};
+std::atomic<int> g_f3d_mode{-2};                              // -2 = not set: CVTX_B200_F3D_MODE decides; -1 auto, 0 new, 1 reference form                           // -1 = not set: CVTX_B200_GUARDED decides, read once
 std::mutex g_devices_mu;
 std::vector<Device *> g_devices;
 int g_device_count = -2;                                       // -2 = not probed yet
@@ -93,53 +94,43 @@ int ensure_ready(Device *d) {                   // caller holds d->mu and has do
 }
 
 // ---- launch planning ----------------------------------------------------------
-struct Plan { int T, B, gx, gy, tiles_per_chunk; };
+struct Plan { int T, B, occ, grain, grid; long long tiles_t, total_grains; };
 
-// Pick the block geometry (targets per thread) and the number of source chunks.
-// Model: a launch is `waves` rounds of co-resident blocks; a block costs its tile count x its
-// target slots (a thread slot computes whether or not it holds a real target), shared `occ` ways,
-// over the geometry's measured relative efficiency, plus a fixed prologue; half a wave is lost
-// in the tail on average.  For large problems this reduces to "the op's preferred geometry,
-// >= 24 waves"; for small ones it trades padding against parallelism (10k x 10k, few targets).
-Plan make_plan(int n_src, int n_tgt, int n_out, int sm_count, int pref_T) {
+// Source sets below this many tiles are walked in grains (= FP32 chains) of 32 sources instead of
+// 256, so that a 10k x 10k call still cuts into enough equal runs for every resident block.  A
+// property of the SOURCES alone: every shard of a multi-GPU call rounds alike.
+constexpr int kSmallSourceTiles = 64;
+
+// Pick the block geometry (targets per thread).  The kernel is persistent and its runs are equal,
+// so a launch costs  (grains per block) x (slots per grain) x (blocks sharing an SM) / (the geometry's
+// measured relative efficiency): for large problems that is the op's preferred geometry, for small
+// ones it trades the padding of the last target tile against parallelism (10k x 10k, few targets).
+Plan make_plan(int n_src, int n_tgt, int sm_count, int pref_T) {
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
 	static const int cand_T[4] = {8, 4, 2, 1}, cand_B[4] = {128, 256, 256, 128}, cand_occ[4] = {2, 2, 3, 8};
 	static const double cand_eff[4] = {1.0, 0.985, 0.96, 0.79};      // profiles/sweep_ops_r1.txt, ubench_r1.txt
-	const double kPrologue = 16000.0;                                 // slot-pairs: ~1.5 us of one SM
-	const long mem_cap = (1L << 30) / ((long)n_tgt * n_out * 8 + 1);  // keep FP64 partials under 1 GiB
-	const int fT = g_force_T.load(), fC = g_force_chunks.load();
+	const int fT = g_force_T.load(), fG = g_force_chunks.load();
 	const int first = pref_T >= 8 ? 0 : (pref_T >= 4 ? 1 : (pref_T >= 2 ? 2 : 3));
+	const int grain = n_src_tiles < kSmallSourceTiles ? 32 : kSrcTile;
 	Plan p = {};
 	double best = 1e300;
 	for (int v = 0; v < 4; ++v) {
 		if (fT ? cand_T[v] != fT : v < first) continue;
-		const long slots_t = (long)cand_B[v] * cand_T[v];
-		const long tiles_t = ((long)n_tgt + slots_t - 1) / slots_t;
-		const long resident = (long)sm_count * cand_occ[v];
-		// candidate tiles-per-chunk values: every small one, then n_src_tiles / k
-		for (int pass = 0; pass < 2; ++pass) {
-			for (int k = 1; k <= 64; ++k) {
-				long tpc = pass == 0 ? k : (n_src_tiles + k - 1) / k;
-				if (n_src_tiles == 0) tpc = 0;
-				else if (tpc < 1 || tpc > n_src_tiles) continue;
-				long c = n_src_tiles ? (n_src_tiles + tpc - 1) / tpc : 1;
-				if (fC > 0) {
-					c = fC < n_src_tiles ? fC : (n_src_tiles ? n_src_tiles : 1);
-					tpc = n_src_tiles ? (n_src_tiles + c - 1) / c : 0;
-					c = n_src_tiles ? (n_src_tiles + tpc - 1) / tpc : 1;
-				}
-				if (c > 1 && c > mem_cap) continue;
-				if (c > 65535) continue;                                  // gridDim.y
-				if (c > 32 && tiles_t * 32 >= 24 * resident) continue;    // enough waves already: spare the partials
-				const long ctas = tiles_t * c;
-				const long waves = (ctas + resident - 1) / resident;
-				const double block = (double)tpc * kSrcTile * slots_t * cand_occ[v] / cand_eff[v] + kPrologue;
-				const double cost = ((double)waves + 0.5) * block + (c > 1 ? 2.0 * kPrologue : 0.0);
-				if (cost < best) {
-					best = cost;
-					p.T = cand_T[v]; p.B = cand_B[v]; p.gx = (int)tiles_t; p.gy = (int)c; p.tiles_per_chunk = (int)tpc;
-				}
-			}
+		const long long slots = (long long)cand_B[v] * cand_T[v];
+		const long long tiles_t = ((long long)n_tgt + slots - 1) / slots;
+		const long long total = tiles_t * n_src_tiles * (kSrcTile / grain);
+		long long grid = (long long)sm_count * cand_occ[v];
+		if (fG > 0) grid = fG;
+		if (grid > total) grid = total;
+		if (grid < 1) grid = 1;
+		const long long per_block = (total + grid - 1) / grid;
+		const long long sharing = (grid + sm_count - 1) / sm_count;
+		const double cost = (double)per_block * grain * (double)slots * (double)sharing / cand_eff[v]
+		                    + 4000.0 * (double)slots / 128.0;         // per-block prologue, ~1 us
+		if (cost < best) {
+			best = cost;
+			p.T = cand_T[v]; p.B = cand_B[v]; p.occ = cand_occ[v]; p.grain = grain; p.grid = (int)grid;
+			p.tiles_t = tiles_t; p.total_grains = total;
 		}
 	}
 	return p;
@@ -161,10 +152,54 @@ int guard_mode() {
 	return v;
 }
 
+// ---- run-time pipe peaks (cvtx_b200_measure_peak): the roofline denominators, measured ----
+// Packed FP32 FMA (FFMA2): 8 independent chains per thread, two lane-ops per instruction slot.
+__global__ void __launch_bounds__(256) peak_ffma2_kernel(float *out, int iters, float a, float b) {
+	float2 x[8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int r = 0; r < 16; ++r)
+#pragma unroll
+			for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], make_float2(a, a), make_float2(b, b));
+	}
+	float s = 0.f;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+	if (s == 123.456f) out[0] = s;
+}
+__global__ void __launch_bounds__(256) peak_mufu_kernel(float *out, int iters) {
+	float x[8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i) x[i] = 1.0f + threadIdx.x * 1e-3f + i;
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int r = 0; r < 16; ++r)
+#pragma unroll
+			for (int i = 0; i < 8; ++i) x[i] = mufu_rsqrt(x[i]);
+	}
+	float s = 0.f;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) s += x[i];
+	if (s == 123.456f) out[0] = s;
+}
+
+// -1 = decided per call from the filaments (f3d_pick_mode); 0 / 1 pin the fast form (tests, experiments)
+int f3d_mode_override() {
+	int v = g_f3d_mode.load();
+	if (v == -2) {
+		const char *e = getenv("CVTX_B200_F3D_MODE");
+		v = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
+		g_f3d_mode = v;
+	}
+	return v;
+}
+
 struct Launcher {
 	M2MArgs args; Plan plan; cudaStream_t st; cudaError_t err;
 	template <class P> void run() {
-		const dim3 grid(plan.gx, plan.gy);
+		const dim3 grid(plan.grid);
 		if (plan.T == 8) m2m_kernel<P, 8, 128, 2><<<grid, 128, 0, st>>>(args);
 		else if (plan.T == 4) m2m_kernel<P, 4, 256, 2><<<grid, 256, 0, st>>>(args);
 		else if (plan.T == 2) m2m_kernel<P, 2, 256, 3><<<grid, 256, 0, st>>>(args);
@@ -232,7 +267,7 @@ void cvtx_b200_release(void) {
 			if (!d->ready) continue;
 			cudaSetDevice((int)i);
 			cudaDeviceSynchronize();
-			Buffer *all[] = {&d->packedA, &d->packedB, &d->partial, &d->d_src, &d->d_tgt, &d->d_out};
+			Buffer *all[] = {&d->packedA, &d->packedB, &d->packedC, &d->pieces, &d->tickets, &d->aux, &d->d_src, &d->d_tgt, &d->d_out};
 			for (Buffer *b : all) b->release();
 			for (Buffer &b : d->remesh) b.release();
 			cudaEventDestroy(d->arena_idle); cudaEventDestroy(d->k_start); cudaEventDestroy(d->k_stop);
@@ -261,17 +296,19 @@ int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tp
 	Info q = {};
 	if (!d || n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "bad device or counts");
 	if (!dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "bad op");
-	const Plan p = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount, q.pref_T);
+	const Plan p = make_plan(n_src, n_tgt, d->prop.multiProcessorCount, q.pref_T);
 	if (block) *block = p.B;
 	if (tpt) *tpt = p.T;
-	if (grid_x) *grid_x = p.gx;
-	if (grid_y) *grid_y = p.gy;
+	if (grid_x) *grid_x = p.grid;
+	if (grid_y) *grid_y = p.grain;
 	return CVTX_B200_OK;
 }
 
 unsigned long long cvtx_b200_kernel_launches(void) { return g_launches.load(); }
 
 void cvtx_b200_tune(int force_T, int force_chunks) { g_force_T = force_T; g_force_chunks = force_chunks; }
+
+void cvtx_b200_f3d_mode(int mode) { g_f3d_mode = (mode == 0 || mode == 1) ? mode : -1; }
 
 void cvtx_b200_guarded_only(int mode) { g_guard_mode = (mode == 1 || mode == 2) ? mode : 0; }
 
@@ -287,6 +324,42 @@ float cvtx_b200_last_pair_kernel_ms(int device) {
 	if (cudaEventSynchronize(d->k_stop) != cudaSuccess) return -1.f;
 	if (cudaEventElapsedTime(&ms, d->k_start, d->k_stop) != cudaSuccess) return -1.f;
 	return ms;
+}
+
+int cvtx_b200_measure_peak(int device, int what, double *ops_per_second)
+{
+	g_err.clear();
+	Device *d = get_device(device);
+	if (!d || !ops_per_second || (what != 0 && what != 1)) return fail(CVTX_B200_ERR_ARGUMENT, "bad device, selector or pointer");
+	std::lock_guard<std::mutex> lk(d->mu);
+	CUDA_TRY(cudaSetDevice(device));
+	if (int rc = ensure_ready(d)) return rc;
+	float *sink = nullptr;
+	CUDA_TRY(cudaMalloc(&sink, sizeof(float)));
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));
+	CUDA_TRY(cudaEventCreate(&e1));
+	const int blocks = d->prop.multiProcessorCount * 8, threads = 256;
+	const int iters = what == 0 ? 4096 : 1024;
+	double best = 0.0;
+	cudaError_t err = cudaSuccess;
+	for (int rep = 0; rep < 4 && err == cudaSuccess; ++rep) {          // first pass warms up
+		cudaEventRecord(e0, d->stream);
+		if (what == 0) peak_ffma2_kernel<<<blocks, threads, 0, d->stream>>>(sink, iters, 0.999f, 1e-3f);
+		else peak_mufu_kernel<<<blocks, threads, 0, d->stream>>>(sink, iters);
+		cudaEventRecord(e1, d->stream);
+		err = cudaEventSynchronize(e1);
+		float ms = 0.f;
+		if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+		// per thread and iteration: 16 x 8 instructions; an FFMA2 is two lane-ops
+		const double ops = (double)blocks * threads * iters * 16.0 * 8.0 * (what == 0 ? 2.0 : 1.0);
+		if (rep > 0 && ms > 0.f && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+	g_launches += 4;
+	CUDA_TRY(err);
+	*ops_per_second = best;
+	return CVTX_B200_OK;
 }
 
 int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, int n_src,
@@ -312,37 +385,65 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 		return CVTX_B200_OK;
 	}
 
-	const Plan plan = make_plan(n_src, n_tgt, q.nout, d->prop.multiProcessorCount, q.pref_T);
+	const Plan plan = make_plan(n_src, n_tgt, d->prop.multiProcessorCount, q.pref_T);
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
 	const int n_pad = n_src_tiles * kSrcTile;
-	const bool two = src_kind(op) != SRC_P2D;
+	const int records = src_records(op);
+	if ((plan.total_grains + plan.grid - 1) / plan.grid > 2147483647LL || plan.tiles_t > 2147483647LL)
+		return fail(CVTX_B200_ERR_ARGUMENT, "problem too large for one launch (more than 2^31 grains per block)");
+	const bool filament = op_is_filament(op);
 
 	// the arena may still be in use by an earlier call on another stream
 	CUDA_TRY(cudaStreamWaitEvent(st, d->arena_idle, 0));
 	const size_t need_packed = (size_t)n_pad * sizeof(float4);
-	const size_t need_partial = plan.gy > 1 ? sizeof(double) * (size_t)plan.gy * n_tgt * q.nout : 0;
-	if (need_packed > d->packedA.cap || (two && need_packed > d->packedB.cap) || need_partial > d->partial.cap) {
+	const size_t need_pieces = sizeof(double) * 2 * (size_t)plan.grid * plan.T * plan.B * q.nout;
+	const size_t need_tickets = sizeof(int) * (size_t)plan.tiles_t;
+	const size_t need_aux = filament ? sizeof(F3DStats) * (size_t)n_src_tiles + 64 : 0;
+	if (need_packed > d->packedA.cap || (records >= 2 && need_packed > d->packedB.cap) || (records >= 3 && need_packed > d->packedC.cap)
+	    || need_pieces > d->pieces.cap || need_tickets > d->tickets.cap || need_aux > d->aux.cap) {
 		CUDA_TRY(cudaDeviceSynchronize());             // growing frees memory earlier launches may still read
 		CUDA_TRY(d->packedA.reserve(need_packed));
-		if (two) CUDA_TRY(d->packedB.reserve(need_packed));
-		CUDA_TRY(d->partial.reserve(need_partial));
+		if (records >= 2) CUDA_TRY(d->packedB.reserve(need_packed));
+		if (records >= 3) CUDA_TRY(d->packedC.reserve(need_packed));
+		CUDA_TRY(d->pieces.reserve(need_pieces));
+		CUDA_TRY(d->aux.reserve(need_aux));
+		if (need_tickets > d->tickets.cap) {
+			CUDA_TRY(d->tickets.reserve(need_tickets));
+			CUDA_TRY(cudaMemsetAsync(d->tickets.p, 0, d->tickets.cap, st));      // the kernel leaves them at zero
+		}
 	}
 
-	pack_sources_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src_kind(op), src_cols(op), src, n_src, n_pad,
-	                                                          (float4 *)d->packedA.p, two ? (float4 *)d->packedB.p : nullptr);
+	// aux: [0, 64) the filament mode word, then one F3DStats per packed tile
+	int *mode_word = (int *)d->aux.p;
+	F3DStats *stats = filament ? (F3DStats *)((char *)d->aux.p + 64) : nullptr;
+	pack_sources_kernel<<<n_src_tiles, kSrcTile, 0, st>>>(src_kind(op), src_cols(op), src, n_src, n_pad, (float4 *)d->packedA.p,
+	                                                        records >= 2 ? (float4 *)d->packedB.p : nullptr,
+	                                                        records >= 3 ? (float4 *)d->packedC.p : nullptr, stats);
 	CUDA_TRY(cudaGetLastError());
+	unsigned long long launched = 2;
+	if (filament) {
+		f3d_mode_kernel<<<1, 256, 0, st>>>(stats, n_src_tiles, n_src, f3d_mode_override(), mode_word);
+		CUDA_TRY(cudaGetLastError());
+		++launched;
+	}
 
 	ConstsOf ck = {sigma, nu, {}};
 	dispatch_op(op, reg, ck);
 	Launcher L = {};
 	L.args.srcA = (const float4 *)d->packedA.p;
-	L.args.srcB = two ? (const float4 *)d->packedB.p : nullptr;
+	L.args.srcB = records >= 2 ? (const float4 *)d->packedB.p : nullptr;
+	L.args.srcC = records >= 3 ? (const float4 *)d->packedC.p : nullptr;
+	L.args.src_raw = src;
+	L.args.n_src = n_src;
 	L.args.n_src_tiles = n_src_tiles;
-	L.args.tiles_per_chunk = plan.tiles_per_chunk;
+	L.args.grain = plan.grain;
+	L.args.total_grains = plan.total_grains;
 	L.args.tgt = tgt;
 	L.args.n_tgt = n_tgt;
 	L.args.out = out;
-	L.args.partial = (double *)d->partial.p;
+	L.args.pieces = (double *)d->pieces.p;
+	L.args.tickets = (int *)d->tickets.p;
+	L.args.f3d_mode = mode_word;
 	L.args.k = ck.k;
 	const int gm = guard_mode();
 	L.args.exact_only = (gm == 1 || (gm == 0 && n_src_tiles < kMinTilesOptimistic)) ? 1 : 0;
@@ -353,16 +454,6 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	CUDA_TRY(L.err);
 	CUDA_TRY(cudaEventRecord(d->k_stop, st));
 	d->timed = true;
-	unsigned long long launched = 2;
-	if (plan.gy > 1) {
-		const long n_vals = (long)n_tgt * q.nout;
-		if (n_vals <= 8192 && plan.gy >= 64)      // few values, many chunks: a warp per value
-			reduce_partials_wide_kernel<<<(unsigned)((n_vals * 32 + 255) / 256), 256, 0, st>>>((const double *)d->partial.p, out, n_vals, plan.gy);
-		else
-			reduce_partials_kernel<<<(unsigned)((n_vals + 255) / 256), 256, 0, st>>>((const double *)d->partial.p, out, n_vals, plan.gy);
-		CUDA_TRY(cudaGetLastError());
-		++launched;
-	}
 	CUDA_TRY(cudaEventRecord(d->arena_idle, st));
 	g_launches += launched;
 	return CVTX_B200_OK;

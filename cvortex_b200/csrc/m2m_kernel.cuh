@@ -6,33 +6,37 @@
 // 256-wide shared-memory tree adds them up, work-item 0 read-modify-writes the
 // target's result, and the host launches one NDRange per 256 sources.  Here
 //
-//   grid  = (target tiles, source chunks); ONE launch per call
-//   block = B threads, each owning T targets held in registers for the
-//           whole kernel (positions + per-target attributes)
-//   the block streams its source chunk through shared memory in tiles of S
-//   packed records, double-buffered with 1-D TMA bulk copies
+//   ONE launch per call, PERSISTENT: grid = the blocks that are resident at once
+//   (SMs x blocks per SM).  The work -- (target tile) x (source grain) cells,
+//   target-tile-major -- is one linear sequence cut into `gridDim.x` contiguous
+//   runs of equal length, so every block does the same number of pair
+//   evaluations whatever the target count: no tail wave.  A block walks its
+//   run: B threads, each owning T targets held in registers (positions +
+//   per-target attributes) while the block streams source tiles of S packed
+//   records through shared memory, double-buffered with 1-D TMA bulk copies
 //   (cp.async.bulk + mbarrier transaction counts) issued by one thread, so the
-//   math warps spend no issue slots on loads or address arithmetic;
+//   math warps spend no issue slots on loads or address arithmetic; the stream
+//   simply continues across target-tile boundaries.
 //   every thread reads the same source record at the same time -> LDS.128
-//   broadcasts, 2 per source per warp, amortised over T targets;
-//   running sums are FP32 per chain (a tile, or Policy::CHAIN sources) and
-//   are flushed into FP64 accumulators, matching the reference CPU path's
-//   double accumulation (src/P3D.cpp:237-249) at ~0.1 % extra instructions;
-//   ops whose coincident-pair / non-finite guards only ever replace an inf or a
-//   NaN (Policy::OPTIMISTIC, pair_math.cuh "GUARDS") run the pair loop without
+//   broadcasts, amortised over T targets;
+//   running sums are FP32 per chain (a grain: 256 sources, or 32 for small
+//   source sets) and are flushed into FP64 accumulators, matching the
+//   reference CPU path's double accumulation (src/P3D.cpp:237-249);
+//   ops whose coincident-pair guards only ever replace an inf or a NaN
+//   (Policy::OPTIMISTIC, pair_math.cuh "GUARDS") run the pair loop without
 //   them and check the FP32 running sums once per chain; a chain that comes out
-//   non-finite is evaluated again with the guards (bit-identical results, and
-//   2-6 ALU-pipe instructions fewer per pair);
-//   the epilogue applies Policy::finish() in FP64 and either writes the
-//   final floats (one chunk) or FP64 partials that reduce_partials_kernel
-//   adds in a fixed order (deterministic, no atomics).
-//
-// The source-chunk dimension exists for load balance only: 1M targets give 977
-// target tiles of 1024, i.e. 3.3 waves on 296 resident blocks (18 % tail
-// loss); splitting the sources C ways turns that into 3.3*C waves of work
-// units that the hardware block scheduler hands out dynamically.  blockIdx.x
-// (fastest) walks the target tiles so that co-resident blocks read the same
-// source chunk from L2.
+//   non-finite is evaluated again with the guards (bit-identical results);
+//   the filament ops (Policy::HYBRID, pair_math.cuh "FILAMENTS") run their fast
+//   form over sub-chains of 32 sources and re-evaluate, per target, the
+//   sub-chains whose flag fired in the reference's own arithmetic;
+//   a run that covers a target tile completely finishes it in registers
+//   (Policy::finish() in FP64) and writes the final floats.  Only the tiles a
+//   run boundary cuts -- at most two per block -- go through memory: each
+//   block writes its FP64 piece, takes a ticket on the tile, and the block that
+//   arrives last adds the pieces in run order and writes the result
+//   (deterministic, no floating-point atomics, no second kernel, and a few MB
+//   of scratch where the first version of this kernel wrote [chunks][m] FP64
+//   partials -- 550 MB at 1M x 1M -- for a reduce kernel to read back).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,12 +49,18 @@ constexpr int kSrcTile = 256;   // S: packed sources per shared-memory tile (als
 struct M2MArgs {
 	const float4 *srcA;        // packed source records, padded to a multiple of kSrcTile
 	const float4 *srcB;        // second record (unused when Policy::NSRC4 == 1)
-	int n_src_tiles;           // total tiles of kSrcTile sources
-	int tiles_per_chunk;       // tiles handled by one blockIdx.y
+	const float4 *srcC;        // third record (filaments)
+	const float *src_raw;      // the raw source rows (filaments: the reference-arithmetic tier reads them)
+	int n_src;                 // real sources
+	int n_src_tiles;           // tiles of kSrcTile sources
+	int grain;                 // sources per grain = FP32 chain length: 256, or 32 for small source sets
+	long long total_grains;    // (target tiles) x (n_src_tiles x 256 / grain)
 	const float *tgt;          // raw target rows, Policy::TCOLS floats each
 	int n_tgt;
-	float *out;                // final result, Policy::NOUT floats per target (gridDim.y == 1)
-	double *partial;           // [gridDim.y][n_tgt][NOUT] FP64 partials (gridDim.y > 1)
+	float *out;                // final result, Policy::NOUT floats per target
+	double *pieces;            // [2 x gridDim.x][T][B][NOUT] FP64 pieces of the target tiles a run boundary cuts
+	int *tickets;              // [target tiles], zero between launches
+	const int *f3d_mode;       // filaments: which fast form (pair_math.cuh f3d_pick_mode), decided while packing
 	PairConsts k;
 	int exact_only;            // 1: always evaluate the guarded pair form (never the optimistic one)
 };
@@ -84,27 +94,56 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// The run of grains block b of R owns: [run_begin(b), run_begin(b + 1)).
+__host__ __device__ __forceinline__ long long run_begin(long long b, long long R, long long total) {
+	return (long long)(((unsigned __int128)b * (unsigned __int128)total) / (unsigned __int128)R);
+}
+// The block whose run holds grain x.
+__host__ __device__ __forceinline__ long long run_of(long long x, long long R, long long total) {
+	return (long long)((((unsigned __int128)(x + 1)) * (unsigned __int128)R - 1) / (unsigned __int128)total);
+}
+
+// The filament ops' slow tier: sub-chain [j0, j0 + F3D_SUB) of the source order for ONE target, in the
+// reference's own arithmetic (Policy::exact), from the raw rows.  Kept out of line: it runs for one pair
+// in a million and must not cost the pair loop registers.
+template <class P>
+__device__ __noinline__ void exact_subchain(const float *__restrict__ src_raw, long j0, long j1, const float *__restrict__ tgt_row, float *sums)
+{
+	float acc[P::NACC];
+#pragma unroll
+	for (int c = 0; c < P::NACC; ++c) acc[c] = 0.0f;
+	for (long j = j0; j < j1; ++j) P::exact(src_raw + j * 7, tgt_row, acc);
+#pragma unroll
+	for (int c = 0; c < P::NACC; ++c) sums[c] = acc[c];
+}
+
 template <class P, int T, int B, int MINB>
 __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 {
 	constexpr int S = kSrcTile;
-	constexpr int CHAIN = P::CHAIN ? P::CHAIN : S;
 #ifndef CVTX_UNROLL
 #define CVTX_UNROLL 8
 #endif
-	constexpr int UNROLL = CHAIN < CVTX_UNROLL ? CHAIN : CVTX_UNROLL;
-	static_assert(S % CHAIN == 0, "a tile must hold whole chains");
+	constexpr int UNROLL = CVTX_UNROLL;
 	constexpr uint32_t kTileBytes = S * sizeof(float4);
+	constexpr int NR = P::NSRC4;
 
-	__shared__ __align__(128) float4 tileA[2][S];
-	__shared__ __align__(128) float4 tileB[2][P::NSRC4 == 2 ? S : 1];
+	__shared__ __align__(128) float4 tile[2][NR][S];
 	__shared__ __align__(8) uint64_t full[2];
+	__shared__ int s_ticket;
 
 	const int tid = threadIdx.x;
-	const int tile0 = blockIdx.y * args.tiles_per_chunk;
-	const int ntile = min(args.tiles_per_chunk, args.n_src_tiles - tile0);
-	const float4 *gA = args.srcA + (size_t)tile0 * S;
-	const float4 *gB = args.srcB + (size_t)tile0 * S;
+	const int G = args.grain;
+	const int gps = S / G;                                              // grains per source tile
+	const int gpt = args.n_src_tiles * gps;                             // grains per target tile
+	// this block's run, as (target tile, grain within the tile, grains left): 32-bit state in the loop
+	int tt, gs, left;
+	bool from_start;                                                    // the run entered tile tt at the tile's first grain
+	{
+		const long long g0 = run_begin(blockIdx.x, gridDim.x, args.total_grains), g1 = run_begin(blockIdx.x + 1, gridDim.x, args.total_grains);
+		tt = (int)(g0 / gpt); gs = (int)(g0 % gpt); left = (int)(g1 - g0);
+		from_start = gs == 0;
+	}
 
 	if (tid == 0) {
 		mbar_init(&full[0], 1);
@@ -112,93 +151,167 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		mbar_fence_init();
 	}
 	__syncthreads();
-	if (tid == 0 && ntile > 0) {
-		mbar_expect_tx(&full[0], kTileBytes * P::NSRC4);
-		bulk_g2s(tileA[0], gA, kTileBytes, &full[0]);
-		if (P::NSRC4 == 2) bulk_g2s(tileB[0], gB, kTileBytes, &full[0]);
-	}
 
-	// ---- this thread's T targets, strided by B so a warp touches contiguous rows.
+	auto fetch = [&](int src_tile, int buf) {                           // thread 0 only
+		const size_t off = (size_t)src_tile * S;
+		mbar_expect_tx(&full[buf], kTileBytes * NR);
+		bulk_g2s(tile[buf][0], args.srcA + off, kTileBytes, &full[buf]);
+		if (NR >= 2) bulk_g2s(tile[buf][NR >= 2 ? 1 : 0], args.srcB + off, kTileBytes, &full[buf]);
+		if (NR >= 3) bulk_g2s(tile[buf][NR >= 3 ? 2 : 0], args.srcC + off, kTileBytes, &full[buf]);
+	};
+	if (tid == 0 && left > 0) fetch(gs / gps, 0);
+
 	// Two targets share one Vec<2> (packed FP32x2 lanes) when T is even.
 	constexpr int W = (T % 2 == 0) ? 2 : 1;
 	constexpr int NV = T / W;
-	const long base = (long)blockIdx.x * (B * T) + tid;
 	Vec<W> tg[NV][P::NTGT];
 	double dacc[T][P::NACC];      // (moving these to shared memory to raise occupancy was measured: no gain)
-#pragma unroll
-	for (int t = 0; t < T; ++t) {
-		long i = base + (long)t * B;
-		i = i < args.n_tgt ? i : (long)args.n_tgt - 1;          // clamp: tail threads redo the last target, never store
-		float one[P::NTGT];
-		P::load_target(args.tgt + i * P::TCOLS, one);
-#pragma unroll
-		for (int c = 0; c < P::NTGT; ++c) tg[t / W][c].set(t % W, one[c]);
-#pragma unroll
-		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
-	}
-
-	// A warp none of whose target slots is real (most of the block in a few-target call) only
-	// keeps the tile hand-over in step.  Slot (t = 0, lane 0) is the warp's lowest target index.
-	// Only the T = 1 geometry, the one the planner gives few-target calls, carries the test: in
-	// the large-problem geometries it would cost the Gaussian kernels 0.8 % for a tail that is
-	// one block in a thousand.
-	const bool idle_warp = T == 1 && (long)blockIdx.x * (B * T) + (tid & ~31) >= (long)args.n_tgt;
 	const bool optimistic = P::OPTIMISTIC && !args.exact_only;
+	int f3d_mode = F3D_REF;
+	if (P::HYBRID) f3d_mode = *args.f3d_mode;
 
-	for (int it = 0; it < ntile; ++it) {
+	bool fresh = true;                                                  // the next step starts a target tile
+	bool idle_warp = false;
+	int it = 0;
+	while (left > 0) {
 		const int buf = it & 1;
-		if (tid == 0 && it + 1 < ntile) {                          // prefetch the next tile into the other buffer
-			mbar_expect_tx(&full[buf ^ 1], kTileBytes * P::NSRC4);
-			bulk_g2s(tileA[buf ^ 1], gA + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
-			if (P::NSRC4 == 2) bulk_g2s(tileB[buf ^ 1], gB + (size_t)(it + 1) * S, kTileBytes, &full[buf ^ 1]);
+		// this step: grains [gs, gs + n) of tile tt, all inside one source tile
+		int n = gps - gs % gps;
+		n = n < left ? n : left;
+		if (left > n) {                                                 // prefetch the next step's source tile into the other buffer
+			const int gs_next = gs + n == gpt ? 0 : gs + n;
+			if (tid == 0) fetch(gs_next / gps, buf ^ 1);
 		}
+		if (fresh) {
+			// ---- this thread's T targets of the new tile, strided by B so a warp touches contiguous rows
+			fresh = false;
+			const long base = (long)tt * (B * T) + tid;
+#pragma unroll
+			for (int t = 0; t < T; ++t) {
+				long i = base + (long)t * B;
+				i = i < args.n_tgt ? i : (long)args.n_tgt - 1;      // clamp: tail threads redo the last target, never store
+				float one[P::NTGT];
+				P::load_target(args.tgt + i * P::TCOLS, one);
+#pragma unroll
+				for (int c = 0; c < P::NTGT; ++c) tg[t / W][c].set(t % W, one[c]);
+#pragma unroll
+				for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
+			}
+			// A warp none of whose target slots is real (most of the block in a few-target call) only
+			// keeps the tile hand-over in step.  Only the T = 1 geometry, the one the planner gives
+			// few-target calls, carries the test.
+			idle_warp = T == 1 && (long)tt * (B * T) + (tid & ~31) >= (long)args.n_tgt;
+		}
+		const int lo = (gs % gps) * G, hi = lo + n * G;                 // this step's sources within the tile
 		if (!idle_warp) {
 			mbar_wait(&full[buf], (it >> 1) & 1);
-
-			const float4 *sA = tileA[buf];
-			const float4 *sB = tileB[P::NSRC4 == 2 ? buf : 0];
+			const float4 *sA = tile[buf][0];
+			const float4 *sB = tile[buf][NR >= 2 ? 1 : 0];
+			const float4 *sC = tile[buf][NR >= 3 ? 2 : 0];
 #pragma unroll 1
-			for (int j0 = 0; j0 < S; j0 += CHAIN) {
+			for (int j0 = lo; j0 < hi; j0 += G) {
 				Vec<W> acc[NV][P::NACC];
 #pragma unroll
 				for (int v = 0; v < NV; ++v)
 #pragma unroll
 					for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
-				bool guarded = true;
-				if (P::OPTIMISTIC && optimistic) {
-#pragma unroll UNROLL
-					for (int j = 0; j < CHAIN; ++j) {
-						const float4 a = sA[j0 + j];
-						float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-						if (P::NSRC4 == 2) b = sB[j0 + j];
+				if constexpr (P::HYBRID) {
+#pragma unroll 1
+					for (int s0 = j0; s0 < j0 + G; s0 += F3D_SUB) {
+						Vec<W> sub[NV][P::NACC], flag[NV];
 #pragma unroll
-						for (int v = 0; v < NV; ++v) P::template pair<W, false>(tg[v], a, b, acc[v], args.k);
-					}
-					// inf and NaN survive any further addition, so one sum over this thread's running sums
-					// tells whether a guard would have fired anywhere in the chain (a sum of finite values
-					// that overflows only costs a needless second evaluation)
-					Vec<W> chk = acc[0][0];
+						for (int v = 0; v < NV; ++v) {
+							flag[v] = bc<W>(3.0e38f);
 #pragma unroll
-					for (int v = 0; v < NV; ++v)
+							for (int c = 0; c < P::NACC; ++c) sub[v][c] = bc<W>(0.0f);
+						}
+						if (f3d_mode == F3D_NEW) {
+#pragma unroll 1
+							for (int j = 0; j < F3D_SUB; j += UNROLL) {
 #pragma unroll
-						for (int c = (v == 0 ? 1 : 0); c < P::NACC; ++c) chk = vadd(chk, acc[v][c]);
-					const float s = W == 2 ? chk.lane(0) + chk.lane(1) : chk.lane(0);
-					guarded = !(fabsf(s) <= 3.40282346e38f);
-					if (guarded) {
+								for (int u = 0; u < UNROLL; ++u) {
+									const float4 a = sA[s0 + j + u], b = sB[s0 + j + u], c = sC[s0 + j + u];
+#pragma unroll
+									for (int v = 0; v < NV; ++v) P::template fast<W, F3D_NEW>(tg[v], a, b, c, sub[v], flag[v], args.k);
+								}
+							}
+						} else {
+#pragma unroll 1
+							for (int j = 0; j < F3D_SUB; j += UNROLL) {
+#pragma unroll
+								for (int u = 0; u < UNROLL; ++u) {
+									const float4 a = sA[s0 + j + u], b = sB[s0 + j + u], c = sC[s0 + j + u];
+#pragma unroll
+									for (int v = 0; v < NV; ++v) P::template fast<W, F3D_REF>(tg[v], a, b, c, sub[v], flag[v], args.k);
+								}
+							}
+						}
+						bool redo = false;
+#pragma unroll
+						for (int t = 0; t < T; ++t) redo |= !(flag[t / W].lane(t % W) > 0.0f);
+						if (redo) {
+							const long js = (long)(gs / gps) * S + s0;
+							const long je = js + F3D_SUB < (long)args.n_src ? js + F3D_SUB : (long)args.n_src;
+#pragma unroll
+							for (int t = 0; t < T; ++t) {
+								if (!(flag[t / W].lane(t % W) > 0.0f)) {
+									long i = (long)tt * (B * T) + tid + (long)t * B;
+									i = i < args.n_tgt ? i : (long)args.n_tgt - 1;
+									float e[P::NACC];
+									exact_subchain<P>(args.src_raw, js, je, args.tgt + i * P::TCOLS, e);
+#pragma unroll
+									for (int c = 0; c < P::NACC; ++c) sub[t / W][c].set(t % W, e[c]);
+								}
+							}
+						}
 #pragma unroll
 						for (int v = 0; v < NV; ++v)
 #pragma unroll
-							for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+							for (int c = 0; c < P::NACC; ++c) acc[v][c] = vadd(acc[v][c], sub[v][c]);
 					}
-				}
-				if (guarded) {
-#pragma unroll UNROLL
-					for (int j = 0; j < CHAIN; ++j) {
-						const float4 a = sA[j0 + j];
-						float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-						if (P::NSRC4 == 2) b = sB[j0 + j];
+				} else {
+					bool guarded = true;
+					if (P::OPTIMISTIC && optimistic) {
+#pragma unroll 1
+						for (int j = 0; j < G; j += UNROLL) {
 #pragma unroll
-						for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+							for (int u = 0; u < UNROLL; ++u) {
+								const float4 a = sA[j0 + j + u];
+								float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+								if (NR == 2) b = sB[j0 + j + u];
+#pragma unroll
+								for (int v = 0; v < NV; ++v) P::template pair<W, false>(tg[v], a, b, acc[v], args.k);
+							}
+						}
+						// inf and NaN survive any further addition, so one sum over this thread's running sums
+						// tells whether a guard would have fired anywhere in the chain (a sum of finite values
+						// that overflows only costs a needless second evaluation)
+						Vec<W> chk = acc[0][0];
+#pragma unroll
+						for (int v = 0; v < NV; ++v)
+#pragma unroll
+							for (int c = (v == 0 ? 1 : 0); c < P::NACC; ++c) chk = vadd(chk, acc[v][c]);
+						const float s = W == 2 ? chk.lane(0) + chk.lane(1) : chk.lane(0);
+						guarded = !(fabsf(s) <= 3.40282346e38f);
+						if (guarded) {
+#pragma unroll
+							for (int v = 0; v < NV; ++v)
+#pragma unroll
+								for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+						}
+					}
+					if (guarded) {
+#pragma unroll 1
+						for (int j = 0; j < G; j += UNROLL) {
+#pragma unroll
+							for (int u = 0; u < UNROLL; ++u) {
+								const float4 a = sA[j0 + j + u];
+								float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+								if (NR == 2) b = sB[j0 + j + u];
+#pragma unroll
+								for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+							}
+						}
 					}
 				}
 #pragma unroll
@@ -207,69 +320,154 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 					for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
 			}
 		}
-		__syncthreads();      // everyone is done with tile[buf] before it is refilled two iterations on
-	}
+		__syncthreads();      // everyone is done with tile[buf] before it is refilled two steps on
+		gs += n;
+		left -= n;
+		++it;
 
-	// ---- epilogue: FP64 finish, then final floats or FP64 partials
+		if (left == 0 || gs == gpt) {
+			// ---- leaving target tile tt: FP64 finish, then final floats or an FP64 piece
+			const long base = (long)tt * (B * T) + tid;
+			if (from_start && gs == gpt) {
 #pragma unroll
-	for (int t = 0; t < T; ++t) {
-		const long i = base + (long)t * B;
-		if (i < args.n_tgt) {
-			double res[P::NOUT];
-			P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
-			if (gridDim.y == 1) {
+				for (int t = 0; t < T; ++t) {
+					const long i = base + (long)t * B;
+					if (i < args.n_tgt) {
+						double res[P::NOUT];
+						P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
 #pragma unroll
-				for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)res[c];
+						for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)res[c];
+					}
+				}
 			} else {
-				double *dst = args.partial + ((size_t)blockIdx.y * args.n_tgt + i) * P::NOUT;
+				const long long R = gridDim.x;
+				const long long g_begin = run_begin(blockIdx.x, R, args.total_grains);
+				// slot 2b: the tile the block's run starts in; 2b + 1: the tile its run ends in, if that is another one
+				const long long slot = 2 * (long long)blockIdx.x + (g_begin / gpt == tt ? 0 : 1);
+				double *mine = args.pieces + (size_t)slot * (T * B * P::NOUT);
 #pragma unroll
-				for (int c = 0; c < P::NOUT; ++c) dst[c] = res[c];
+				for (int t = 0; t < T; ++t) {
+					const long i = base + (long)t * B;
+					double res[P::NOUT];
+					if (i < args.n_tgt) P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
+					else for (int c = 0; c < P::NOUT; ++c) res[c] = 0.0;
+#pragma unroll
+					for (int c = 0; c < P::NOUT; ++c) __stcg(mine + ((size_t)t * B + tid) * P::NOUT + c, res[c]);
+				}
+				const long long b_first = run_of((long long)tt * gpt, R, args.total_grains);
+				const long long b_last = run_of((long long)(tt + 1) * gpt - 1, R, args.total_grains);
+				__threadfence();
+				__syncthreads();
+				if (tid == 0) s_ticket = atomicAdd(args.tickets + tt, 1);
+				__syncthreads();
+				if (s_ticket == (int)(b_last - b_first)) {              // last to arrive: add the pieces in run order
+					__threadfence();
+#pragma unroll 1
+					for (int t = 0; t < T; ++t) {
+						const long i = base + (long)t * B;
+						double sum[P::NOUT];
+#pragma unroll
+						for (int c = 0; c < P::NOUT; ++c) sum[c] = 0.0;
+						for (long long bb = b_first; bb <= b_last; ++bb) {
+							const long long sl = 2 * bb + (run_begin(bb, R, args.total_grains) / gpt == tt ? 0 : 1);
+							const double *pc = args.pieces + (size_t)sl * (T * B * P::NOUT) + ((size_t)t * B + tid) * P::NOUT;
+#pragma unroll
+							for (int c = 0; c < P::NOUT; ++c) sum[c] += __ldcg(pc + c);
+						}
+						if (i < args.n_tgt) {
+#pragma unroll
+							for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)sum[c];
+						}
+					}
+					if (tid == 0) args.tickets[tt] = 0;                  // leave the ticket counter ready for the next launch
+				}
+				__syncthreads();
 			}
+			if (gs == gpt) { gs = 0; ++tt; }
+			from_start = true;
+			fresh = true;
 		}
 	}
 }
 
-// out[i] = (float) sum_c partial[c][i], chunks added in index order.
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, float *__restrict__ out,
-                                       long n_vals, int n_chunks)
-{
-	const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_vals) return;
-	double s = 0.0;
-	for (int c = 0; c < n_chunks; ++c) s += partial[(size_t)c * n_vals + i];
-	out[i] = (float)s;
-}
-
-// The same sum for few values and many chunks (a few-target call splits its sources thousands of
-// ways): one warp per value, lane l adds chunks l, l + 32, ... in order, then a fixed shuffle tree.
-__global__ void reduce_partials_wide_kernel(const double *__restrict__ partial, float *__restrict__ out,
-                                            long n_vals, int n_chunks)
-{
-	const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	if (i >= n_vals) return;
-	double s = 0.0;
-	for (int c = lane; c < n_chunks; c += 32) s += partial[(size_t)c * n_vals + i];
-	for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-	if (lane == 0) out[i] = (float)s;
-}
-
 // Raw rows -> packed float4 records, padded with zero-strength records (pad_source) to n_pad, a
-// multiple of kSrcTile.
-__global__ void pack_sources_kernel(int kind, int cols, const float *__restrict__ rows, int n, int n_pad,
-                                    float4 *__restrict__ A, float4 *__restrict__ Bq)
+// multiple of kSrcTile.  One block packs one tile.  For filaments each block also leaves the
+// statistics f3d_pick_mode() wants (sum of l^3, longest l, bounding box of the end points) in
+// stats[blockIdx.x]; f3d_mode_kernel combines them in block order.
+struct F3DStats { double sum_len3; float max_len; float lo[3], hi[3]; };
+
+__global__ void __launch_bounds__(kSrcTile) pack_sources_kernel(int kind, int cols, const float *__restrict__ rows, int n, int n_pad,
+                                                                float4 *__restrict__ A, float4 *__restrict__ Bq, float4 *__restrict__ Cq,
+                                                                F3DStats *__restrict__ stats)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_pad) return;
-	float4 a, b;
-	pad_source(kind, a, b);
-	if (i < n) {
+	float4 a, b, c;
+	pad_source(kind, a, b, c);
+	const bool real = i < n;
+	if (real) {
 		float row[7];
-		for (int c = 0; c < cols; ++c) row[c] = rows[(size_t)i * cols + c];
-		pack_source(kind, row, a, b);
+		for (int k = 0; k < cols; ++k) row[k] = rows[(size_t)i * cols + k];
+		pack_source(kind, row, a, b, c);
 	}
-	A[i] = a;
-	if (Bq) Bq[i] = b;
+	if (i < n_pad) {
+		A[i] = a;
+		if (Bq) Bq[i] = b;
+		if (Cq) Cq[i] = c;
+	}
+	if (stats) {
+		__shared__ F3DStats part[kSrcTile / 32];
+		const float len = real ? sqrtf(c.w) : 0.0f;
+		double l3 = (double)len * len * len;
+		float mx = len;
+		float lo[3], hi[3];
+		const float big = 3.0e38f;
+		lo[0] = real ? fminf(a.x, b.x) : big; lo[1] = real ? fminf(a.y, b.y) : big; lo[2] = real ? fminf(a.z, b.z) : big;
+		hi[0] = real ? fmaxf(a.x, b.x) : -big; hi[1] = real ? fmaxf(a.y, b.y) : -big; hi[2] = real ? fmaxf(a.z, b.z) : -big;
+		for (int o = 16; o > 0; o >>= 1) {                      // fixed shuffle tree: the same sum on every run
+			l3 += __shfl_down_sync(0xffffffffu, l3, o);
+			mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+			for (int d = 0; d < 3; ++d) {
+				lo[d] = fminf(lo[d], __shfl_down_sync(0xffffffffu, lo[d], o));
+				hi[d] = fmaxf(hi[d], __shfl_down_sync(0xffffffffu, hi[d], o));
+			}
+		}
+		if ((threadIdx.x & 31) == 0) {
+			F3DStats &w = part[threadIdx.x >> 5];
+			w.sum_len3 = l3; w.max_len = mx;
+			for (int d = 0; d < 3; ++d) { w.lo[d] = lo[d]; w.hi[d] = hi[d]; }
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			F3DStats r = part[0];
+			for (int k = 1; k < kSrcTile / 32; ++k) {
+				r.sum_len3 += part[k].sum_len3; r.max_len = fmaxf(r.max_len, part[k].max_len);
+				for (int d = 0; d < 3; ++d) { r.lo[d] = fminf(r.lo[d], part[k].lo[d]); r.hi[d] = fmaxf(r.hi[d], part[k].hi[d]); }
+			}
+			stats[blockIdx.x] = r;
+		}
+	}
+}
+
+// mode[0] = f3d_pick_mode over all filaments: one block, thread t takes blocks t, t + 256, ... in order,
+// then a fixed tree -- the same sums on every run and every device.  `force` >= 0 pins the mode.
+__device__ __forceinline__ void f3d_stats_merge(F3DStats &r, const F3DStats &o) {
+	r.sum_len3 += o.sum_len3; r.max_len = fmaxf(r.max_len, o.max_len);
+	for (int d = 0; d < 3; ++d) { r.lo[d] = fminf(r.lo[d], o.lo[d]); r.hi[d] = fmaxf(r.hi[d], o.hi[d]); }
+}
+__global__ void __launch_bounds__(256) f3d_mode_kernel(const F3DStats *__restrict__ stats, int n_blocks, int n, int force, int *__restrict__ mode)
+{
+	__shared__ F3DStats sh[256];
+	F3DStats r;
+	r.sum_len3 = 0.0; r.max_len = 0.0f;
+	for (int d = 0; d < 3; ++d) { r.lo[d] = 3.0e38f; r.hi[d] = -3.0e38f; }
+	for (int k = threadIdx.x; k < n_blocks; k += 256) f3d_stats_merge(r, stats[k]);
+	sh[threadIdx.x] = r;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int)threadIdx.x < o) f3d_stats_merge(sh[threadIdx.x], sh[threadIdx.x + o]);
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) mode[0] = force >= 0 ? force : f3d_pick_mode(sh[0].sum_len3, (double)n, sh[0].lo, sh[0].hi, sh[0].max_len);
 }
 
 // ---------------------------------------------------------------------------

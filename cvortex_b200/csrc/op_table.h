@@ -59,14 +59,15 @@ inline int reg_from_name(const char *name) {
 // ---- packed source records (16-byte aligned, one or two float4 per source) --
 // P3D: a = {x, y, z, vol}     b = {wx, wy, wz, 0}
 // P2D: a = {x, y, Gamma, area}                      (a cvtx_P2D verbatim)
-// F3D: a = {ax, ay, az, G/4pi} b = {bx, by, bz, 3 G/(4 pi |r0|)},  r0 = end - start
+// F3D: a = {ax, ay, az, G/4pi} b = {bx, by, bz, 3 G/(4 pi |r0|)} c = {r0, |r0|^2},  r0 = end - start (FP32)
 // Rows beyond n (padding up to a whole tile) carry zero strength, which makes
 // every pair formula contribute exactly 0: particles are all-zero records; the
 // padding filament is the unit segment (0,0,0)-(1,0,0) with zero strength, NOT a
 // zero-length one, so that its terms are finite zeros for every target off the
 // x axis and the optimistic pair loop (pair_math.cuh, GUARDS) does not have to
 // re-evaluate the last chain of every call.
-CVTX_HD void pack_source(int kind, const float *row, f4 &a, f4 &b) {
+CVTX_HD void pack_source(int kind, const float *row, f4 &a, f4 &b, f4 &c) {
+	c.x = c.y = c.z = c.w = 0.0f;
 	if (kind == SRC_P3D) {
 		a.x = row[0]; a.y = row[1]; a.z = row[2]; a.w = row[6];
 		b.x = row[3]; b.y = row[4]; b.z = row[5]; b.w = 0.0f;
@@ -79,14 +80,17 @@ CVTX_HD void pack_source(int kind, const float *row, f4 &a, f4 &b) {
 		a.x = row[0]; a.y = row[1]; a.z = row[2]; a.w = t1;
 		b.x = row[3]; b.y = row[4]; b.z = row[5];
 		b.w = (3.0f / sqrtf(rx * rx + ry * ry + rz * rz)) * t1;      // (3/|r0|) t1, reference src/F3D.cpp:70
+		c.x = rx; c.y = ry; c.z = rz; c.w = rx * rx + ry * ry + rz * rz;
 	}
 }
 
-CVTX_HD void pad_source(int kind, f4 &a, f4 &b) {
+CVTX_HD void pad_source(int kind, f4 &a, f4 &b, f4 &c) {
 	a.x = a.y = a.z = a.w = 0.0f;
 	b.x = b.y = b.z = b.w = 0.0f;
-	if (kind == SRC_F3D) b.x = 1.0f;
+	c.x = c.y = c.z = c.w = 0.0f;
+	if (kind == SRC_F3D) { b.x = 1.0f; c.x = 1.0f; c.w = 1.0f; }
 }
+inline int src_records(int op) { return src_kind(op) == SRC_P2D ? 1 : (src_kind(op) == SRC_F3D ? 3 : 2); }   // float4 records per packed source
 
 // Call f.template run<Policy>() for the policy of (op, reg).  Returns false
 // for an unsupported combination.

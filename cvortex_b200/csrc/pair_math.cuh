@@ -77,6 +77,7 @@
 //                       formulation (FMA = 1 lane-op; compares/selects not
 //                       counted) -- the roofline denominators, see DESIGN.md
 //   OPTIMISTIC  pair<W, false>() exists and differs from pair<W, true>() (see GUARDS)
+//   HYBRID      filament policies: fast<W, MODE>() + exact() instead of pair<>() (see FILAMENTS)
 //   load_target(row, tg[]), pair<W, G>(tg, a, b, acc, k), finish(row, acc, out, k)
 // and is usable from host code too (tests/hostcheck compiles this header with
 // g++ to validate the algebra against the oracle without a GPU; MUFU ops are
@@ -372,6 +373,7 @@ template <int REG> struct P3DVel {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 15 + Reg3D<REG>::A_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // K = inf / NaN meets finite factors: every sum is poisoned
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
@@ -407,6 +409,7 @@ template <int REG> struct P3DDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = REG == REG_SINGULAR ? 4 : 8;
 	static constexpr int LANE_OPS = 22 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // A = inf / NaN enters all three sums through fma(A, c, .)
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
@@ -449,6 +452,7 @@ template <int REG> struct P3DVelDvort {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 6, NOUT = 6, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 31 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
@@ -512,6 +516,7 @@ template <int REG> struct P3DVisc {
 	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 15 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = false;      // eta(0) is finite: the coincident-pair test is a real selection
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
 	}
@@ -576,6 +581,7 @@ template <int REG> struct P3DVort {
 	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 9 + Zeta3D<REG>::OPS, SFU_OPS = Zeta3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = false;      // the box cutoff selects between finite values
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
@@ -650,6 +656,7 @@ template <int REG> struct P2DVel {
 	static constexpr int NSRC4 = 1, TCOLS = 2, NTGT = 2, NACC = 2, NOUT = 2, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 7 + Reg2D<REG>::OPS, SFU_OPS = Reg2D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg2D<REG>::POISONS;
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
@@ -695,6 +702,7 @@ template <int REG> struct P2DVisc {
 	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 2 : 8;
 	static constexpr int LANE_OPS = 7 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = false;      // eta(0) is finite
+	static constexpr bool HYBRID = false;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
@@ -741,89 +749,270 @@ template <int W> CVTX_HD void cross_rounded(Vec<W> ux, Vec<W> uy, Vec<W> uz, Vec
 	cz = vfma(vmul(ux, vy), one, vneg(vmul(uy, vx)));
 }
 
-template <int W> struct Fil { Vec<W> px, py, pz, qx, qy, qz, ox, oy, oz, n1, n2, d1, d2; };
-template <int W> CVTX_HD Fil<W> filament_geometry(const Vec<W> *tg, const f4 a, const f4 b) {   // 21 lane-ops
-	Fil<W> f;
-	f.px = vsub(tg[0], a.x); f.py = vsub(tg[1], a.y); f.pz = vsub(tg[2], a.z);        // r1
-	f.qx = vsub(tg[0], b.x); f.qy = vsub(tg[1], b.y); f.qz = vsub(tg[2], b.z);        // r2
-	f.ox = vsub(f.px, f.qx); f.oy = vsub(f.py, f.qy); f.oz = vsub(f.pz, f.qz);        // r0 = r1 - r2 (exact)
-	f.n1 = vfma(f.pz, f.pz, vfma(f.py, f.py, vmul(f.px, f.px)));
-	f.n2 = vfma(f.qz, f.qz, vfma(f.qy, f.qy, vmul(f.qx, f.qx)));
-	f.d1 = vfma(f.pz, f.oz, vfma(f.py, f.oy, vmul(f.px, f.ox)));
-	f.d2 = vfma(f.qz, f.oz, vfma(f.qy, f.oy, vmul(f.qx, f.ox)));
-	return f;
+// ---------------------------------------------------------------------------
+// FILAMENTS, second version: three tiers per (target, 32-source sub-chain).
+//
+// Where the FP32 error of the reference's filament formulas comes from, for a segment of
+// length l seen from distance r at angle theta: (i) c = r1 x r2 is a cross product of nearly
+// parallel vectors, relative error ~ 1e-7 r/(l sin theta), and c/|c|^2 carries it three times;
+// (ii) t2 = r1.r0/|r1| - r2.r0/|r2| cancels to ~ l^2 sin^2(theta)/r, relative error
+// ~ 1e-7 r/(l sin^2 theta).  Both grow as the segments get short -- the FP32 reference itself
+// sits 1e-6 ... 1e-5 from FP64 on short segments -- and (ii) makes it noise next to the axis.
+// With |c|^2 = (|r1||r2| - r1.r2)(|r1||r2| + r1.r2) and
+// t2 = (|r1| + |r2|)(|r1||r2| - r1.r2)/(|r1||r2|) the singular factor cancels exactly:
+//     Kf := t2/|c|^2 = (1/|r1| + 1/|r2|) / (|r1||r2| + r1.r2)
+// a sum of positive terms wherever r1.r2 > 0, i.e. outside the sphere whose diameter is the
+// segment; and c = r1 x r2 = r0 x r1 with the per-SOURCE r0 = b - a (rounded once) is a cross
+// product of non-parallel vectors.  Likewise 1/|r1| - 1/|r2| = -(|r1|^2 - |r2|^2) / ((|r1| + |r2|)|r1||r2|)
+// with |r1|^2 - |r2|^2 = r0.(r1 + r2) = 2 r0.r1 - l^2.  That is the FAST form (`fast<W, F3D_NEW>`): ~2e-7
+// from FP64 at any segment length, 34 / 41 lane-ops instead of 40 / 45.
+// It is not usable (a) inside that sphere, where |r1||r2| + r1.r2 cancels and the reference's form
+// is the accurate one, and (b) within ~1e-3 rad of the filament's axis, where the reference's result
+// is decided by how ITS operations round (exact zeros for collinear points, or garbage / |c|) and a
+// drop-in replacement has to return what the reference returns.  Each fast pair therefore also
+// feeds a per-TARGET running minimum `flag` of  min(r1.r2, |c|^2 - tau l^2 |r1|^2)  (NaN-propagating);
+// after every sub-chain of F3D_SUB = 32 sources the kernel looks at it and, for the targets whose
+// flag is not positive, throws the sub-chain's sums away and evaluates those 32 pairs again with
+// `exact()`: the reference's own operations in the reference's order with IEEE division and square
+// root -- op for op what src/F3D.cpp:34-85 does, so points on a vortex line get the reference's bits.
+// The decision is per target and per fixed sub-chain of the source order, never per thread: a result
+// does not depend on which other targets share a thread, on the launch geometry or on the shard.
+// A call whose filaments are long against the region they live in would take the slow tier all the
+// time; for those the fast form is the reference's formula with MUFU (`fast<W, F3D_REF>`, the first
+// version of this kernel) with only the axis test in the flag.  Which of the two is a property of
+// the SOURCES alone (f3d_pick_mode, decided on the device while packing), so every shard of a
+// multi-GPU call makes the same choice.
+// ---------------------------------------------------------------------------
+enum F3DMode { F3D_NEW = 0, F3D_REF = 1 };
+constexpr int F3D_SUB = 32;
+
+// running per-lane minimum that keeps a NaN once it has seen one (one FMNMX3.NAN on sm_100)
+CVTX_HD float min3_nan(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+	float y; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y;
+#else
+	if (a != a || b != b || c != c) return NAN;
+	return fminf(fminf(a, b), c);
+#endif
+}
+CVTX_HD float min2_nan(float a, float b) {
+#if defined(__CUDA_ARCH__)
+	float y; asm("min.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y;
+#else
+	if (a != a || b != b) return NAN;
+	return fminf(a, b);
+#endif
 }
 
+// single rounded FP32 operations, immune to FMA contraction (the host build uses -ffp-contract=off)
+#if defined(__CUDA_ARCH__)
+CVTX_HD float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+CVTX_HD float rn_add(float a, float b) { return __fadd_rn(a, b); }
+CVTX_HD float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+CVTX_HD float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+CVTX_HD float rn_sqrt(float a) { return __fsqrt_rn(a); }
+#else
+CVTX_HD float rn_mul(float a, float b) { return a * b; }
+CVTX_HD float rn_add(float a, float b) { return a + b; }
+CVTX_HD float rn_sub(float a, float b) { return a - b; }
+CVTX_HD float rn_div(float a, float b) { return a / b; }
+CVTX_HD float rn_sqrt(float a) { return sqrtf(a); }
+#endif
+struct V3r { float x, y, z; };
+CVTX_HD V3r r_sub(V3r a, V3r b) { V3r r = {rn_sub(a.x, b.x), rn_sub(a.y, b.y), rn_sub(a.z, b.z)}; return r; }
+CVTX_HD float r_dot(V3r a, V3r b) { return rn_add(rn_add(rn_mul(a.x, b.x), rn_mul(a.y, b.y)), rn_mul(a.z, b.z)); }
+CVTX_HD float r_abs(V3r a) { return rn_sqrt(r_dot(a, a)); }
+CVTX_HD V3r r_cross(V3r a, V3r b) {
+	V3r r = {rn_sub(rn_mul(a.y, b.z), rn_mul(a.z, b.y)), rn_sub(rn_mul(a.z, b.x), rn_mul(a.x, b.z)),
+	         rn_sub(rn_mul(a.x, b.y), rn_mul(a.y, b.x))};
+	return r;
+}
+
+// Per-call choice of the fast form from the filaments alone: the expected share of (filament, point)
+// pairs with the point inside the filament's sphere, for points spread over the filaments' own
+// bounding box (every extent at least the longest filament).  A warp that meets one such pair
+// re-evaluates a 32-source sub-chain in scalar code, ~3x the cost of the sub-chain itself, for
+// 32 lanes x 8 targets x 32 sources = 8192 pairs: at p = 4e-6 that is +10 %.
+CVTX_HD int f3d_pick_mode(double sum_len3, double n, const float *lo, const float *hi, float max_len) {
+	if (!(n > 0.0)) return F3D_REF;
+	double vol = 1.0;
+	for (int i = 0; i < 3; ++i) {
+		const double e = (double)hi[i] - (double)lo[i];
+		vol *= e > (double)max_len ? e : (double)max_len;
+	}
+	if (!(vol > 0.0)) return F3D_REF;
+	const double p = 0.5235987755982988 * sum_len3 / (n * vol);      // (pi/6) <l^3> / V
+	return p < 4e-6 ? F3D_NEW : F3D_REF;
+}
+
+// ===========================================================================
+// cvtx_F3D_M2M_vel      straight singular filament a->b on a point x:
+//   r1 = x-a, r2 = x-b, r0 = r1-r2, c = r1 x r2,
+//   u = c [G/(4 pi |c|^2)] [r1.r0/|r1| - r2.r0/|r2|],  dropped unless both
+//   bracketed factors are finite.
+// reference: src/F3D.cpp:34-54 (pair), :87-107 (sum), :162-180 (entry)
+// source  a = {ax, ay, az, G/4pi}   b = {bx, by, bz, 3 G/(4 pi |b-a|)}   c = {b - a, |b-a|^2}
+// ===========================================================================
 struct F3DVel {
-	static constexpr int NSRC4 = 2, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
-	static constexpr int LANE_OPS = 40, SFU_OPS = 3;
-	// the rule fires when t1 or t2 is inf / NaN; their product is then inf or NaN (inf * 0 = NaN), and so
-	// is every fma(kk, c, acc)
-	static constexpr bool OPTIMISTIC = true;
+	static constexpr int NSRC4 = 3, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
+	static constexpr int LANE_OPS = 34, SFU_OPS = 3;           // of fast<W, F3D_NEW>; the F3D_REF form: 44 / 3
+	static constexpr bool OPTIMISTIC = false, HYBRID = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
-		const Fil<W> f = filament_geometry(tg, a, b);
-		Vec<W> cx, cy, cz;
-		cross_rounded(f.px, f.py, f.pz, f.qx, f.qy, f.qz, k.c0, cx, cy, cz);      // c = r1 x r2
-		const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
-		const Vec<W> t1 = vmul(vrcp(c2), a.w);
-		const Vec<W> t2 = vfms(f.d1, vrsqrt(f.n1), vmul(f.d2, vrsqrt(f.n2)));
-		const Vec<W> kk0 = vmul(t1, t2);
-		Vec<W> kk = kk0;
-		if (G) for (int i = 0; i < W; ++i) {
-			const bool ok = (fabsf(t1.lane(i)) <= 3.40282346e38f) && (fabsf(t2.lane(i)) <= 3.40282346e38f);
-			kk.set(i, ok ? kk0.lane(i) : 0.0f);
+
+	template <int W, int MODE> CVTX_HD static void fast(const Vec<W> *tg, const f4 a, const f4 b, const f4 c, Vec<W> *acc,
+	                                                   Vec<W> &flag, const PairConsts &k) {
+		const Vec<W> px = vsub(tg[0], a.x), py = vsub(tg[1], a.y), pz = vsub(tg[2], a.z);          // r1
+		const Vec<W> n1 = vfma(pz, pz, vfma(py, py, vmul(px, px)));
+		const float tl = c.w * k.c1;                                                                // tau l^2
+		if (MODE == F3D_NEW) {
+			const Vec<W> qx = vsub(px, c.x), qy = vsub(py, c.y), qz = vsub(pz, c.z);               // r2 = r1 - r0
+			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
+			const Vec<W> d12 = vfma(pz, qz, vfma(py, qy, vmul(px, qx)));                          // r1 . r2
+			const Vec<W> cx = vfms(pz, c.y, vmul(py, c.z));                                       // r0 x r1 = r1 x r2
+			const Vec<W> cy = vfms(px, c.z, vmul(pz, c.x));
+			const Vec<W> cz = vfms(py, c.x, vmul(px, c.y));
+			const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
+			const Vec<W> rs1 = vrsqrt(n1), rs2 = vrsqrt(n2);
+			const Vec<W> md = vfma(vmul(n1, rs1), vmul(n2, rs2), d12);                            // |r1||r2| + r1.r2
+			const Vec<W> kk = vmul(vmul(vadd(rs1, rs2), a.w), vrcp(md));                          // G/4pi Kf
+			acc[0] = vfma(kk, cx, acc[0]);
+			acc[1] = vfma(kk, cy, acc[1]);
+			acc[2] = vfma(kk, cz, acc[2]);
+			const Vec<W> margin = vfma(n1, -tl, c2);                                              // > 0: off the axis
+			for (int i = 0; i < W; ++i) flag.set(i, min3_nan(flag.lane(i), d12.lane(i), margin.lane(i)));
+		} else {
+			const Vec<W> qx = vsub(tg[0], b.x), qy = vsub(tg[1], b.y), qz = vsub(tg[2], b.z);     // r2
+			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);                 // r0 = r1 - r2 (exact)
+			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
+			const Vec<W> d1 = vfma(pz, oz, vfma(py, oy, vmul(px, ox)));
+			const Vec<W> d2 = vfma(qz, oz, vfma(qy, oy, vmul(qx, ox)));
+			Vec<W> cx, cy, cz;
+			cross_rounded(px, py, pz, qx, qy, qz, k.c0, cx, cy, cz);                              // c = r1 x r2
+			const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
+			const Vec<W> t1 = vmul(vrcp(c2), a.w);
+			const Vec<W> t2 = vfms(d1, vrsqrt(n1), vmul(d2, vrsqrt(n2)));
+			const Vec<W> kk = vmul(t1, t2);
+			acc[0] = vfma(kk, cx, acc[0]);
+			acc[1] = vfma(kk, cy, acc[1]);
+			acc[2] = vfma(kk, cz, acc[2]);
+			// a target ON an end point has c = 0 and n1 = 0 (or r2 = 0): margin = 0 or -tl n1, never positive
+			const Vec<W> margin = vfma(n1, -tl, c2);
+			for (int i = 0; i < W; ++i) flag.set(i, min2_nan(flag.lane(i), margin.lane(i)));
 		}
-		acc[0] = vfma(kk, cx, acc[0]);
-		acc[1] = vfma(kk, cy, acc[1]);
-		acc[2] = vfma(kk, cz, acc[2]);
+	}
+
+	// One pair in the reference's own arithmetic (src/F3D.cpp:34-54): raw filament row, raw target row.
+	CVTX_HD static void exact(const float *fil, const float *tgt, float *acc) {
+		const V3r x = {tgt[0], tgt[1], tgt[2]}, a = {fil[0], fil[1], fil[2]}, b = {fil[3], fil[4], fil[5]};
+		const V3r r1 = r_sub(x, a), r2 = r_sub(x, b), r0 = r_sub(r1, r2), c = r_cross(r1, r2);
+		const float nc = r_abs(c);
+		const float t1 = rn_div(fil[6], rn_mul(4.0f * 3.14159265359f, rn_mul(nc, nc)));      // powf(|c|, 2)
+		const float t21 = rn_div(r_dot(r1, r0), r_abs(r1)), t22 = rn_div(r_dot(r2, r0), r_abs(r2));
+		const float t2 = rn_sub(t21, t22);
+		if (fabsf(t1) <= 3.40282346e38f && fabsf(t2) <= 3.40282346e38f) {
+			const float s = rn_mul(t1, t2);
+			acc[0] = rn_add(acc[0], rn_mul(c.x, s));
+			acc[1] = rn_add(acc[1], rn_mul(c.y, s));
+			acc[2] = rn_add(acc[2], rn_mul(c.z, s));
+		}
 	}
 	CVTX_HD static void finish(const float *, const double *acc, double *out, const PairConsts &) {
 		out[0] = acc[0]; out[1] = acc[1]; out[2] = acc[2];
 	}
-	static PairConsts make_consts(float, float) { PairConsts k = {}; k.c0 = 1.0f; k.s0 = 1.0; return k; }   // c0: cross_rounded's `one`
+	// c0: cross_rounded's `one`; c1: tau, the axis test |c|^2 < tau l^2 |r1|^2 (sin(theta) < 3e-5)
+	static PairConsts make_consts(float, float) { PairConsts k = {}; k.c0 = 1.0f; k.c1 = 1e-9f; k.s0 = 1.0; return k; }
 };
 
 // ===========================================================================
 // cvtx_F3D_M2M_dvort    filament on particle (x_t, w_t):
 //   dw = B w_t + A x w_t,  A = -r0 t1 t212/|r1 x r0|^2,  B = (3/|r0|) t1 t222
 //   t212 = r0.r1/|r1| - r0.r2/|r2|,  t222 = |r0 x r1| (1/|r1| - 1/|r2|)
-//   dropped when A, B (hence t212, t222) are NaN.
+//   dropped when the result, t212 or t222 is NaN.
 // reference: src/F3D.cpp:56-85 (pair), :109-128 (sum), :182-202 (entry)
 // running sums: sum A (3), sum B (1); w_t applied once in finish().
+// fast form: A = -r0 t1 Kf (Kf as above),  B = -(3 t1/l) |X| (2 r0.r1 - l^2) / ((|r1| + |r2|)|r1||r2|),
+//            |X|^2 = l^2 |r1|^2 - (r0.r1)^2
 // ===========================================================================
 struct F3DDvort {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
-	static constexpr int LANE_OPS = 45, SFU_OPS = 3;
-	// the rule fires when A's scalar or B is NaN; a NaN scalar reaches the A sums through fma(sa, r0, acc),
-	// a NaN B reaches the B sum through its fma
-	static constexpr bool OPTIMISTIC = true;
+	static constexpr int NSRC4 = 3, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
+	static constexpr int LANE_OPS = 41, SFU_OPS = 4;           // of fast<W, F3D_NEW>; the F3D_REF form: 46 / 3
+	static constexpr bool OPTIMISTIC = false, HYBRID = true;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
-	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
-		const Fil<W> f = filament_geometry(tg, a, b);
-		Vec<W> xx, xy, xz;
-		cross_rounded(f.px, f.py, f.pz, f.ox, f.oy, f.oz, k.c0, xx, xy, xz);      // X = r1 x r0
-		const Vec<W> x2 = vfma(xz, xz, vfma(xy, xy, vmul(xx, xx)));
-		const Vec<W> rs1 = vrsqrt(f.n1), rs2 = vrsqrt(f.n2), rsx = vrsqrt(x2);
-		const Vec<W> t212 = vfms(f.d1, rs1, vmul(f.d2, rs2));
-		const Vec<W> sA = vmul(vneg(vmul(t212, a.w)), vmul(rsx, rsx));
-		const Vec<W> t222 = vmul(vmul(x2, rsx), vsub(rs1, rs2));
-		// B = t222 * b.w enters its sum through ONE fused multiply-add in both forms (a separate
-		// product and sum would be contracted by nvcc in the plain form only, and the two forms
-		// must round identically); the guarded form forms B once more just to test it
-		Vec<W> sa = sA, nb = vfma(t222, b.w, acc[3]);
-		if (G) {
-			const Vec<W> Bv = vmul(t222, b.w);
-			for (int i = 0; i < W; ++i) {
-				const bool ok = (sA.lane(i) == sA.lane(i)) && (Bv.lane(i) == Bv.lane(i));
-				sa.set(i, ok ? sA.lane(i) : 0.0f);
-				nb.set(i, ok ? nb.lane(i) : acc[3].lane(i));
-			}
+
+	template <int W, int MODE> CVTX_HD static void fast(const Vec<W> *tg, const f4 a, const f4 b, const f4 c, Vec<W> *acc,
+	                                                   Vec<W> &flag, const PairConsts &k) {
+		const Vec<W> px = vsub(tg[0], a.x), py = vsub(tg[1], a.y), pz = vsub(tg[2], a.z);          // r1
+		const Vec<W> n1 = vfma(pz, pz, vfma(py, py, vmul(px, px)));
+		if (MODE == F3D_NEW) {
+			const Vec<W> qx = vsub(px, c.x), qy = vsub(py, c.y), qz = vsub(pz, c.z);               // r2 = r1 - r0
+			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
+			const Vec<W> d12 = vfma(pz, qz, vfma(py, qy, vmul(px, qx)));                          // r1 . r2
+			const Vec<W> d1 = vfma(pz, c.z, vfma(py, c.y, vmul(px, c.x)));                        // r0 . r1
+			const Vec<W> ln = vmul(n1, c.w);                                                      // l^2 |r1|^2
+			const Vec<W> x2 = vfma(vneg(d1), d1, ln);                                             // |r0 x r1|^2
+			const Vec<W> rs1 = vrsqrt(n1), rs2 = vrsqrt(n2), rsx = vrsqrt(x2);
+			const Vec<W> q1 = vmul(n1, rs1), q2 = vmul(n2, rs2);
+			const Vec<W> md = vfma(q1, q2, d12), qs = vadd(q1, q2);
+			const Vec<W> R = vrcp(vmul(md, qs)), P = vmul(rs1, rs2);
+			const Vec<W> iq = vmul(R, md);                                                        // 1/(|r1| + |r2|)
+			const Vec<W> sa = vmul(vmul(qs, P), vmul(vmul(qs, R), -a.w));                         // -t1 Kf
+			acc[0] = vfma(sa, c.x, acc[0]);
+			acc[1] = vfma(sa, c.y, acc[1]);
+			acc[2] = vfma(sa, c.z, acc[2]);
+			const Vec<W> s12 = vfma(d1, 2.0f, -c.w);                                              // r0 . (r1 + r2)
+			const Vec<W> bv = vmul(vmul(vmul(x2, rsx), P), vmul(s12, iq));
+			acc[3] = vfma(bv, -b.w, acc[3]);
+			const Vec<W> margin = vfma(ln, -k.c1, x2);
+			for (int i = 0; i < W; ++i) flag.set(i, min3_nan(flag.lane(i), d12.lane(i), margin.lane(i)));
+		} else {
+			const Vec<W> qx = vsub(tg[0], b.x), qy = vsub(tg[1], b.y), qz = vsub(tg[2], b.z);     // r2
+			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);                 // r0 = r1 - r2 (exact)
+			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
+			const Vec<W> d1 = vfma(pz, oz, vfma(py, oy, vmul(px, ox)));
+			const Vec<W> d2 = vfma(qz, oz, vfma(qy, oy, vmul(qx, ox)));
+			Vec<W> xx, xy, xz;
+			cross_rounded(px, py, pz, ox, oy, oz, k.c0, xx, xy, xz);                              // X = r1 x r0
+			const Vec<W> x2 = vfma(xz, xz, vfma(xy, xy, vmul(xx, xx)));
+			const Vec<W> rs1 = vrsqrt(n1), rs2 = vrsqrt(n2), rsx = vrsqrt(x2);
+			const Vec<W> t212 = vfms(d1, rs1, vmul(d2, rs2));
+			const Vec<W> sa = vmul(vneg(vmul(t212, a.w)), vmul(rsx, rsx));
+			const Vec<W> t222 = vmul(vmul(x2, rsx), vsub(rs1, rs2));
+			acc[0] = vfma(sa, ox, acc[0]);
+			acc[1] = vfma(sa, oy, acc[1]);
+			acc[2] = vfma(sa, oz, acc[2]);
+			acc[3] = vfma(t222, b.w, acc[3]);
+			const Vec<W> margin = vfma(vmul(n1, c.w), -k.c1, x2);
+			for (int i = 0; i < W; ++i) flag.set(i, min2_nan(flag.lane(i), margin.lane(i)));
 		}
-		acc[0] = vfma(sa, f.ox, acc[0]);
-		acc[1] = vfma(sa, f.oy, acc[1]);
-		acc[2] = vfma(sa, f.oz, acc[2]);
-		acc[3] = nb;
+	}
+
+	// One pair in the reference's own arithmetic (src/F3D.cpp:56-85): the pair is dropped on the
+	// reference's test (result, t222 or t212 NaN), otherwise its A and B join the running sums.
+	CVTX_HD static void exact(const float *fil, const float *tgt, float *acc) {
+		const V3r x = {tgt[0], tgt[1], tgt[2]}, w = {tgt[3], tgt[4], tgt[5]};
+		const V3r a = {fil[0], fil[1], fil[2]}, b = {fil[3], fil[4], fil[5]};
+		const V3r r1 = r_sub(x, a), r2 = r_sub(x, b), r0 = r_sub(r1, r2);
+		const float t1 = rn_div(fil[6], 4.0f * 3.14159265359f);
+		const float nx = r_abs(r_cross(r1, r0));
+		const float den = -rn_mul(nx, nx);                                                       // -powf(|r1 x r0|, 2)
+		const V3r t211 = {rn_div(r0.x, den), rn_div(r0.y, den), rn_div(r0.z, den)};
+		const float n1 = r_abs(r1), n2 = r_abs(r2);
+		const float t2121 = rn_div(r_dot(r0, r1), n1), t2122 = rn_div(-r_dot(r0, r2), n2);
+		const float t221 = rn_div(3.0f, r_abs(r0));
+		const float ny = r_abs(r_cross(r0, r1));
+		const float t2221 = rn_div(ny, n1), t2222 = rn_div(-ny, n2);
+		const float t222 = rn_add(t2221, t2222), t212 = rn_add(t2121, t2122);
+		const float sc = rn_mul(t1, t212);
+		const V3r A = {rn_mul(t211.x, sc), rn_mul(t211.y, sc), rn_mul(t211.z, sc)};
+		const float B = rn_mul(rn_mul(t221, t1), t222);
+		const V3r cr = r_cross(A, w);
+		const float rx = rn_add(rn_mul(w.x, B), cr.x), ry = rn_add(rn_mul(w.y, B), cr.y), rz = rn_add(rn_mul(w.z, B), cr.z);
+		if (rx == rx && ry == ry && rz == rz && t222 == t222 && t212 == t212) {
+			acc[0] = rn_add(acc[0], A.x);
+			acc[1] = rn_add(acc[1], A.y);
+			acc[2] = rn_add(acc[2], A.z);
+			acc[3] = rn_add(acc[3], B);
+		}
 	}
 	CVTX_HD static void finish(const float *row, const double *acc, double *out, const PairConsts &) {
 		const double wx = row[3], wy = row[4], wz = row[5];
@@ -831,7 +1020,9 @@ struct F3DDvort {
 		out[1] = acc[3] * wy + (acc[2] * wx - acc[0] * wz);
 		out[2] = acc[3] * wz + (acc[0] * wy - acc[1] * wx);
 	}
-	static PairConsts make_consts(float, float) { PairConsts k = {}; k.c0 = 1.0f; k.s0 = 1.0; return k; }   // c0: cross_rounded's `one`
+	// c0: cross_rounded's `one`; c1: tau of the axis test |X|^2 < tau l^2 |r1|^2 (sin(theta) < 1e-3: the
+	// fast form's |X|^2 = l^2 |r1|^2 - (r0.r1)^2 resolves sin^2(theta) to ~3e-7)
+	static PairConsts make_consts(float, float) { PairConsts k = {}; k.c0 = 1.0f; k.c1 = 1e-6f; k.s0 = 1.0; return k; }
 };
 
 }  // namespace cvtx

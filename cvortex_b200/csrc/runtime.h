@@ -27,7 +27,7 @@ struct Device {
 	bool ready = false;
 	cudaDeviceProp prop;
 	// arena of cvtx_b200_m2m
-	Buffer packedA, packedB, partial;
+	Buffer packedA, packedB, packedC, pieces, tickets, aux;
 	cudaEvent_t arena_idle = nullptr, k_start = nullptr, k_stop = nullptr;
 	bool timed = false;
 	// raw rows of the staged (host-array) path

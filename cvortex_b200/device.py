@@ -62,9 +62,11 @@ class DeviceBackend:
         lib.cvtx_b200_op_info.restype, lib.cvtx_b200_op_info.argtypes = i, [i, i, ip, ip, ip, ip, ip]
         lib.cvtx_b200_plan.restype, lib.cvtx_b200_plan.argtypes = i, [i, i, i, i, ip, ip, ip, ip]
         lib.cvtx_b200_kernel_launches.restype = C.c_ulonglong
+        lib.cvtx_b200_measure_peak.restype, lib.cvtx_b200_measure_peak.argtypes = i, [i, i, C.POINTER(C.c_double)]
         lib.cvtx_b200_last_pair_kernel_ms.restype, lib.cvtx_b200_last_pair_kernel_ms.argtypes = f, [i]
         lib.cvtx_b200_tune.restype, lib.cvtx_b200_tune.argtypes = None, [i, i]
         lib.cvtx_b200_guarded_only.restype, lib.cvtx_b200_guarded_only.argtypes = None, [i]
+        lib.cvtx_b200_f3d_mode.restype, lib.cvtx_b200_f3d_mode.argtypes = None, [i]
         lib.cvtx_b200_last_dispatch.restype = i
         lib.cvtx_b200_last_devices_used.restype = i
         lib.cvtx_b200_last_error.restype = C.c_char_p
@@ -106,6 +108,14 @@ class DeviceBackend:
             raise BackendError(self.last_error())
         return dict(zip(("block", "tgt_per_thread", "grid_x", "grid_y"), (x.value for x in v)))
 
+    def measure_peak(self, device: int, what: str) -> float:
+        """Measured pipe peak of `device`: "fp32" -> FP32 lane-ops/s (FFMA2 loop), "mufu" -> MUFU ops/s."""
+        v = C.c_double()
+        rc = self.lib.cvtx_b200_measure_peak(device, {"fp32": 0, "mufu": 1}[what], C.byref(v))
+        if rc:
+            raise BackendError(f"cvtx_b200_measure_peak failed ({rc}): {self.last_error()}")
+        return float(v.value)
+
     def kernel_launches(self) -> int:
         return int(self.lib.cvtx_b200_kernel_launches())
 
@@ -119,6 +129,11 @@ class DeviceBackend:
         """Tests / experiments (cvtx_b200_guarded_only): 1 = every chain in the guarded pair form,
         2 = the optimistic form at any size, 0 = the default (optimistic from 16 source tiles up)."""
         self.lib.cvtx_b200_guarded_only(int(mode))
+
+    def f3d_mode(self, mode: int) -> None:
+        """Tests / experiments (cvtx_b200_f3d_mode): 0 = cancellation-free filament form, 1 = the
+        reference's formula, -1 = chosen per call from the filaments (the default)."""
+        self.lib.cvtx_b200_f3d_mode(int(mode))
 
     def last_dispatch(self) -> int:
         return int(self.lib.cvtx_b200_last_dispatch())

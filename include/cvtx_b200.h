@@ -140,8 +140,14 @@ CVTX_B200_API int cvtx_b200_pedrizzetti_relaxation(int reg, int device, void *st
  * formulation. */
 CVTX_B200_API int cvtx_b200_op_info(int op, int reg, int *src_cols, int *tgt_cols, int *out_cols,
                       int *lane_ops_per_pair, int *sfu_ops_per_pair);
-/* Geometry the planner would use: threads per block, targets per thread,
- * grid.x (target tiles), grid.y (source chunks). */
+/* Run-time pipe peaks of `device`, the measured counterparts of the nominal roofline
+ * denominators (SMs x 128 lanes x clock, SMs x 16 x clock): what = 0 -> FP32 lane-ops/s sustained
+ * by a packed-FMA (FFMA2) loop, what = 1 -> MUFU ops/s sustained by an rsqrt loop.  Synchronous,
+ * a few milliseconds. */
+CVTX_B200_API int cvtx_b200_measure_peak(int device, int what, double *ops_per_second);
+/* Geometry the planner would use: threads per block, targets per thread, the number of
+ * persistent blocks (grid_x) and the sources per grain = FP32 chain (grid_y: 256, or 32 for
+ * small source sets). */
 CVTX_B200_API int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tgt_per_thread,
                    int *grid_x, int *grid_y);
 /* Kernels launched by this library since load (pack + pair + reduce). */
@@ -150,8 +156,8 @@ CVTX_B200_API unsigned long long cvtx_b200_kernel_launches(void);
  * around the pair-kernel launch of the most recent cvtx_b200_m2m() call on
  * `device`.  Blocks until that kernel finishes.  <0 if nothing was recorded. */
 CVTX_B200_API float cvtx_b200_last_pair_kernel_ms(int device);
-/* Experiments only: force targets-per-thread (1, 2, 4; 0 = planner) and the
- * number of source chunks (0 = planner). */
+/* Experiments and tests only: force targets-per-thread (1, 2, 4, 8; 0 = planner) and the
+ * number of persistent blocks the work is cut into (0 = planner). */
 CVTX_B200_API void cvtx_b200_tune(int force_tgt_per_thread, int force_chunks);
 /* Experiments and tests only.  Ops whose coincident-pair / non-finite tests can
  * only ever replace an inf or a NaN run the pair loop without them and evaluate
@@ -162,6 +168,11 @@ CVTX_B200_API void cvtx_b200_tune(int force_tgt_per_thread, int force_chunks);
  * restores the default; CVTX_B200_GUARDED=0|1|2 in the environment sets the
  * initial mode. */
 CVTX_B200_API void cvtx_b200_guarded_only(int mode);
+/* Experiments and tests only.  The filament ops pick their fast pair form per call from the
+ * filaments themselves: 0 pins the cancellation-free form, 1 the
+ * reference's formula, anything else restores the automatic choice.  CVTX_B200_F3D_MODE=0|1
+ * in the environment sets the initial value. */
+CVTX_B200_API void cvtx_b200_f3d_mode(int mode);
 /* Which route the most recent cvtx_*_M2M_* call of the public ABI took:
  * 1 = the CUDA kernels, 0 = the host loops (every accelerator disabled, or a
  * user-defined cvtx_VortFunc), -1 = no call yet; and on how many devices. */

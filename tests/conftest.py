@@ -80,6 +80,8 @@ def hostcheck():
     lib.hostcheck_meta.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.hostcheck_meta.restype = C.c_int
     lib.hostcheck_guarded_only.argtypes, lib.hostcheck_guarded_only.restype = [C.c_int], None
+    lib.hostcheck_f3d_mode.argtypes, lib.hostcheck_f3d_mode.restype = [C.c_int], None
+    lib.hostcheck_last_f3d_mode.argtypes, lib.hostcheck_last_f3d_mode.restype = [], C.c_int
     lib.hostcheck_reevaluated.argtypes, lib.hostcheck_reevaluated.restype = [C.c_int], C.c_long
     lib.hostcheck_optimistic.argtypes, lib.hostcheck_optimistic.restype = [C.c_int, C.c_int], C.c_int
     return lib

@@ -102,8 +102,9 @@ def test_full_size_1m_sampled_parity_and_linearity(gpu, oracle, torch_cuda, op, 
     assert float(num / den) <= 2e-6
 
 
-def test_full_size_4m_visc_strength_scaling(gpu, torch_cuda):
-    """Config 3 (4M particles, visc_dvort Winckelmans) on a 64k-target shard: doubling every
+def test_full_size_4m_visc_sampled_parity_and_strength_scaling(gpu, oracle, torch_cuda):
+    """Config 3 (4M particles, visc_dvort Winckelmans) on a 64k-target shard against ALL 4M sources: the
+    oracle checks 256 strided targets of the shard (1e9 pair evaluations on the CPU), and doubling every
     vorticity doubles the result exactly (power-of-two scaling commutes with rounding)."""
     torch = torch_cuda
     _, dev = gpu
@@ -113,10 +114,18 @@ def test_full_size_4m_visc_strength_scaling(gpu, torch_cuda):
     src = torch.from_numpy(P).cuda()
     tgt = src[:m].contiguous()
     a = _device_run(dev, torch, "P3D_M2M_visc_dvort", "winckelmans", src, tgt, 0.02)
+    assert torch.isfinite(a).all()
+    idx = np.arange(0, m, m // 256)[:256]
+    sub = np.ascontiguousarray(P[idx])
+    want = oracle.m2m("P3D_M2M_visc_dvort", P, sub, "winckelmans", 0.02, 1.0)
+    f64 = oracle.m2m("P3D_M2M_visc_dvort", P, sub, "winckelmans", 0.02, 1.0, f64=True)
+    got = a[torch.from_numpy(idx).cuda()].cpu().numpy()
+    e_par, e_gpu, e_ref = rel_l2(got, want), rel_l2(got, f64), rel_l2(want, f64)
+    print(f"P3D_M2M_visc_dvort/winckelmans 4M sampled: gpu-vs-ref {e_par:.2e} gpu-vs-f64 {e_gpu:.2e} ref-vs-f64 {e_ref:.2e}")
+    assert e_par <= TOL and e_gpu <= TOL + e_ref
     src2 = src.clone()
     src2[:, 3:6] *= 2
     b = _device_run(dev, torch, "P3D_M2M_visc_dvort", "winckelmans", src2, src2[:m].contiguous(), 0.02)
-    assert torch.isfinite(a).all()
     assert torch.equal(b, 2 * a)
 
 
@@ -148,8 +157,8 @@ def test_full_size_4m_p2d_sampled_parity(gpu, oracle, torch_cuda):
 
 def test_full_size_filaments_100k_on_2m(gpu, oracle, torch_cuda):
     """Config 5 (100k filaments on 2M points / particles): full run on the GPU, 256 strided targets
-    checked against the oracle (FP64 arbitrates, see is_strict in test_gpu_parity.py), and
-    linearity in the filament strengths checked on every target."""
+    checked against the FP64 oracle at the stated tolerance and against the reference (see
+    assert_parity in test_gpu_parity.py), and linearity in the filament strengths checked on every target."""
     from util import filaments
     torch = torch_cuda
     _, dev = gpu
@@ -168,7 +177,11 @@ def test_full_size_filaments_100k_on_2m(gpu, oracle, torch_cuda):
         got = full[torch.from_numpy(idx).cuda()].cpu().numpy()
         e_par, e_gpu, e_ref = rel_l2(got, f32), rel_l2(got, f64), rel_l2(f32, f64)
         print(f"{op} 100k x 2M sampled: gpu-vs-ref {e_par:.2e} gpu-vs-f64 {e_gpu:.2e} ref-vs-f64 {e_ref:.2e}")
-        assert e_par <= TOL or e_gpu <= 3.0 * e_ref + 1e-6
+        # the stated tolerance against FP64, no slack; never further from it than the FP32 reference;
+        # and against the reference wherever the reference is itself sound
+        assert e_gpu <= TOL and e_gpu <= 1.1 * e_ref + 5e-7
+        if e_ref <= 3e-6:
+            assert e_par <= TOL
         src2 = src.clone()
         src2[:, 6] *= 4                                           # strengths x4 -> results x4 exactly
         assert torch.equal(_device_run(dev, torch, op, "singular", src2, tgt, 0.0), 4 * full)
@@ -281,3 +294,69 @@ def test_optimistic_chains_give_the_bits_of_the_guarded_form(gpu, oracle, op, re
     finally:
         dev.guarded_only(0)
         dev.tune(0, 0)
+
+
+# ---- filaments, second version: fast form + per-target reference tier (pair_math.cuh FILAMENTS) ----
+@pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
+def test_filament_forms_and_the_per_call_choice(gpu, oracle, op):
+    """Short segments -> the cancellation-free form by itself, long ones -> the reference's formula; pinned
+    either way the answer stays within tolerance (the slow tier takes what the fast form must not), and the
+    result is the same for every launch geometry and every cut of the work."""
+    from util import filaments
+    _, dev = gpu
+    rng = np.random.default_rng(21)
+    tgt = particles3d(rng, 3000)
+    tgt = tgt if op.endswith("dvort") else np.ascontiguousarray(tgt[:, :3])
+    try:
+        for seg, auto_like in ((0.1, 0), (None, 1)):
+            fil = filaments(rng, 6000, seg=seg)
+            f32, f64 = oracle.m2m(op, fil, tgt), oracle.m2m(op, fil, tgt, f64=True)
+            res = {}
+            for mode in (-1, 0, 1):
+                dev.f3d_mode(mode)
+                res[mode], _, _ = dev.m2m_host(op, "singular", 0, fil, tgt)
+                e_gpu, e_par, e_ref = rel_l2(res[mode], f64), rel_l2(res[mode], f32), rel_l2(f32, f64)
+                print(f"{op} seg={seg} mode={mode}: gpu-vs-f64 {e_gpu:.2e} gpu-vs-ref {e_par:.2e} ref-vs-f64 {e_ref:.2e}")
+                assert e_gpu <= 1.1 * e_ref + 5e-7 or e_par <= TOL
+            assert np.array_equal(res[-1], res[auto_like])
+            dev.f3d_mode(-1)
+            for T, blocks in ((8, 3), (4, 50), (2, 7), (1, 333)):
+                dev.tune(T, blocks)
+                got, _, _ = dev.m2m_host(op, "singular", 0, fil, tgt)
+                assert np.array_equal(got, res[-1]), (seg, T, blocks)
+            dev.tune(0, 0)
+    finally:
+        dev.f3d_mode(-1)
+        dev.tune(0, 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
+def test_points_on_a_filament_axis_get_the_reference_bits(gpu, oracle, op, mode):
+    """Points on a segment's axis, inside and beyond its ends, and on its end points go through the
+    reference's own operations on the device too (IEEE division and square root, no contraction): the
+    velocity is the reference's bit for bit, the stretching to the last ulp or two (w_t is applied to the
+    sums in FP64).  The first version of this kernel was O(0.1) off beyond the ends."""
+    _, dev = gpu
+    rng = np.random.default_rng(13)
+    try:
+        dev.f3d_mode(mode)
+        for _ in range(20):
+            a, d = rng.uniform(0, 10, 3), rng.uniform(-1, 1, 3)
+            fil = np.zeros((1, 7), np.float32)
+            fil[0, 0:3], fil[0, 3:6], fil[0, 6] = a, a + d, rng.uniform(0.5, 5)
+            a32, d32 = fil[0, 0:3].astype(np.float64), (fil[0, 3:6] - fil[0, 0:3]).astype(np.float64)
+            ts = np.concatenate([rng.uniform(0.02, 0.98, 6), rng.uniform(1.05, 6, 6), rng.uniform(-6, -0.05, 6), [0.0, 1.0]])
+            pts = (a32[None, :] + ts[:, None] * d32[None, :]).astype(np.float32)
+            tgt = np.concatenate([pts, np.tile(np.float32([[0.2, -0.4, 0.9, 0.01]]), (len(pts), 1))], axis=1) if op.endswith("dvort") else pts
+            tgt = np.ascontiguousarray(tgt, np.float32)
+            got, _, _ = dev.m2m_host(op, "singular", 0, fil, tgt)
+            with np.errstate(all="ignore"):
+                want = oracle.m2m(op, fil, tgt)
+            if op == "F3D_M2M_vel":
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (fil, np.abs(got - want).max())
+            else:
+                assert np.all(np.abs(got - want) <= 3e-7 * np.abs(want).max(axis=1, keepdims=True)), (fil, np.abs(got - want).max())
+                assert np.array_equal(got == 0, want == 0)
+    finally:
+        dev.f3d_mode(-1)

@@ -3,9 +3,10 @@
 Bar (BASELINE.json north_star): relative L2 <= 1e-5 per output array against the
 reference's arithmetic (oracle *_f32, which is bit-identical to the reference's OpenMP CPU
 path -- tests/test_oracle.py), arbitrated by the all-FP64 oracle.  In regimes where the
-FP32 reference is itself further than that from the FP64 truth (deep-overlap Gaussian,
-points next to a filament's axis) the GPU has to be at least as close to FP64 as the
-reference is.
+FP32 reference is itself further than that from the FP64 truth (deep-overlap Gaussian)
+the GPU has to be at least as close to FP64 as the reference is.  Filaments: within 1e-5
+of FP64 outright and never further from it than the reference; within 1e-5 of the reference
+wherever the reference is itself within 3e-6 of FP64 (pair_math.cuh FILAMENTS).
 """
 import numpy as np
 import pytest
@@ -33,28 +34,29 @@ def run_all(gpu, oracle, op, reg, src, tgt, sigma, nu=0.1):
 
 
 def assert_parity(got, f32, f64, strict, label, slack=None):
-    # filament sums are dominated by the few targets nearest a filament axis, where FP32
-    # cancellation is worst; which of the two FP32 evaluations lands closer to FP64 there is
-    # seed-dependent (measured 0.2x - 2.5x), hence the wider band for F3D
-    if slack is None:
-        slack = 3.0 if label.startswith("F3D") else 1.5
     assert np.all(np.isfinite(got)), label
     e_par, e_gpu, e_ref = rel_l2(got, f32), rel_l2(got, f64), rel_l2(f32, f64)
     msg = f"{label}: gpu-vs-ref {e_par:.2e}  gpu-vs-f64 {e_gpu:.2e}  ref-vs-f64 {e_ref:.2e}"
     print(msg)
-    if strict:
+    if strict == "f3d":
+        # filaments: the stated tolerance against FP64, no slack; never further from FP64 than the FP32
+        # reference; and the stated tolerance against the reference wherever the reference is itself sound
+        assert e_gpu <= TOL, msg
+        assert e_gpu <= 1.1 * e_ref + 5e-7, msg
+        if e_ref <= 3e-6:
+            assert e_par <= TOL, msg
+    elif strict:
         assert e_par <= TOL, msg
         assert e_gpu <= TOL + e_ref, msg
     else:
-        assert e_par <= TOL or e_gpu <= slack * e_ref + 1e-6, msg
+        assert e_par <= TOL or e_gpu <= (slack or 1.5) * e_ref + 1e-6, msg
 
 
 def is_strict(op, reg):
-    """Where the bar is plain rel-L2 <= 1e-5 against the reference.  Not for the filament ops:
-    their FP32 formulas subtract nearly equal terms (r1.r0/|r1| - r2.r0/|r2|, 1/|r1| - 1/|r2|),
-    which puts the FP32 *reference* itself 0.7-1.3e-5 from FP64 on short segments (measured, see
-    DESIGN.md section 6); there the GPU must be as close to FP64 as the reference is."""
-    return not op.startswith("F3D")
+    """Plain rel-L2 <= 1e-5 against the reference -- for the filament ops the two-sided bar of assert_parity:
+    their FP32 *reference* is 0.2 - 2e-5 from FP64 on short segments (it subtracts nearly equal terms,
+    DESIGN.md section 6), so there the bar is FP64 and the reference's own distance from it."""
+    return "f3d" if op.startswith("F3D") else True
 
 
 # ---- the reference's own differential test recipe (N = 1000, sigma 0.3, nu 0.1) ----
@@ -66,7 +68,9 @@ def test_reference_recipe_overlap(gpu, oracle, op, reg):
         src = filaments(rng, n)                                  # both ends anywhere in the box
         tgt = particles3d(rng, n) if SHAPES[op][3] else points(rng, n, 3)
         got, f32, f64 = run_all(gpu, oracle, op, reg, src, tgt, 0.3)
-        assert_parity(got, f32, f64, strict=False, label=f"{op} long filaments")
+        # long filaments -> the per-call choice is the reference's formula: plain parity, whatever the reference's
+        # own distance from FP64 (1.2e-5 on this recipe)
+        assert rel_l2(got, f32) <= TOL, (rel_l2(got, f32), rel_l2(f32, f64))
         return
     src, tgt = make_case(op, rng, n, n, self_targets=True)
     got, f32, f64 = run_all(gpu, oracle, op, reg, src, tgt, 0.3)
@@ -100,7 +104,7 @@ def test_tiny_box_regime(gpu, oracle, op, reg):
         assert np.all(np.isfinite(got)) and rel_l2(got, f64) < 2.0
         return
     noisy = reg == "gaussian" and op in ("P3D_M2M_vel", "P3D_M2M_dvort")
-    assert_parity(got, f32, f64, strict=is_strict(op, reg) and not noisy, label=f"{op}/{reg} tiny box")
+    assert_parity(got, f32, f64, strict=False if noisy else is_strict(op, reg), label=f"{op}/{reg} tiny box")
 
 
 # ---- smooth vorticity field on a jittered lattice: PSE / stretching cancel to 2nd order ----
@@ -138,14 +142,14 @@ def test_smooth_field(gpu, oracle, reg):
 
 
 # ---- every kernel geometry the planner can choose gives the same answer ----
-@pytest.mark.parametrize("tpt,chunks", [(8, 1), (8, 4), (4, 1), (4, 3), (2, 1), (2, 5), (1, 1), (1, 7), (0, 0)])
+@pytest.mark.parametrize("tpt,chunks", [(8, 1), (8, 4), (4, 1), (4, 3), (2, 1), (2, 5), (1, 1), (1, 7), (8, 37), (4, 296), (1, 1000), (0, 0)])
 @pytest.mark.parametrize("op,reg", [("P3D_M2M_vel", "winckelmans"), ("P3D_M2M_dvort", "gaussian"),
                                      ("P2D_M2M_visc_dvort", "gaussian"), ("F3D_M2M_dvort", "singular")])
 def test_kernel_geometries(gpu, oracle, op, reg, tpt, chunks):
     lib, dev = gpu
     rng = np.random.default_rng(11)
     src, tgt = make_case(op, rng, 2500, 1100, self_targets=SHAPES[op][3])
-    dev.tune(tpt, chunks)
+    dev.tune(tpt, chunks)          # targets per thread, number of persistent blocks the work is cut into
     try:
         got, f32, f64 = run_all(gpu, oracle, op, reg, src, tgt, 0.05, nu=0.5)
     finally:
@@ -272,7 +276,7 @@ def test_points_on_a_vortex_line_follow_the_reference(gpu, oracle, op):
         assert np.all(np.isfinite(got))
         e = rel_l2(got, want)
         print(f"{op} on a line along {d}: gpu-vs-ref {e:.2e}, max |gpu| {np.abs(got).max():.3e}, max |ref| {np.abs(want).max():.3e}")
-        assert e <= 1e-3 and np.abs(got).max() <= 1.05 * np.abs(want).max(), (op, d, e)      # (a fused cross product: e ~ 1e2)
+        assert e <= 1e-5 and np.abs(got).max() <= 1.001 * np.abs(want).max(), (op, d, e)      # (a fused cross product: e ~ 1e2)
     fil = np.zeros((1, 7), np.float32)
     fil[0, 0:3], fil[0, 3:6], fil[0, 6] = (0.1, 0.1, 0.0), (0.7, 0.7, 0.0), 2.0
     pts = np.float32([[0.4, 0.4, 0.0], [0.25, 0.25, 0.0], [1.3, 1.3, 0.0], [-2.0, -2.0, 0.0]])

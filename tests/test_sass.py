@@ -32,12 +32,10 @@ def test_plain_and_guarded_loops_do_the_same_fp32_work(loops):
     pairs = {}
     for row in loops:
         pairs.setdefault((row["policy"], row["T"]), {})[row["form"]] = row
-    both = {k: v for k, v in pairs.items() if len(v) == 2}
-    assert len(both) == 4 * 10, sorted(both)          # 10 optimistic policies x 4 geometries
+    both = {k: v for k, v in pairs.items() if len(v) == 2 and not k[0].startswith("F3D")}
+    assert len(both) == 4 * 8, sorted(both)           # 8 optimistic policies x 4 geometries
     for key, v in both.items():
-        # (F3D dvort's guarded form multiplies t222 * b.w once more, only to test the product for NaN)
-        extra = 1 if key[0] == "F3DDvort" else 0
-        assert v["plain"]["lane_ops"] + extra == v["guarded"]["lane_ops"], (key, v)
+        assert v["plain"]["lane_ops"] == v["guarded"]["lane_ops"], (key, v)
         assert v["plain"]["mufu"] == v["guarded"]["mufu"], (key, v)
         assert v["plain"]["alu"] == 0, (key, v)
 
@@ -56,8 +54,15 @@ def test_loops_match_the_declared_work_per_pair(loops):
         info = api.backend().op_info(ops[name], reg)
         if name == "P3DVort" and reg == "singular":
             continue                                  # zeta = 0: the compiler deletes the loop body
-        extra = 1 if (name == "F3DDvort" and row["form"] == "guarded") else 0
-        assert row["lane_ops"] == info["lane_ops"] + extra, (row, info)
+        if name.startswith("F3D"):
+            # filament tiers: the declared work is the cancellation-free form's; the loop also carries one scalar
+            # multiply per SOURCE (tau l^2), i.e. 1/T per pair.  The reference-formula loop: 41 / 47 lane-ops, 3 MUFU.
+            want = {"new": (info["lane_ops"], info["sfu_ops"]), "ref": ({"F3DVel": 41, "F3DDvort": 47}[name], 3)}[row["form"]]
+            assert want[0] <= row["lane_ops"] <= want[0] + 1.0 / row["T"] + 1e-9, (row, info)
+            assert row["mufu"] == want[1] and row["alu"] == 1.0, (row, info)
+            seen += 1
+            continue
+        assert row["lane_ops"] == info["lane_ops"], (row, info)
         assert row["mufu"] == info["sfu_ops"], (row, info)
         seen += 1
     assert seen >= 100 and lib is not None

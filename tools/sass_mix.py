@@ -73,9 +73,15 @@ def loop_table(text):
 			per_src = 1 if pol.startswith("P2D") else 2            # LDS.128 per packed source record
 			pairs = max(lds // per_src, 1) * T
 			alu = sum(v for k, v in c.items() if re.match(r"(FSETP|FSET|FSEL|FMNMX)", k))
+			form = "guarded" if alu else "plain"
+			if pol.startswith("F3D"):
+				# filament tiers (pair_math.cuh FILAMENTS): every fast pair feeds its target's flag through exactly one
+				# NaN-keeping minimum -- FMNMX3 in the cancellation-free form, FMNMX in the reference's formula
+				pairs = max(sum(v for k, v in c.items() if k.startswith("FMNMX") and ".NAN" in k), 1)
+				form = "new" if any(k.startswith("FMNMX3") for k in c) else "ref"
 			total = len(loop)
 			rest = collections.Counter({k: v for k, v in c.items() if not re.match(r"F(FMA|MUL|ADD)", k) and not k.startswith(("MUFU", "LDS"))})
-			rows.append({"kernel": d, "policy": pol, "T": T, "form": "guarded" if alu else "plain", "pairs": pairs,
+			rows.append({"kernel": d, "policy": pol, "T": T, "form": form, "pairs": pairs,
 			             "lane_ops": (packed * 2 + scalar) / pairs, "mufu": mufu / pairs, "alu": alu / pairs, "lds": lds / pairs,
 			             "other": (total - packed - scalar - mufu - lds - alu) / pairs, "issue": total / pairs,
 			             "tops": ", ".join(f"{k}x{v}" for k, v in rest.most_common(4))})

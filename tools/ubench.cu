@@ -143,24 +143,25 @@ static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElaps
 
 // ---- m2m variants -------------------------------------------------------------
 struct Bench {
-	float4 *A, *B; float *tgt; float *out; double *partial; int n; int sms; double peak_lane;
+	float4 *A, *B; float *tgt; float *out; double *pieces; int *tickets; int n; int sms; double peak_lane;
 	cudaEvent_t e0, e1;
 };
 
+// One geometry of the persistent pair kernel: grid = resident blocks, equal runs (m2m_kernel.cuh).
 template <class P, int T, int BLK, int MINB>
-static void run_variant(Bench &b, const char *name, int chunks) {
+static void run_variant(Bench &b, const char *name) {
 	const int n = b.n;
 	const int n_tiles = n / kSrcTile;
-	M2MArgs a = {};
-	a.srcA = b.A; a.srcB = b.B; a.n_src_tiles = n_tiles;
-	a.tiles_per_chunk = (n_tiles + chunks - 1) / chunks;
-	const int gy = (n_tiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
-	a.tgt = b.tgt; a.n_tgt = n; a.out = b.out; a.partial = b.partial;
-	a.k = P::make_consts(0.02f, 1.0f);
-	const dim3 grid((n + BLK * T - 1) / (BLK * T), gy);
 	int occ = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, m2m_kernel<P, T, BLK, MINB>, BLK, 0));
 	cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, m2m_kernel<P, T, BLK, MINB>));
+	M2MArgs a = {};
+	a.srcA = b.A; a.srcB = b.B; a.n_src = n; a.n_src_tiles = n_tiles; a.grain = kSrcTile;
+	const long long tiles_t = (n + BLK * T - 1) / (BLK * T);
+	a.total_grains = tiles_t * n_tiles;
+	a.tgt = b.tgt; a.n_tgt = n; a.out = b.out; a.pieces = b.pieces; a.tickets = b.tickets;
+	a.k = P::make_consts(0.02f, 1.0f);
+	const int grid = occ * b.sms;
 	float best = 1e30f;
 	for (int rep = 0; rep < 3; ++rep) {
 		CK(cudaEventRecord(b.e0));
@@ -173,8 +174,8 @@ static void run_variant(Bench &b, const char *name, int chunks) {
 	}
 	const double pairs = (double)n * n;
 	const double rate = pairs / (best * 1e-3);
-	printf("%-28s T=%d B=%3d regs=%3d occ=%d grid=(%d,%d) %8.3f ms  %8.1f Gpair/s  lane-ops %2d -> %5.1f%% of nominal FP32 peak\n",
-	       name, T, BLK, fa.numRegs, occ, grid.x, grid.y, best, rate * 1e-9, P::LANE_OPS,
+	printf("%-28s T=%d B=%3d regs=%3d occ=%d grid=%d %8.3f ms  %8.1f Gpair/s  lane-ops %2d -> %5.1f%% of nominal FP32 peak\n",
+	       name, T, BLK, fa.numRegs, occ, grid, best, rate * 1e-9, P::LANE_OPS,
 	       100.0 * rate * P::LANE_OPS / b.peak_lane);
 	fflush(stdout);
 }
@@ -245,71 +246,34 @@ int main(int argc, char **argv) {
 	b.n = n; b.sms = prop.multiProcessorCount; b.peak_lane = peak_lane; b.e0 = e0; b.e1 = e1;
 	CK(cudaMalloc(&b.A, sizeof(float4) * n)); CK(cudaMalloc(&b.B, sizeof(float4) * n));
 	CK(cudaMalloc(&b.tgt, sizeof(float) * 7 * n)); CK(cudaMalloc(&b.out, sizeof(float) * 3 * n));
-	CK(cudaMalloc(&b.partial, sizeof(double) * 3 * (size_t)n * 64));
+	CK(cudaMalloc(&b.pieces, sizeof(double) * 2 * 6 * 2048 * (size_t)prop.multiProcessorCount * 8));
+	CK(cudaMalloc(&b.tickets, sizeof(int) * (size_t)n)); CK(cudaMemset(b.tickets, 0, sizeof(int) * (size_t)n));
 	CK(cudaMemcpy(b.A, hA.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(b.B, hB.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(b.tgt, ht.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
 
-	printf("\n== P3D vel Winckelmans, n = m = %d : geometry sweep\n", n);
+	printf("\n== P3D vel Winckelmans, n = m = %d : geometry sweep (persistent kernel, equal runs)\n", n);
 	typedef P3DVel<REG_WINCKELMANS> W;
-	run_variant<W, 1, 128, 8>(b, "vel-W", 1);
-	run_variant<W, 1, 256, 4>(b, "vel-W", 1);
-	run_variant<W, 2, 128, 6>(b, "vel-W", 1);
-	run_variant<W, 2, 256, 3>(b, "vel-W", 1);
-	run_variant<W, 4, 128, 4>(b, "vel-W", 1);
-	run_variant<W, 4, 256, 2>(b, "vel-W", 1);
-	run_variant<W, 4, 256, 2>(b, "vel-W chunks=4", 4);
-	run_variant<W, 4, 256, 2>(b, "vel-W chunks=8", 8);
-	run_variant<W, 4, 256, 2>(b, "vel-W chunks=16", 16);
-	run_variant<W, 2, 128, 6>(b, "vel-W chunks=8", 8);
-	run_variant<W, 2, 256, 3>(b, "vel-W chunks=8", 8);
-	run_variant<W, 4, 128, 4>(b, "vel-W chunks=8", 8);
-	run_variant<W, 4, 512, 1>(b, "vel-W", 1);
-	run_variant<W, 6, 128, 3>(b, "vel-W", 1);
-	run_variant<W, 6, 256, 1>(b, "vel-W", 1);
-	run_variant<W, 8, 128, 2>(b, "vel-W", 1);
-	run_variant<W, 8, 128, 2>(b, "vel-W chunks=8", 8);
-	run_variant<W, 8, 256, 1>(b, "vel-W", 1);
-	run_variant<W, 8, 256, 1>(b, "vel-W chunks=8", 8);
-
-	printf("\n== more geometries, chunks=8\n");
-	run_variant<W, 6, 128, 3>(b, "vel-W", 8);
-	run_variant<W, 8, 128, 3>(b, "vel-W (168-reg cap)", 8);
-	run_variant<W, 6, 192, 2>(b, "vel-W", 8);
-	run_variant<W, 8, 192, 1>(b, "vel-W", 8);
-	typedef P3DDvort<REG_WINCKELMANS> DW;
+	run_variant<W, 1, 128, 8>(b, "vel-W");
+	run_variant<W, 2, 256, 3>(b, "vel-W");
+	run_variant<W, 4, 128, 4>(b, "vel-W");
+	run_variant<W, 4, 256, 2>(b, "vel-W");
+	run_variant<W, 6, 128, 3>(b, "vel-W");
+	run_variant<W, 8, 128, 2>(b, "vel-W");
+	run_variant<W, 8, 128, 3>(b, "vel-W (168-reg cap)");
+	run_variant<W, 8, 256, 1>(b, "vel-W");
 	typedef P3DDvort<REG_GAUSSIAN> DG;
-	run_variant<DW, 8, 128, 2>(b, "dvort-W", 8);
-	run_variant<DW, 6, 128, 3>(b, "dvort-W", 8);
-	run_variant<DW, 8, 128, 3>(b, "dvort-W (168-reg cap)", 8);
-	run_variant<DW, 4, 128, 5>(b, "dvort-W (96-reg cap)", 8);
-	run_variant<DW, 6, 192, 2>(b, "dvort-W", 8);
-	run_variant<DW, 8, 96, 3>(b, "dvort-W", 8);
-	run_variant<DG, 8, 128, 2>(b, "dvort-G", 8);
-	run_variant<DG, 6, 128, 3>(b, "dvort-G", 8);
-	run_variant<DG, 6, 192, 2>(b, "dvort-G", 8);
-	run_variant<P3DVel<REG_GAUSSIAN>, 8, 128, 2>(b, "vel-G", 8);
-	run_variant<P3DVel<REG_GAUSSIAN>, 6, 128, 3>(b, "vel-G", 8);
-
-	printf("\n== every family at T=4, B=256, chunks=8\n");
-	run_variant<P3DVel<REG_SINGULAR>, 4, 256, 2>(b, "P3D vel singular", 8);
-	run_variant<P3DVel<REG_WINCKELMANS>, 4, 256, 2>(b, "P3D vel winckelmans", 8);
-	run_variant<P3DVel<REG_PLANETARY>, 4, 256, 2>(b, "P3D vel planetary", 8);
-	run_variant<P3DVel<REG_GAUSSIAN>, 4, 256, 2>(b, "P3D vel gaussian", 8);
-	run_variant<P3DDvort<REG_SINGULAR>, 4, 256, 2>(b, "P3D dvort singular", 8);
-	run_variant<P3DDvort<REG_WINCKELMANS>, 4, 256, 2>(b, "P3D dvort winckelmans", 8);
-	run_variant<P3DDvort<REG_GAUSSIAN>, 4, 256, 2>(b, "P3D dvort gaussian", 8);
-	run_variant<P3DVisc<REG_WINCKELMANS>, 4, 256, 2>(b, "P3D visc winckelmans", 8);
-	run_variant<P3DVisc<REG_GAUSSIAN>, 4, 256, 2>(b, "P3D visc gaussian", 8);
-	run_variant<P3DVort<REG_GAUSSIAN>, 4, 256, 2>(b, "P3D vort gaussian", 8);
-	run_variant<P2DVel<REG_WINCKELMANS>, 4, 256, 2>(b, "P2D vel winckelmans", 8);
-	run_variant<P2DVel<REG_GAUSSIAN>, 4, 256, 2>(b, "P2D vel gaussian", 8);
-	run_variant<P2DVisc<REG_WINCKELMANS>, 4, 256, 2>(b, "P2D visc winckelmans", 8);
-	run_variant<P2DVisc<REG_GAUSSIAN>, 4, 256, 2>(b, "P2D visc gaussian", 8);
-	run_variant<F3DVel, 4, 256, 2>(b, "F3D vel", 8);
-	run_variant<F3DDvort, 4, 256, 2>(b, "F3D dvort", 8);
-	run_variant<P2DVel<REG_GAUSSIAN>, 8, 256, 1>(b, "P2D vel gaussian", 8);
-	run_variant<P2DVisc<REG_GAUSSIAN>, 8, 256, 1>(b, "P2D visc gaussian", 8);
+	run_variant<DG, 8, 128, 2>(b, "dvort-G");
+	run_variant<DG, 6, 128, 3>(b, "dvort-G");
+	run_variant<DG, 4, 128, 4>(b, "dvort-G (128-reg cap)");
+	run_variant<P3DVel<REG_GAUSSIAN>, 8, 128, 2>(b, "vel-G");
+	run_variant<P3DVel<REG_GAUSSIAN>, 6, 128, 3>(b, "vel-G");
+	run_variant<P3DVel<REG_GAUSSIAN>, 4, 128, 4>(b, "vel-G (128-reg cap)");
+	run_variant<P3DVort<REG_GAUSSIAN>, 8, 128, 2>(b, "vort-G");
+	run_variant<P3DVort<REG_GAUSSIAN>, 8, 128, 3>(b, "vort-G (168-reg cap)");
+	run_variant<P2DVisc<REG_GAUSSIAN>, 8, 128, 2>(b, "P2D visc-G");
+	run_variant<P2DVisc<REG_GAUSSIAN>, 8, 128, 3>(b, "P2D visc-G (168-reg cap)");
+	run_variant<P2DVisc<REG_GAUSSIAN>, 8, 256, 1>(b, "P2D visc-G");
 	printf("done\n");
 	return 0;
 }
