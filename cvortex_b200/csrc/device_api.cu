@@ -94,47 +94,90 @@ int ensure_ready(Device *d) {                   // caller holds d->mu and has do
 }
 
 // ---- launch planning ----------------------------------------------------------
-struct Plan { int T, B, occ, grain, grid; long long tiles_t, total_grains; };
+// One compiled geometry of the pair kernel for one policy: what the planner needs to know about it.
+struct KernelChoice { const void *fn; int T, B; size_t smem; int occ; };
 
 // Source sets below this many tiles are walked in grains (= FP32 chains) of 32 sources instead of
 // 256, so that a 10k x 10k call still cuts into enough equal runs for every resident block.  A
 // property of the SOURCES alone: every shard of a multi-GPU call rounds alike.
 constexpr int kSmallSourceTiles = 64;
+// The grid is this many times the blocks that are resident at once when the problem is big enough:
+// two blocks that share an SM do not advance at the same pace (the warp schedulers favour one of them:
+// with exactly one resident set the favoured block of every SM was measured to finish after 54 % of the
+// launch and its partner ran the rest alone, profiles/kernel_ab_r2.txt), so the hardware block scheduler
+// has to have a next run to hand out.  Runs stay equal; 3 ... 8 measured the same, 16 worse.
+constexpr int kRunsPerSlot = 4;
+constexpr int kMinRunGrains = 24;
 
-// Pick the block geometry (targets per thread).  The kernel is persistent and its runs are equal,
-// so a launch costs  (grains per block) x (slots per grain) x (blocks sharing an SM) / (the geometry's
-// measured relative efficiency): for large problems that is the op's preferred geometry, for small
-// ones it trades the padding of the last target tile against parallelism (10k x 10k, few targets).
-Plan make_plan(int n_src, int n_tgt, int sm_count, int pref_T) {
-	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
-	static const int cand_T[4] = {8, 4, 2, 1}, cand_B[4] = {128, 256, 256, 128}, cand_occ[4] = {2, 2, 3, 8};
-	static const double cand_eff[4] = {1.0, 0.985, 0.96, 0.79};      // profiles/sweep_ops_r1.txt, ubench_r1.txt
-	const int fT = g_force_T.load(), fG = g_force_chunks.load();
-	const int first = pref_T >= 8 ? 0 : (pref_T >= 4 ? 1 : (pref_T >= 2 ? 2 : 3));
-	const int grain = n_src_tiles < kSmallSourceTiles ? 32 : kSrcTile;
-	Plan p = {};
-	double best = 1e300;
-	for (int v = 0; v < 4; ++v) {
-		if (fT ? cand_T[v] != fT : v < first) continue;
-		const long long slots = (long long)cand_B[v] * cand_T[v];
-		const long long tiles_t = ((long long)n_tgt + slots - 1) / slots;
-		const long long total = tiles_t * n_src_tiles * (kSrcTile / grain);
-		long long grid = (long long)sm_count * cand_occ[v];
-		if (fG > 0) grid = fG;
-		if (grid > total) grid = total;
-		if (grid < 1) grid = 1;
-		const long long per_block = (total + grid - 1) / grid;
-		const long long sharing = (grid + sm_count - 1) / sm_count;
-		const double cost = (double)per_block * grain * (double)slots * (double)sharing / cand_eff[v]
-		                    + 4000.0 * (double)slots / 128.0;         // per-block prologue, ~1 us
-		if (cost < best) {
-			best = cost;
-			p.T = cand_T[v]; p.B = cand_B[v]; p.occ = cand_occ[v]; p.grain = grain; p.grid = (int)grid;
-			p.tiles_t = tiles_t; p.total_grains = total;
+// The kernel (function pointer, dynamic shared memory, blocks per SM) of policy P in geometry V
+// (0: T=8 B=128, 1: T=4 B=256, 2: T=2 B=256, 3: T=1 B=128) for chain length `grain`.  The two
+// large-problem geometries exist with the chain length as a compile-time 256 (the form ptxas
+// schedules best) and as a run-time value for small source sets; vector width
+// and accumulator placement are the policy's measured TUNE_* constants.
+template <class P, int T, int B, int MINB, int VW, int OPT, int GRAIN>
+KernelChoice choice_of(int device) {
+	auto kern = m2m_kernel<P, T, B, MINB, VW, OPT, GRAIN>;
+	static int occ_cache[64];                          // per device: the attribute below is per device too
+	const size_t smem = m2m_smem_bytes<P, T, B, OPT>();
+	int &occ = occ_cache[device & 63];
+	if (occ == 0) {
+		if (smem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		int o = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, B, smem) != cudaSuccess || o < 1) { cudaGetLastError(); o = MINB; }
+		occ = o;
+	}
+	KernelChoice c = {(const void *)kern, T, B, smem, occ};
+	return c;
+}
+template <class P> KernelChoice choice(int v, bool grain256, int device) {
+	if (v == 0) return grain256 ? choice_of<P, 8, 128, 2, P::VW8, P::OPT8, 256>(device) : choice_of<P, 8, 128, 2, P::VW8, P::OPT8, 0>(device);
+	if (v == 1) return grain256 ? choice_of<P, 4, 256, 2, P::VW4, P::OPT4, 256>(device) : choice_of<P, 4, 256, 2, P::VW4, P::OPT4, 0>(device);
+	if (v == 2) return choice_of<P, 2, 256, 3, 2, 0, 0>(device);
+	return choice_of<P, 1, 128, 8, 1, 0, 0>(device);
+}
+
+struct Plan { KernelChoice k; int grain, grid; long long tiles_t, total_grains; };
+
+// Pick the block geometry (targets per thread) and the grid.  The work -- (target tile) x (grain) cells
+// -- is cut into `grid` equal runs; a launch costs (grains per run) x (slots per grain) x (waves of runs)
+// / (the geometry's measured relative efficiency): for large problems that is the op's preferred
+// geometry, for small ones it trades the padding of the last target tile against parallelism.
+struct Planner {
+	int device, n_src, n_tgt, sm_count; Plan plan;
+	template <class P> void run() {
+		const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
+		static const double cand_eff[4] = {1.0, 0.985, 0.96, 0.79};      // profiles/sweep_ops_r1.txt, ubench_r1.txt
+		const int fT = g_force_T.load(), fG = g_force_chunks.load();
+		const int pref = P::PREF_T;
+		const int first = pref >= 8 ? 0 : (pref >= 4 ? 1 : (pref >= 2 ? 2 : 3));
+		const int grain = n_src_tiles < kSmallSourceTiles ? 32 : kSrcTile;
+		double best = 1e300;
+		plan = Plan();
+		for (int v = 0; v < 4; ++v) {
+			const KernelChoice k = choice<P>(v, grain == kSrcTile, device);
+			if (fT ? k.T != fT : v < first) continue;
+			const long long slots = (long long)k.B * k.T;
+			const long long tiles_t = ((long long)n_tgt + slots - 1) / slots;
+			const long long total = tiles_t * n_src_tiles * (kSrcTile / grain);
+			const long long resident = (long long)sm_count * k.occ;
+			long long mult = total / (resident * kMinRunGrains);
+			mult = mult < 1 ? 1 : (mult > kRunsPerSlot ? kRunsPerSlot : mult);
+			long long grid = resident * mult;
+			if (fG > 0) grid = fG;
+			if (grid > total) grid = total;
+			if (grid < 1) grid = 1;
+			const long long per_block = (total + grid - 1) / grid;
+			const long long waves = (grid + resident - 1) / resident;
+			const long long sharing = grid < resident ? (grid + sm_count - 1) / sm_count : k.occ;
+			const double cost = (double)per_block * (double)waves * grain * (double)slots * (double)sharing / cand_eff[v]
+			                    + 4000.0 * (double)waves * (double)slots / 128.0;         // per-block prologue, ~1 us
+			if (cost < best) {
+				best = cost;
+				plan.k = k; plan.grain = grain; plan.grid = (int)grid; plan.tiles_t = tiles_t; plan.total_grains = total;
+			}
 		}
 	}
-	return p;
-}
+};
 
 // Chains shorter than this many tiles per target are evaluated in the guarded form straight away:
 // a self-interaction call re-evaluates one chain per target, which is noise among thousands of
@@ -196,21 +239,9 @@ int f3d_mode_override() {
 	return v;
 }
 
-struct Launcher {
-	M2MArgs args; Plan plan; cudaStream_t st; cudaError_t err;
-	template <class P> void run() {
-		const dim3 grid(plan.grid);
-		if (plan.T == 8) m2m_kernel<P, 8, 128, 2><<<grid, 128, 0, st>>>(args);
-		else if (plan.T == 4) m2m_kernel<P, 4, 256, 2><<<grid, 256, 0, st>>>(args);
-		else if (plan.T == 2) m2m_kernel<P, 2, 256, 3><<<grid, 256, 0, st>>>(args);
-		else m2m_kernel<P, 1, 128, 8><<<grid, 128, 0, st>>>(args);
-		err = cudaGetLastError();
-	}
-};
-
 struct Info {
-	int lane, sfu, tcols, nout, pref_T;
-	template <class P> void run() { lane = P::LANE_OPS; sfu = P::SFU_OPS; tcols = P::TCOLS; nout = P::NOUT; pref_T = P::PREF_T; }
+	int lane, sfu, tcols, nout;
+	template <class P> void run() { lane = P::LANE_OPS; sfu = P::SFU_OPS; tcols = P::TCOLS; nout = P::NOUT; }
 };
 
 struct ConstsOf {
@@ -229,6 +260,7 @@ cvtx::Device *cvtx::get_device(int device) {
 int cvtx::device_stream(int device, cudaStream_t *stream) {
 	Device *d = get_device(device);
 	if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
@@ -259,6 +291,8 @@ int cvtx_b200_device_clock_khz(int device) {
 }
 
 void cvtx_b200_release(void) {
+	release_exchange();
+	DeviceGuard restore;
 	{
 		std::lock_guard<std::mutex> lk(g_devices_mu);
 		for (size_t i = 0; i < g_devices.size(); ++i) {
@@ -296,9 +330,16 @@ int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tp
 	Info q = {};
 	if (!d || n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "bad device or counts");
 	if (!dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "bad op");
-	const Plan p = make_plan(n_src, n_tgt, d->prop.multiProcessorCount, q.pref_T);
-	if (block) *block = p.B;
-	if (tpt) *tpt = p.T;
+	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, {}};
+	{
+		DeviceGuard restore;
+		std::lock_guard<std::mutex> lk(d->mu);
+		CUDA_TRY(cudaSetDevice(device));
+		dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, pl);
+	}
+	const Plan &p = pl.plan;
+	if (block) *block = p.k.B;
+	if (tpt) *tpt = p.k.T;
 	if (grid_x) *grid_x = p.grid;
 	if (grid_y) *grid_y = p.grain;
 	return CVTX_B200_OK;
@@ -317,6 +358,7 @@ const char *cvtx_b200_last_error(void) { return g_err.c_str(); }
 float cvtx_b200_last_pair_kernel_ms(int device) {
 	Device *d = get_device(device);
 	if (!d) return -1.f;
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(d->mu);
 	if (!d->timed) return -1.f;
 	float ms = -1.f;
@@ -331,6 +373,7 @@ int cvtx_b200_measure_peak(int device, int what, double *ops_per_second)
 	g_err.clear();
 	Device *d = get_device(device);
 	if (!d || !ops_per_second || (what != 0 && what != 1)) return fail(CVTX_B200_ERR_ARGUMENT, "bad device, selector or pointer");
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
@@ -377,6 +420,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	if (!tgt || !out || (n_src > 0 && !src)) return fail(CVTX_B200_ERR_ARGUMENT, "null pointer");
 
 	cudaStream_t st = (cudaStream_t)stream_;
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
@@ -385,7 +429,9 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 		return CVTX_B200_OK;
 	}
 
-	const Plan plan = make_plan(n_src, n_tgt, d->prop.multiProcessorCount, q.pref_T);
+	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, {}};
+	dispatch_op(op, reg, pl);
+	const Plan &plan = pl.plan;
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
 	const int n_pad = n_src_tiles * kSrcTile;
 	const int records = src_records(op);
@@ -396,7 +442,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	// the arena may still be in use by an earlier call on another stream
 	CUDA_TRY(cudaStreamWaitEvent(st, d->arena_idle, 0));
 	const size_t need_packed = (size_t)n_pad * sizeof(float4);
-	const size_t need_pieces = sizeof(double) * 2 * (size_t)plan.grid * plan.T * plan.B * q.nout;
+	const size_t need_pieces = sizeof(double) * 2 * (size_t)plan.grid * plan.k.T * plan.k.B * q.nout;
 	const size_t need_tickets = sizeof(int) * (size_t)plan.tiles_t;
 	const size_t need_aux = filament ? sizeof(F3DStats) * (size_t)n_src_tiles + 64 : 0;
 	if (need_packed > d->packedA.cap || (records >= 2 && need_packed > d->packedB.cap) || (records >= 3 && need_packed > d->packedC.cap)
@@ -429,29 +475,27 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 
 	ConstsOf ck = {sigma, nu, {}};
 	dispatch_op(op, reg, ck);
-	Launcher L = {};
-	L.args.srcA = (const float4 *)d->packedA.p;
-	L.args.srcB = records >= 2 ? (const float4 *)d->packedB.p : nullptr;
-	L.args.srcC = records >= 3 ? (const float4 *)d->packedC.p : nullptr;
-	L.args.src_raw = src;
-	L.args.n_src = n_src;
-	L.args.n_src_tiles = n_src_tiles;
-	L.args.grain = plan.grain;
-	L.args.total_grains = plan.total_grains;
-	L.args.tgt = tgt;
-	L.args.n_tgt = n_tgt;
-	L.args.out = out;
-	L.args.pieces = (double *)d->pieces.p;
-	L.args.tickets = (int *)d->tickets.p;
-	L.args.f3d_mode = mode_word;
-	L.args.k = ck.k;
+	M2MArgs args = {};
+	args.srcA = (const float4 *)d->packedA.p;
+	args.srcB = records >= 2 ? (const float4 *)d->packedB.p : nullptr;
+	args.srcC = records >= 3 ? (const float4 *)d->packedC.p : nullptr;
+	args.src_raw = src;
+	args.n_src = n_src;
+	args.n_src_tiles = n_src_tiles;
+	args.grain = plan.grain;
+	args.total_grains = plan.total_grains;
+	args.tgt = tgt;
+	args.n_tgt = n_tgt;
+	args.out = out;
+	args.pieces = (double *)d->pieces.p;
+	args.tickets = (int *)d->tickets.p;
+	args.f3d_mode = mode_word;
+	args.k = ck.k;
 	const int gm = guard_mode();
-	L.args.exact_only = (gm == 1 || (gm == 0 && n_src_tiles < kMinTilesOptimistic)) ? 1 : 0;
-	L.plan = plan;
-	L.st = st;
+	args.exact_only = (gm == 1 || (gm == 0 && n_src_tiles < kMinTilesOptimistic)) ? 1 : 0;
 	CUDA_TRY(cudaEventRecord(d->k_start, st));
-	dispatch_op(op, reg, L);
-	CUDA_TRY(L.err);
+	void *params[1] = {&args};
+	CUDA_TRY(cudaLaunchKernel(plan.k.fn, dim3(plan.grid), dim3(plan.k.B), params, plan.k.smem, st));
 	CUDA_TRY(cudaEventRecord(d->k_stop, st));
 	d->timed = true;
 	CUDA_TRY(cudaEventRecord(d->arena_idle, st));
@@ -468,6 +512,7 @@ int cvtx_b200_f3d_inf_mtrx(int device, void *stream_, const float *fil, int n_fi
 	if (n_fil < 0 || n_mes < 0) return fail(CVTX_B200_ERR_ARGUMENT, "negative count");
 	if (n_fil == 0 || n_mes == 0) return CVTX_B200_OK;
 	if (!fil || !mes || !dir || !out) return fail(CVTX_B200_ERR_ARGUMENT, "null pointer");
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
@@ -504,6 +549,7 @@ int cvtx_b200_m2m_host(int op, int reg, int device, const float *src, int n_src,
 	const size_t sb = sizeof(float) * (size_t)n_src * src_cols(op);
 	const size_t tb = sizeof(float) * (size_t)n_tgt * q.tcols;
 	HostStage &hs = host_stage();
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(hs.mu);
 	CUDA_TRY(cudaSetDevice(device));
 	CUDA_TRY(hs.src.reserve(sb));
@@ -516,59 +562,70 @@ int cvtx_b200_m2m_host(int op, int reg, int device, const float *src, int n_src,
 }  // extern "C"
 
 // =============================================================================
-// Staged multi-device runner: one host thread drives every device
-// asynchronously (H2D of the replicated sources and of the device's target
-// shard, pack + pair kernels, D2H of the shard's result), then waits for all.
-// Targets are embarrassingly parallel -- each output is an independent sum over
-// all sources (reference src/P3D.cpp:335-339) -- so the results need no
-// collective; each device writes its own slice.
-int cvtx::run_staged(int op, int reg, const std::vector<int> &devices, int n_src, int n_tgt,
+// Staged multi-device runner: one host thread drives every device asynchronously.  The source
+// set crosses PCIe once in total: device g receives rows [g n / G, (g + 1) n / G) straight into
+// their place in its full-size buffer, the devices then all-gather the shards between themselves
+// (exchange.cu: NCCL over NVLink), and each runs pack + pair kernels on its own target shard and
+// returns that shard's result.  Targets are embarrassingly parallel -- each output is an independent
+// sum over all sources (reference src/P3D.cpp:335-339) -- so the results need no collective.
+int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_src, int n_tgt,
                      float *out, float sigma, float nu, size_t *h2d_bytes, size_t *d2h_bytes)
 {
 	Info q = {};
 	if (op_is_filament(op)) reg = REG_SINGULAR;
 	if (!dispatch_op(op, reg, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "no kernel for this (op, regularisation)");
-	if (devices.empty()) return fail(CVTX_B200_ERR_ARGUMENT, "no device given");
+	if (devices_in.empty()) return fail(CVTX_B200_ERR_ARGUMENT, "no device given");
+	DeviceGuard restore;
 	HostStage &hs = host_stage();
+	// a device without a target has nothing to do: use the first min(G, n_tgt) devices
+	std::vector<int> devices(devices_in.begin(), devices_in.begin() + (n_tgt < (int)devices_in.size() ? (n_tgt > 0 ? n_tgt : 1) : (int)devices_in.size()));
 	const int G = (int)devices.size();
 	const size_t srow = sizeof(float) * src_cols(op), trow = sizeof(float) * q.tcols, orow = sizeof(float) * q.nout;
-	const size_t sb = srow * (size_t)n_src;
 	CUDA_TRY(cudaSetDevice(devices[0]));
 	CUDA_TRY(hs.out.reserve(orow * (size_t)n_tgt));
+	std::vector<cudaStream_t> streams(G, nullptr);
+	std::vector<const void *> shard(G, nullptr);
+	std::vector<void *> full(G, nullptr);
+	std::vector<long> soff(G + 1, 0);
+	for (int g = 0; g <= G; ++g) soff[g] = (long)n_src * g / G;
 	size_t up = 0, down = 0;
 	for (int g = 0; g < G; ++g) {
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
-		if (hi == lo) continue;
 		Device *d = get_device(devices[g]);
 		if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
-		cudaStream_t st;
 		{
 			std::lock_guard<std::mutex> lk(d->mu);
 			CUDA_TRY(cudaSetDevice(devices[g]));
 			if (int rc = ensure_ready(d)) return rc;
-			st = d->stream;
-			CUDA_TRY(d->d_src.reserve(sb));
+			streams[g] = d->stream;
+			CUDA_TRY(d->d_src.reserve(srow * (size_t)n_src));
 			CUDA_TRY(d->d_tgt.reserve(trow * (size_t)(hi - lo)));
 			CUDA_TRY(d->d_out.reserve(orow * (size_t)(hi - lo)));
 		}
-		if (sb) CUDA_TRY(cudaMemcpyAsync(d->d_src.p, hs.src.p, sb, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaMemcpyAsync(d->d_tgt.p, (const char *)hs.tgt.p + trow * lo, trow * (size_t)(hi - lo),
-		                         cudaMemcpyHostToDevice, st));
-		if (int rc = cvtx_b200_m2m(op, reg, devices[g], st, (const float *)d->d_src.p, n_src,
-		                           (const float *)d->d_tgt.p, (int)(hi - lo), (float *)d->d_out.p, sigma, nu))
-			return rc;
-		CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo),
-		                         cudaMemcpyDeviceToHost, st));
+		full[g] = d->d_src.p;
+		shard[g] = (const char *)d->d_src.p + srow * (size_t)soff[g];
+		const size_t sb = srow * (size_t)(soff[g + 1] - soff[g]);
+		if (sb) CUDA_TRY(cudaMemcpyAsync((void *)shard[g], (const char *)hs.src.p + srow * (size_t)soff[g], sb, cudaMemcpyHostToDevice, streams[g]));
+		if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d->d_tgt.p, (const char *)hs.tgt.p + trow * lo, trow * (size_t)(hi - lo), cudaMemcpyHostToDevice, streams[g]));
 		up += sb + trow * (size_t)(hi - lo);
-		down += orow * (size_t)(hi - lo);
 	}
+	if (int rc = all_gather_rows(devices, streams, shard, soff, full, srow)) return rc;
 	for (int g = 0; g < G; ++g) {
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
 		if (hi == lo) continue;
 		Device *d = get_device(devices[g]);
+		if (int rc = cvtx_b200_m2m(op, reg, devices[g], streams[g], (const float *)d->d_src.p, n_src,
+		                           (const float *)d->d_tgt.p, (int)(hi - lo), (float *)d->d_out.p, sigma, nu))
+			return rc;
 		CUDA_TRY(cudaSetDevice(devices[g]));
-		CUDA_TRY(cudaStreamSynchronize(d->stream));
-		std::memcpy((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
+		CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo), cudaMemcpyDeviceToHost, streams[g]));
+		down += orow * (size_t)(hi - lo);
+	}
+	for (int g = 0; g < G; ++g) {
+		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
+		CUDA_TRY(cudaSetDevice(devices[g]));
+		CUDA_TRY(cudaStreamSynchronize(streams[g]));
+		if (hi > lo) std::memcpy((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
 	}
 	if (h2d_bytes) *h2d_bytes = up;
 	if (d2h_bytes) *d2h_bytes = down;

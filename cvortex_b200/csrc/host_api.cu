@@ -143,6 +143,7 @@ bool gpu_m2m(const char *entry, int op, const cvtx_VortFunc *kernel,
 	cvtx_b200_op_info(op, reg, &scols, &tcols, nullptr, nullptr, nullptr);
 	const size_t srow = sizeof(float) * scols, trow = sizeof(float) * tcols;
 	HostStage &hs = host_stage();
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(hs.mu);
 	cudaError_t e = cudaSetDevice(devs[0]);
 	if (e == cudaSuccess) e = hs.src.reserve(srow * (size_t)(n_src > 0 ? n_src : 0));
@@ -330,6 +331,7 @@ CVTX_API void cvtx_F3D_inf_mtrx(const cvtx_F3D **array_start, const int num_fila
 	const int dev = devs[0];
 	Device *d = get_device(dev);
 	HostStage &hs = host_stage();
+	DeviceGuard restore;
 	std::lock_guard<std::mutex> lk(hs.mu);
 	const size_t fb = sizeof(cvtx_F3D) * (size_t)num_filaments, pb = sizeof(bsv_V3f) * (size_t)num_mes;
 	const size_t row_bytes = sizeof(float) * (size_t)num_filaments;

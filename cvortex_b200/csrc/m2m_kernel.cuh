@@ -6,17 +6,18 @@
 // 256-wide shared-memory tree adds them up, work-item 0 read-modify-writes the
 // target's result, and the host launches one NDRange per 256 sources.  Here
 //
-//   ONE launch per call, PERSISTENT: grid = the blocks that are resident at once
-//   (SMs x blocks per SM).  The work -- (target tile) x (source grain) cells,
-//   target-tile-major -- is one linear sequence cut into `gridDim.x` contiguous
-//   runs of equal length, so every block does the same number of pair
-//   evaluations whatever the target count: no tail wave.  A block walks its
-//   run: B threads, each owning T targets held in registers (positions +
-//   per-target attributes) while the block streams source tiles of S packed
-//   records through shared memory, double-buffered with 1-D TMA bulk copies
-//   (cp.async.bulk + mbarrier transaction counts) issued by one thread, so the
-//   math warps spend no issue slots on loads or address arithmetic; the stream
-//   simply continues across target-tile boundaries.
+//   ONE launch per call.  The work -- (target tile) x (source grain) cells, target-tile-major -- is
+//   one linear sequence cut into `gridDim.x` contiguous runs of equal length, gridDim.x = a small
+//   multiple (4) of the blocks that are resident at once: every block does the same number of pair
+//   evaluations whatever the target count, and the hardware block scheduler always has a next run to
+//   hand to an SM whose favoured block has finished (two blocks that share an SM do NOT advance at the
+//   same pace: with exactly one resident set the faster one of each SM was measured to finish after 54 %
+//   of the launch and its partner ran the rest alone, 1.5 - 3 % slower overall).
+//   A block walks its run: B threads, each owning T targets held in registers (positions +
+//   per-target attributes) while the block streams source tiles of S packed records through shared
+//   memory, double-buffered with 1-D TMA bulk copies (cp.async.bulk + mbarrier transaction counts)
+//   issued by one thread, so the math warps spend no issue slots on loads or address arithmetic; the
+//   stream simply continues across target-tile boundaries.
 //   every thread reads the same source record at the same time -> LDS.128
 //   broadcasts, amortised over T targets;
 //   running sums are FP32 per chain (a grain: 256 sources, or 32 for small
@@ -63,6 +64,7 @@ struct M2MArgs {
 	const int *f3d_mode;       // filaments: which fast form (pair_math.cuh f3d_pick_mode), decided while packing
 	PairConsts k;
 	int exact_only;            // 1: always evaluate the guarded pair form (never the optimistic one)
+	unsigned long long *block_times;   // diagnostics (tools/kernel_ab): per block {SM id, start ns, end ns}, or null
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------
@@ -117,7 +119,16 @@ __device__ __noinline__ void exact_subchain(const float *__restrict__ src_raw, l
 	for (int c = 0; c < P::NACC; ++c) sums[c] = acc[c];
 }
 
-template <class P, int T, int B, int MINB>
+// VW: lanes per Vec (pair_math.cuh LANES): 2 = one packed pair at a time, 4 / 8 = two / four packed pairs
+// evaluated stage by stage (more independent instructions in flight, more registers).
+// OPT (bit set): 1 = the FP64 accumulators live in shared memory instead of registers (T x NACC x 2 registers
+// handed back to the pair loop's schedule; one LDS.64 + DADD + STS.64 per sum and chain);
+// 2 = the pair loops are written `#pragma unroll 8` over the chain instead of an explicit 8-wide body.
+enum { M2M_SMEM_ACC = 1, M2M_PLAIN_LOOP = 2 };
+// dynamic shared memory a launch of m2m_kernel<P, T, B, .., OPT> needs (beyond 48 KB in total the launcher has to
+// raise cudaFuncAttributeMaxDynamicSharedMemorySize first)
+template <class P, int T, int B, int OPT> constexpr size_t m2m_smem_bytes() { return (OPT & M2M_SMEM_ACC) ? sizeof(double) * T * P::NACC * B : 0; }
+template <class P, int T, int B, int MINB, int VW = 2, int OPT = 0, int GRAIN = 0>
 __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 {
 	constexpr int S = kSrcTile;
@@ -131,9 +142,11 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 	__shared__ __align__(128) float4 tile[2][NR][S];
 	__shared__ __align__(8) uint64_t full[2];
 	__shared__ int s_ticket;
+	constexpr bool SACC = (OPT & M2M_SMEM_ACC) != 0;
+	extern __shared__ double s_acc[];                                    // SACC: [t][c][thread] (dynamic, m2m_smem_bytes), conflict-free
 
 	const int tid = threadIdx.x;
-	const int G = args.grain;
+	const int G = GRAIN ? GRAIN : args.grain;                            // GRAIN != 0: compile-time chain length
 	const int gps = S / G;                                              // grains per source tile
 	const int gpt = args.n_src_tiles * gps;                             // grains per target tile
 	// this block's run, as (target tile, grain within the tile, grains left): 32-bit state in the loop
@@ -159,13 +172,19 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		if (NR >= 2) bulk_g2s(tile[buf][NR >= 2 ? 1 : 0], args.srcB + off, kTileBytes, &full[buf]);
 		if (NR >= 3) bulk_g2s(tile[buf][NR >= 3 ? 2 : 0], args.srcC + off, kTileBytes, &full[buf]);
 	};
+	if (args.block_times && tid == 0) {
+		unsigned smid; unsigned long long t;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		args.block_times[3 * blockIdx.x] = smid; args.block_times[3 * blockIdx.x + 1] = t;
+	}
 	if (tid == 0 && left > 0) fetch(gs / gps, 0);
 
 	// Two targets share one Vec<2> (packed FP32x2 lanes) when T is even.
-	constexpr int W = (T % 2 == 0) ? 2 : 1;
+	constexpr int W = (T % 2 == 0) ? (T < VW ? T : VW) : 1;
 	constexpr int NV = T / W;
 	Vec<W> tg[NV][P::NTGT];
-	double dacc[T][P::NACC];      // (moving these to shared memory to raise occupancy was measured: no gain)
+	double dacc[SACC ? 1 : T][P::NACC];
 	const bool optimistic = P::OPTIMISTIC && !args.exact_only;
 	int f3d_mode = F3D_REF;
 	if (P::HYBRID) f3d_mode = *args.f3d_mode;
@@ -195,7 +214,10 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 #pragma unroll
 				for (int c = 0; c < P::NTGT; ++c) tg[t / W][c].set(t % W, one[c]);
 #pragma unroll
-				for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
+				for (int c = 0; c < P::NACC; ++c) {
+					if (SACC) s_acc[(t * P::NACC + c) * B + tid] = 0.0;
+					else dacc[t][c] = 0.0;
+				}
 			}
 			// A warp none of whose target slots is real (most of the block in a few-target call) only
 			// keeps the tile hand-over in step.  Only the T = 1 geometry, the one the planner gives
@@ -272,15 +294,26 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 				} else {
 					bool guarded = true;
 					if (P::OPTIMISTIC && optimistic) {
-#pragma unroll 1
-						for (int j = 0; j < G; j += UNROLL) {
-#pragma unroll
-							for (int u = 0; u < UNROLL; ++u) {
-								const float4 a = sA[j0 + j + u];
+						if (OPT & M2M_PLAIN_LOOP) {
+#pragma unroll 8
+							for (int j = 0; j < G; ++j) {
+								const float4 a = sA[j0 + j];
 								float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-								if (NR == 2) b = sB[j0 + j + u];
+								if (NR == 2) b = sB[j0 + j];
 #pragma unroll
 								for (int v = 0; v < NV; ++v) P::template pair<W, false>(tg[v], a, b, acc[v], args.k);
+							}
+						} else {
+#pragma unroll 1
+							for (int j = 0; j < G; j += UNROLL) {
+#pragma unroll
+								for (int u = 0; u < UNROLL; ++u) {
+									const float4 a = sA[j0 + j + u];
+									float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+									if (NR == 2) b = sB[j0 + j + u];
+#pragma unroll
+									for (int v = 0; v < NV; ++v) P::template pair<W, false>(tg[v], a, b, acc[v], args.k);
+								}
 							}
 						}
 						// inf and NaN survive any further addition, so one sum over this thread's running sums
@@ -291,7 +324,9 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 						for (int v = 0; v < NV; ++v)
 #pragma unroll
 							for (int c = (v == 0 ? 1 : 0); c < P::NACC; ++c) chk = vadd(chk, acc[v][c]);
-						const float s = W == 2 ? chk.lane(0) + chk.lane(1) : chk.lane(0);
+						float s = chk.lane(0);
+#pragma unroll
+						for (int l = 1; l < W; ++l) s += chk.lane(l);
 						guarded = !(fabsf(s) <= 3.40282346e38f);
 						if (guarded) {
 #pragma unroll
@@ -301,15 +336,26 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 						}
 					}
 					if (guarded) {
-#pragma unroll 1
-						for (int j = 0; j < G; j += UNROLL) {
-#pragma unroll
-							for (int u = 0; u < UNROLL; ++u) {
-								const float4 a = sA[j0 + j + u];
+						if (OPT & M2M_PLAIN_LOOP) {
+#pragma unroll 8
+							for (int j = 0; j < G; ++j) {
+								const float4 a = sA[j0 + j];
 								float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-								if (NR == 2) b = sB[j0 + j + u];
+								if (NR == 2) b = sB[j0 + j];
 #pragma unroll
 								for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+							}
+						} else {
+#pragma unroll 1
+							for (int j = 0; j < G; j += UNROLL) {
+#pragma unroll
+								for (int u = 0; u < UNROLL; ++u) {
+									const float4 a = sA[j0 + j + u];
+									float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+									if (NR == 2) b = sB[j0 + j + u];
+#pragma unroll
+									for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+								}
 							}
 						}
 					}
@@ -317,7 +363,10 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 #pragma unroll
 				for (int t = 0; t < T; ++t)
 #pragma unroll
-					for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
+					for (int c = 0; c < P::NACC; ++c) {
+						if (SACC) s_acc[(t * P::NACC + c) * B + tid] += (double)acc[t / W][c].lane(t % W);
+						else dacc[t][c] += (double)acc[t / W][c].lane(t % W);
+					}
 			}
 		}
 		__syncthreads();      // everyone is done with tile[buf] before it is refilled two steps on
@@ -328,13 +377,18 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		if (left == 0 || gs == gpt) {
 			// ---- leaving target tile tt: FP64 finish, then final floats or an FP64 piece
 			const long base = (long)tt * (B * T) + tid;
+			auto sums_of = [&](int t, double *d) {                          // this thread's FP64 sums of target slot t
+#pragma unroll
+				for (int c = 0; c < P::NACC; ++c) d[c] = SACC ? s_acc[(t * P::NACC + c) * B + tid] : dacc[SACC ? 0 : t][c];
+			};
 			if (from_start && gs == gpt) {
 #pragma unroll
 				for (int t = 0; t < T; ++t) {
 					const long i = base + (long)t * B;
 					if (i < args.n_tgt) {
-						double res[P::NOUT];
-						P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
+						double res[P::NOUT], d[P::NACC];
+						sums_of(t, d);
+						P::finish(args.tgt + i * P::TCOLS, d, res, args.k);
 #pragma unroll
 						for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)res[c];
 					}
@@ -348,8 +402,9 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 #pragma unroll
 				for (int t = 0; t < T; ++t) {
 					const long i = base + (long)t * B;
-					double res[P::NOUT];
-					if (i < args.n_tgt) P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
+					double res[P::NOUT], d[P::NACC];
+					sums_of(t, d);
+					if (i < args.n_tgt) P::finish(args.tgt + i * P::TCOLS, d, res, args.k);
 					else for (int c = 0; c < P::NOUT; ++c) res[c] = 0.0;
 #pragma unroll
 					for (int c = 0; c < P::NOUT; ++c) __stcg(mine + ((size_t)t * B + tid) * P::NOUT + c, res[c]);
@@ -387,6 +442,11 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 			from_start = true;
 			fresh = true;
 		}
+	}
+	if (args.block_times && tid == 0) {
+		unsigned long long t;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		args.block_times[3 * blockIdx.x + 2] = t;
 	}
 }
 

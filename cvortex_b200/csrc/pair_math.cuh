@@ -76,6 +76,9 @@
 //   LANE_OPS, SFU_OPS   algorithmic FP32 lane-ops / MUFU ops per pair of THIS
 //                       formulation (FMA = 1 lane-op; compares/selects not
 //                       counted) -- the roofline denominators, see DESIGN.md
+//   VW8, OPT8, VW4, OPT4   how m2m_kernel is instantiated for this policy in its two large-problem
+//           geometries (8 targets per thread x 128 threads, 4 x 256): lanes per Vec and the M2M_* option
+//           bits, read off tools/kernel_ab's table (profiles/kernel_ab_r2.txt)
 //   OPTIMISTIC  pair<W, false>() exists and differs from pair<W, true>() (see GUARDS)
 //   HYBRID      filament policies: fast<W, MODE>() + exact() instead of pair<>() (see FILAMENTS)
 //   load_target(row, tg[]), pair<W, G>(tg, a, b, acc, k), finish(row, acc, out, k)
@@ -161,6 +164,18 @@ template <> struct Vec<2> {
 	CVTX_HD void set(int i, float s) { if (i) v.y = s; else v.x = s; }
 };
 
+// W = 4, 8: W/2 packed pairs side by side.  An operation on a Vec<W> is W/2 packed instructions in a row, so a
+// formula written once comes out stage by stage across the pairs -- independent instructions next to each
+// other in the source order.  ptxas schedules around the order it is given: with one pair after the other
+// (W = 2 in a loop over the thread's pairs) it was seen to serialise the Horner chain of the Gaussian g and
+// the rsqrt -> powers chains behind one another ("schedules").
+template <int W> struct Vec {
+	Vec<2> p[W / 2];
+	static constexpr int LANES = W;
+	CVTX_HD float lane(int i) const { return p[i >> 1].lane(i & 1); }
+	CVTX_HD void set(int i, float s) { p[i >> 1].set(i & 1, s); }
+};
+
 template <int W> CVTX_HD Vec<W> bc(float s) {
 	Vec<W> r;
 	for (int i = 0; i < W; ++i) r.set(i, s);
@@ -197,6 +212,12 @@ CVTX_HD Vec<2> vadd(Vec<2> a, Vec<2> b) { Vec<2> r; r.v.x = a.v.x + b.v.x; r.v.y
 CVTX_HD Vec<2> vsub(Vec<2> a, Vec<2> b) { Vec<2> r; r.v.x = a.v.x - b.v.x; r.v.y = a.v.y - b.v.y; return r; }
 #endif
 
+template <int W> CVTX_HD Vec<W> vfma(Vec<W> a, Vec<W> b, Vec<W> c) { Vec<W> r; for (int i = 0; i < W / 2; ++i) r.p[i] = vfma(a.p[i], b.p[i], c.p[i]); return r; }
+template <int W> CVTX_HD Vec<W> vmul(Vec<W> a, Vec<W> b) { Vec<W> r; for (int i = 0; i < W / 2; ++i) r.p[i] = vmul(a.p[i], b.p[i]); return r; }
+template <int W> CVTX_HD Vec<W> vadd(Vec<W> a, Vec<W> b) { Vec<W> r; for (int i = 0; i < W / 2; ++i) r.p[i] = vadd(a.p[i], b.p[i]); return r; }
+template <int W> CVTX_HD Vec<W> vsub(Vec<W> a, Vec<W> b) { Vec<W> r; for (int i = 0; i < W / 2; ++i) r.p[i] = vsub(a.p[i], b.p[i]); return r; }
+template <int W> CVTX_HD Vec<W> vneg(Vec<W> a) { Vec<W> r; for (int i = 0; i < W / 2; ++i) r.p[i] = vneg(a.p[i]); return r; }
+
 // scalar-operand forms (the scalar broadcasts inside the instruction)
 template <int W> CVTX_HD Vec<W> vfma(Vec<W> a, float b, Vec<W> c) { return vfma(a, bc<W>(b), c); }
 template <int W> CVTX_HD Vec<W> vfma(Vec<W> a, Vec<W> b, float c) { return vfma(a, b, bc<W>(c)); }
@@ -230,6 +251,9 @@ template <int W> CVTX_HD Vec<W> pick_if_less(Vec<W> c, float thr, Vec<W> a, Vec<
 	for (int i = 0; i < W; ++i) r.set(i, c.lane(i) < thr ? a.lane(i) : b.lane(i));
 	return r;
 }
+
+// per-regularisation pick for the TUNE constants below: (singular, winckelmans, planetary, gaussian)
+constexpr int by_reg(int reg, int s, int w, int p, int g) { return reg == REG_SINGULAR ? s : (reg == REG_WINCKELMANS ? w : (reg == REG_PLANETARY ? p : g)); }
 
 static constexpr double kPi = 3.14159265359;              // CVTX_PI_F, reference src/P3D.cpp:47 (as a float literal there)
 static constexpr double kSqrt2OverPi = 0.7978845608028654;  // reference src/VortFunc.cpp:49
@@ -374,6 +398,9 @@ template <int REG> struct P3DVel {
 	static constexpr int LANE_OPS = 15 + Reg3D<REG>::A_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // K = inf / NaN meets finite factors: every sum is poisoned
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 8, 2, 8, 2), OPT8 = by_reg(REG, 0, 1, 0, 3);
+	static constexpr int VW4 = by_reg(REG, 2, 2, 4, 2), OPT4 = by_reg(REG, 1, 1, 1, 1);
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
@@ -405,11 +432,14 @@ template <int REG> struct P3DVel {
 // parallel vorticity, and the hoisted sum would cancel catastrophically there.
 // ===========================================================================
 template <int REG> struct P3DDvort {
-	// (singular: 4 targets per thread measured 2 % faster than 8 once the guards left the loop, profiles/sweep_ops_r1b.txt)
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = REG == REG_SINGULAR ? 4 : 8;
+	// (4 targets per thread x 256 threads measured 0.5 - 1.7 % faster than 8 x 128 for all but the Gaussian, profiles/kernel_ab_r2.txt)
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 6, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = REG == REG_GAUSSIAN ? 8 : 4;
 	static constexpr int LANE_OPS = 22 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;      // A = inf / NaN enters all three sums through fma(A, c, .)
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 8, 8, 4, 8), OPT8 = by_reg(REG, 0, 0, 1, 0);
+	static constexpr int VW4 = by_reg(REG, 4, 2, 4, 2), OPT4 = by_reg(REG, 1, 1, 0, 1);
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
@@ -453,6 +483,9 @@ template <int REG> struct P3DVelDvort {
 	static constexpr int LANE_OPS = 31 + Reg3D<REG>::AB_OPS, SFU_OPS = Reg3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg3D<REG>::POISONS;
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 8, 8, 2, 2), OPT8 = by_reg(REG, 3, 3, 1, 1);
+	static constexpr int VW4 = by_reg(REG, 4, 2, 2, 2), OPT4 = by_reg(REG, 1, 1, 3, 1);
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 6; ++i) tg[i] = row[i];
 	}
@@ -513,10 +546,13 @@ template <> struct Eta3D<REG_GAUSSIAN> {      // eta = sqrt(2/pi) exp(-rho^2/2)
 };
 
 template <int REG> struct P3DVisc {
-	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
+	static constexpr int NSRC4 = 2, TCOLS = 7, NTGT = 7, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = REG == REG_GAUSSIAN ? 4 : 8;
 	static constexpr int LANE_OPS = 15 + Eta3D<REG>::OPS, SFU_OPS = Eta3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = false;      // eta(0) is finite: the coincident-pair test is a real selection
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 2, 8, 2, 2), OPT8 = by_reg(REG, 0, 1, 0, 1);
+	static constexpr int VW4 = by_reg(REG, 2, 2, 2, 2), OPT4 = by_reg(REG, 0, 1, 0, 1);
 	CVTX_HD static void load_target(const float *row, float *tg) {
 		for (int i = 0; i < 7; ++i) tg[i] = row[i];
 	}
@@ -582,6 +618,9 @@ template <int REG> struct P3DVort {
 	static constexpr int LANE_OPS = 9 + Zeta3D<REG>::OPS, SFU_OPS = Zeta3D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = false;      // the box cutoff selects between finite values
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 2, 2, 8, 4), OPT8 = by_reg(REG, 0, 1, 0, 0);
+	static constexpr int VW4 = by_reg(REG, 2, 2, 2, 4), OPT4 = by_reg(REG, 0, 1, 1, 1);
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4 b, Vec<W> *acc, const PairConsts &k) {
 		const Rad3<W> d = rad3(tg, a);
@@ -657,6 +696,9 @@ template <int REG> struct P2DVel {
 	static constexpr int LANE_OPS = 7 + Reg2D<REG>::OPS, SFU_OPS = Reg2D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = Reg2D<REG>::POISONS;
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 2, 8, 4, 2), OPT8 = by_reg(REG, 0, 2, 1, 2);
+	static constexpr int VW4 = by_reg(REG, 4, 2, 2, 2), OPT4 = by_reg(REG, 3, 1, 1, 0);
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
@@ -699,10 +741,13 @@ template <> struct Eta2D<REG_GAUSSIAN> {      // eta = exp(-rho^2/2), src/VortFu
 };
 
 template <int REG> struct P2DVisc {
-	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 2 : 8;
+	static constexpr int NSRC4 = 1, TCOLS = 4, NTGT = 4, NACC = 1, NOUT = 1, CHAIN = 0, PREF_T = REG == REG_WINCKELMANS ? 4 : 8;
 	static constexpr int LANE_OPS = 7 + Eta2D<REG>::OPS, SFU_OPS = Eta2D<REG>::SFU;
 	static constexpr bool OPTIMISTIC = false;      // eta(0) is finite
 	static constexpr bool HYBRID = false;
+	// TUNE (profiles/kernel_ab_r2.txt): lanes per Vec and M2M_* option bits of the 8 x 128 and 4 x 256 geometries
+	static constexpr int VW8 = by_reg(REG, 2, 8, 2, 2), OPT8 = by_reg(REG, 0, 0, 0, 0);
+	static constexpr int VW4 = by_reg(REG, 2, 2, 2, 2), OPT4 = by_reg(REG, 0, 0, 0, 1);
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; tg[3] = row[3]; }
 	template <int W, bool G = true> CVTX_HD static void pair(const Vec<W> *tg, const f4 a, const f4, Vec<W> *acc, const PairConsts &k) {
 		const Vec<W> dx = vsub(tg[0], a.x), dy = vsub(tg[1], a.y);
@@ -857,6 +902,7 @@ struct F3DVel {
 	static constexpr int NSRC4 = 3, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 34, SFU_OPS = 3;           // of fast<W, F3D_NEW>; the F3D_REF form: 44 / 3
 	static constexpr bool OPTIMISTIC = false, HYBRID = true;
+	static constexpr int VW8 = 2, OPT8 = 0, VW4 = 2, OPT4 = 0;      // TUNE: vector width / kernel options per geometry (m2m_kernel.cuh), measured
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 
 	template <int W, int MODE> CVTX_HD static void fast(const Vec<W> *tg, const f4 a, const f4 b, const f4 c, Vec<W> *acc,
@@ -937,6 +983,7 @@ struct F3DDvort {
 	static constexpr int NSRC4 = 3, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 8;
 	static constexpr int LANE_OPS = 41, SFU_OPS = 4;           // of fast<W, F3D_NEW>; the F3D_REF form: 46 / 3
 	static constexpr bool OPTIMISTIC = false, HYBRID = true;
+	static constexpr int VW8 = 2, OPT8 = 0, VW4 = 2, OPT4 = 0;      // TUNE: vector width / kernel options per geometry (m2m_kernel.cuh), measured
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 
 	template <int W, int MODE> CVTX_HD static void fast(const Vec<W> *tg, const f4 a, const f4 b, const f4 c, Vec<W> *acc,

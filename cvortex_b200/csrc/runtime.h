@@ -54,11 +54,29 @@ int device_stream(int device, cudaStream_t *stream);
 
 // Run (op, reg) with n_src source rows in host_stage().src and n_tgt target
 // rows in host_stage().tgt.  Targets are split into contiguous shards over
-// `devices` (every device gets the full source set); each shard's result lands
-// in host_stage().out and is copied to `out`.  Synchronous.  Caller holds
-// host_stage().mu.
+// `devices`; the sources are uploaded ONCE in total -- device g receives rows
+// [g n / G, (g + 1) n / G) -- and all-gathered between the devices
+// (all_gather_rows); each shard's result lands in host_stage().out and is
+// copied to `out`.  Synchronous.  Caller holds host_stage().mu.
 int run_staged(int op, int reg, const std::vector<int> &devices, int n_src, int n_tgt,
                float *out, float sigma, float nu, size_t *h2d_bytes, size_t *d2h_bytes);
+
+// exchange.cu: the all-gather of raw source rows over NCCL / NVLink (see there).
+int all_gather_rows(const std::vector<int> &devices, const std::vector<cudaStream_t> &streams,
+                    const std::vector<const void *> &shard, const std::vector<long> &row_off,
+                    const std::vector<void *> &full, size_t row_bytes);
+void release_exchange();
+
+// Restores the calling thread's current device when it goes out of scope: every entry point
+// switches devices, and a host application that shares the thread with its own CUDA or torch
+// code must not find itself on another GPU afterwards.
+struct DeviceGuard {
+	int prev = -1;
+	DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+	~DeviceGuard() { int cur = -1; if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); }
+	DeviceGuard(const DeviceGuard &) = delete;
+	DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 }  // namespace cvtx
 

@@ -53,6 +53,9 @@ class DeviceBackend:
         lib.cvtx_b200_m2m.argtypes = [i, i, i, vp, vp, i, vp, i, vp, f, f]
         lib.cvtx_b200_m2m_host.restype = i
         lib.cvtx_b200_m2m_host.argtypes = [i, i, i, vp, i, vp, i, vp, f, f, C.POINTER(sz), C.POINTER(sz)]
+        lib.cvtx_b200_m2m_sharded.restype = i
+        lib.cvtx_b200_m2m_sharded.argtypes = [i, i, i, ip, C.POINTER(vp), ip, C.POINTER(vp), ip, C.POINTER(vp), f, f]
+        lib.cvtx_b200_exchange_backend.restype = C.c_char_p
         lib.cvtx_b200_f3d_inf_mtrx.restype = i
         lib.cvtx_b200_f3d_inf_mtrx.argtypes = [i, vp, vp, i, vp, vp, i, vp]
         lib.cvtx_b200_redistribute.restype = i
@@ -155,6 +158,23 @@ class DeviceBackend:
                                     _ptr(tgt), n_tgt, _ptr(out), sigma, nu)
         if rc:
             raise BackendError(f"cvtx_b200_m2m({op}, {reg}) failed ({rc}): {self.last_error()}")
+
+    def m2m_sharded(self, op: str, reg: str, devices, src_shards, n_src_shard, tgts, n_tgt, outs,
+                    sigma: float = 1.0, nu: float = 0.0) -> None:
+        """Several devices from this one process, sources sharded (see cvtx_b200_m2m_sharded): lists of
+        per-device source shards, targets and outputs (device pointers / tensors on devices[g]).  The shards
+        are all-gathered over NCCL inside the library; returns when every device has finished."""
+        G = len(devices)
+        ia = lambda v: (C.c_int * G)(*[int(x) for x in v])
+        pa = lambda v: (C.c_void_p * G)(*[_ptr(x) for x in v])
+        rc = self.lib.cvtx_b200_m2m_sharded(OPS[op], REGS[reg], G, ia(devices), pa(src_shards), ia(n_src_shard),
+                                            pa(tgts), ia(n_tgt), pa(outs), sigma, nu)
+        if rc:
+            raise BackendError(f"cvtx_b200_m2m_sharded({op}, {reg}) failed ({rc}): {self.last_error()}")
+
+    def exchange_backend(self) -> str:
+        """How source shards travel between devices in this process ("nccl 2.x.y, ..." / "peer-to-peer copies ...")."""
+        return (self.lib.cvtx_b200_exchange_backend() or b"").decode()
 
     def f3d_inf_mtrx(self, device: int, stream, fil, n_fil: int, mes, dirs, n_mes: int, out) -> None:
         """Asynchronous dense influence matrix on device pointers (see cvtx_b200_f3d_inf_mtrx)."""

@@ -106,6 +106,24 @@ CVTX_B200_API int cvtx_b200_m2m_host(int op, int reg, int device,
                        float *out, float sigma, float nu,
                        size_t *h2d_bytes, size_t *d2h_bytes);
 
+/* Several devices, everything resident, SOURCES SHARDED (BASELINE north_star: "via NCCL all-gather
+ * over NVLink when sources arrive sharded").  Device devices[g] holds n_src_shard[g] source
+ * rows at src_shard_dev[g] and n_tgt[g] target rows at tgt_dev[g], and receives out_dev[g]; the source
+ * set of the call is the concatenation of the shards in list order.  The shards are all-gathered between
+ * the devices -- ncclCommInitAll over the list (re-created when the list changes), one grouped
+ * ncclBroadcast per shard, so unequal shards need no padding -- and every device then runs the
+ * unchanged pair kernel on its own targets.  Results are bit-identical to cvtx_b200_m2m on one device
+ * with the concatenated sources.  The caller's buffers must be complete before the call (it runs on the
+ * library's own per-device streams) and the call returns when every device has finished.  The reference
+ * has no counterpart: its accelerated path uses one device (README.md:149-150). */
+CVTX_B200_API int cvtx_b200_m2m_sharded(int op, int reg, int n_devices, const int *devices,
+                                        const float *const *src_shard_dev, const int *n_src_shard,
+                                        const float *const *tgt_dev, const int *n_tgt,
+                                        float *const *out_dev, float sigma, float nu);
+/* How source shards travel between devices in this process: "nccl 2.x.y, ..." or "peer-to-peer copies ..."
+ * (libnccl.so.2 is opened at run time; CVTX_B200_EXCHANGE=peer switches it off).  Library-owned string. */
+CVTX_B200_API const char *cvtx_b200_exchange_backend(void);
+
 /* cvtx_F3D_inf_mtrx on device pointers (libcvtx.h:299-305; CPU-only in the reference,
  * src/F3D.cpp:204-227): out_dev[i * n_fil + j] = u_j(mes_i) . dir_i for n_fil filament rows
  * (7 floats) and n_mes points / directions (3 floats each).  Asynchronous on `stream`. */

@@ -61,6 +61,15 @@ def gpu(product):
     return product, dev
 
 
+@pytest.fixture(scope="module")
+def torch_cuda():
+    """torch with a live CUDA device 0 current (device memory and streams for the thin-ABI tests)."""
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
 @pytest.fixture(scope="session")
 def hostcheck():
     """tests/hostcheck: the device pair arithmetic compiled for the host (test-only)."""

@@ -9,14 +9,6 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def torch_cuda():
-    import torch
-    assert torch.cuda.is_available()
-    torch.cuda.set_device(0)
-    return torch
-
-
 def test_m2m_host_matches_oracle_and_counts_bytes(gpu, oracle):
     _, dev = gpu
     rng = np.random.default_rng(1)

@@ -39,3 +39,43 @@ def test_targets_shard_over_enabled_accelerators(gpu, oracle):
             lib.accelerator_disable(k)
     dv0 = lib.P3D_M2M_dvort(P, P[:m], "gaussian", 0.02)
     assert np.array_equal(dv0, dv1)
+
+
+def test_sharded_sources_are_all_gathered_inside_the_library(gpu, oracle, torch_cuda):
+    """cvtx_b200_m2m_sharded through the thin C ABI: device-resident source shards of UNEQUAL length, one
+    per device, gathered over NCCL inside the library (BASELINE north_star), targets sharded too; every
+    device must return the bits a single device computes from the concatenated sources.  With one GPU the
+    same entry point runs with a single shard."""
+    torch = torch_cuda
+    lib, dev = gpu
+    G = min(dev.device_count(), 8)
+    rng = np.random.default_rng(21)
+    n, m = 70_001, 9_000
+    P = particles3d(rng, n, vol=0.01)
+    T = np.ascontiguousarray(P[:m])
+    for op, reg in (("P3D_M2M_dvort", "gaussian"), ("P3D_M2M_visc_dvort", "winckelmans")):
+        src0, tgt0 = torch.from_numpy(P).to("cuda:0"), torch.from_numpy(T).to("cuda:0")
+        want = torch.empty((m, 3), device="cuda:0")
+        dev.m2m(op, reg, 0, torch.cuda.current_stream(0).cuda_stream, src0, n, tgt0, m, want, 0.02, 1.0)
+        torch.cuda.synchronize(0)
+        want = want.cpu().numpy()
+        idx = np.arange(0, m, 45)
+        assert rel_l2(want[idx], oracle.m2m(op, P, np.ascontiguousarray(T[idx]), reg, 0.02, 1.0)) <= 1e-5
+        # unequal shards: the first device holds about half of the sources, the rest share the remainder
+        cuts = [0] + [int(n * (0.5 + 0.5 * g / max(G - 1, 1))) for g in range(G - 1)] + [n] if G > 1 else [0, n]
+        tcut = [m * g // G for g in range(G + 1)]
+        shards = [torch.from_numpy(np.ascontiguousarray(P[cuts[g]:cuts[g + 1]])).to(f"cuda:{g}") for g in range(G)]
+        tgts = [torch.from_numpy(np.ascontiguousarray(T[tcut[g]:tcut[g + 1]])).to(f"cuda:{g}") for g in range(G)]
+        outs = [torch.empty((tcut[g + 1] - tcut[g], 3), device=f"cuda:{g}") for g in range(G)]
+        for g in range(G):
+            torch.cuda.synchronize(g)
+        before = torch.cuda.current_device()
+        dev.m2m_sharded(op, reg, list(range(G)), shards, [cuts[g + 1] - cuts[g] for g in range(G)],
+                        tgts, [tcut[g + 1] - tcut[g] for g in range(G)], outs, 0.02, 1.0)
+        assert torch.cuda.current_device() == before, "the library left the calling thread on another device"
+        got = np.concatenate([o.cpu().numpy() for o in outs])
+        assert np.array_equal(got, want), (op, reg, G)
+    backend = dev.exchange_backend()
+    print(f"{G} device(s); exchange backend: {backend}")
+    if G > 1:
+        assert "nccl" in backend or "peer" in backend

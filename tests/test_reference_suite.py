@@ -44,22 +44,23 @@ def test_reference_test_program_passes_on_the_host_path(product):
     assert sections == {"Accelerators": (2, 2), "VortFunc": (24, 24), "Particle": (31, 31)}
 
 
-# Ops whose sums cancel per target (stretching with the Gaussian's g = erf - ..., PSE exchange with random
-# strengths, filament formulas): there the per-target maximum over 1000 targets is decided by the one
-# target whose result is ~100x smaller than its terms, where the FP32 reference itself is 1e-5 .. 4e-4
-# from FP64 (measured) and only an op-for-op copy of its arithmetic could track
-# its rounding.  The mean per-target error of these ops is 1e-7 .. 6e-7 and their array-level relative
-# L2 error (the north-star metric) is <= 2e-6 (tests/test_gpu_parity.py).
-CANCELLING = ("F3D M2M vel", "F3D M2M dvort", "P2D M2M visc dvort gaussian", "P2D M2M visc dvort winckelmans",
-              "P3D M2M dvort gaussian")
+# Ops with cancellation -- stretching with the Gaussian's g = erf - ..., PSE exchange with random strengths, the
+# filament formulas: the reference's per-target criterion rejects a handful of the 1000 targets of a repeat, the
+# ones where the FP32 reference is itself far from FP64.  The counts are pinned per op group (they are
+# deterministic for a given build: same inputs, same arithmetic), so a regression in any of these ops shows up
+# here; WHY those targets are rejected is asserted target by target in
+# test_rejected_targets_are_where_fp32_is_lost below (host build of the kernel arithmetic on CPU boxes, the
+# CUDA path on GPU boxes).
+FAILURE_LIMITS = {"P3D M2M dvort gaussian": 6, "P2D M2M visc dvort": 16, "F3D M2M": 16}
 
 
 @pytest.mark.gpu
 def test_reference_acceptance_test_on_the_gpu(gpu):
     """The reference's own GPU-vs-CPU sections really run on the B200 path (420 tests, not 57).
-    Every velocity test (P3D and P2D, all four regularisations) and every singular / Winckelmans /
-    planetary stretching test must pass the reference's per-target 1e-5 criterion in all 10 repeats of
-    both sections; failures are tolerated only for the cancelling ops named above."""
+    Every velocity test (P3D and P2D, all four regularisations), every P3D viscous test and every singular /
+    Winckelmans / planetary stretching test must pass the reference's per-target 1e-5 criterion in all 10
+    repeats of both sections; the three groups of cancelling ops may fail at most as often as pinned above
+    (the round-1 kernel: 6 / 16 / 20)."""
     lib, _ = gpu
     if not _build_if_possible():
         pytest.skip("oracle/_ref/all_tests_b200 not built (needs /root/reference at build time)")
@@ -73,6 +74,88 @@ def test_reference_acceptance_test_on_the_gpu(gpu):
     for name in ("Accelerators", "VortFunc", "Particle"):
         assert sections[name][0] == sections[name][1], (name, sections[name])
     names = re.findall(r"Test failed:\n\t(.*?)\n", out)
-    stray = sorted({n for n in names if not n.startswith(CANCELLING)})
-    assert not stray, f"non-cancelling ops failed the reference's per-target test: {stray}"
-    assert passed >= 360, out[-2000:]
+    counts = {k: sum(1 for n in names if n.startswith(k)) for k in FAILURE_LIMITS}
+    stray = sorted({n for n in names if not n.startswith(tuple(FAILURE_LIMITS))})
+    print("failures per group:", counts)
+    assert not stray, f"ops outside the cancelling groups failed the reference's per-target test: {stray}"
+    for k, limit in FAILURE_LIMITS.items():
+        assert counts[k] <= limit, (k, counts[k], limit)
+    assert failed == sum(counts.values())
+
+
+# ---- the same recipe in Python, target by target, against the FP64 oracle ------------------------------------
+CANCELLING_OPS = [("P3D_M2M_dvort", "gaussian"), ("P2D_M2M_visc_dvort", "gaussian"), ("P2D_M2M_visc_dvort", "winckelmans"),
+                  ("F3D_M2M_vel", "singular"), ("F3D_M2M_dvort", "singular")]
+
+
+def _rejected_target_evidence(run, oracle, repeats=10):
+    """The reference's "Many particles" recipe (its generator, its arithmetic, sigma 0.3, nu 0.1, N = 1000,
+    reference test/testsamecpugpuresultmany.h:37-46,68-88) for the five cancelling ops; `run(op, reg, src, tgt)`
+    is the implementation under test.  Rounding errors of two FP32 evaluations are independent, so no
+    per-target factor holds between them (on 15 % of the rejected targets one is several times further from
+    FP64 than the other, either way round); what must hold, and is asserted, is
+      * the criterion rejects at most 0.5 % of the targets of an op,
+      * on the rejected targets the implementation is, in the RMS, no further from FP64 than twice the
+        reference's own distance -- the targets are rejected because FP32 is lost there, not because of us,
+      * over ALL targets the tail of the implementation's per-target error distribution (99.9th percentile
+        of |x - f64| / |f64|) is within a factor two of the reference's tail,
+      * and the array-level relative L2 error against the reference (the north-star metric) is <= 1e-5, or
+        -- a repeat whose output is dominated by one pair at rho ~ 0.1, where g = erf - ... cancels to 1e-4 of
+        its terms in BOTH implementations, and filaments with both ends anywhere in the box -- the
+        implementation is within 3x of the reference's own distance from FP64 (two independent draws of the
+        same rounding noise: the host build of this arithmetic with libm's exp is 2.4x off in one repeat and
+        0.5x in others)."""
+    import numpy as np
+    from util import UpstreamRand, rel_l2, upstream_many_inputs, upstream_per_target_rejected
+    gen = UpstreamRand()
+    pool = {k: {"eg": [], "er": [], "rej": [], "l2": []} for k in CANCELLING_OPS}
+    for _ in range(repeats):
+        P, F, P2 = upstream_many_inputs(gen)
+        X = np.ascontiguousarray(P[:, :3])
+        for op, reg in CANCELLING_OPS:
+            src = P2 if op.startswith("P2D") else (F if op.startswith("F3D") else P)
+            tgt = P2 if op.startswith("P2D") else (X if op == "F3D_M2M_vel" else P)
+            got = np.asarray(run(op, reg, src, tgt), np.float64).reshape(len(tgt), -1)
+            ref = np.asarray(oracle.m2m(op, src, tgt, reg, 0.3, 0.1), np.float64).reshape(len(tgt), -1)
+            f64 = np.asarray(oracle.m2m(op, src, tgt, reg, 0.3, 0.1, f64=True), np.float64).reshape(len(tgt), -1)
+            nf = np.linalg.norm(f64, axis=1)
+            q = pool[(op, reg)]
+            q["eg"].append(np.linalg.norm(got - f64, axis=1) / nf)
+            q["er"].append(np.linalg.norm(ref - f64, axis=1) / nf)
+            q["rej"].append(upstream_per_target_rejected(got, ref))
+            q["l2"].append((rel_l2(got, ref), rel_l2(got, f64), rel_l2(ref, f64)))
+    for (op, reg), q in pool.items():
+        eg, er, rej = np.concatenate(q["eg"]), np.concatenate(q["er"]), np.concatenate(q["rej"])
+        n_rej = int(rej.sum())
+        rms = lambda v: float(np.sqrt(np.mean(v ** 2))) if len(v) else 0.0
+        tail_g, tail_r = float(np.quantile(eg, 0.999)), float(np.quantile(er, 0.999))
+        print(f"{op}/{reg}: {n_rej} of {len(rej)} targets rejected in {sum(int(r.any()) for r in q['rej'])} of {repeats} repeats; "
+              f"on them RMS |x-f64|/|f64|: ours {rms(eg[rej]):.2e}, reference {rms(er[rej]):.2e}; "
+              f"99.9th percentile over all targets: ours {tail_g:.2e}, reference {tail_r:.2e}; "
+              f"worst array-level rel-L2 vs reference {max(l[0] for l in q['l2']):.2e}")
+        assert n_rej <= 0.005 * len(rej), (op, reg, n_rej)
+        if n_rej:
+            assert rms(eg[rej]) <= 2.0 * rms(er[rej]), (op, reg, rms(eg[rej]), rms(er[rej]))
+        assert tail_g <= 2.0 * tail_r + 1e-7, (op, reg, tail_g, tail_r)
+        for e_par, e_gpu, e_ref in q["l2"]:
+            assert e_par <= 1e-5 or e_gpu <= 3.0 * e_ref + 1e-6, (op, reg, e_par, e_gpu, e_ref)
+
+
+def test_rejected_targets_are_where_fp32_is_lost_host_arithmetic(hostcheck, oracle):
+    """The evidence on a CPU box: the kernel's pair arithmetic compiled for the host (MUFU -> libm)."""
+    import numpy as np
+    from test_pair_math_host import run as host_run
+    _rejected_target_evidence(lambda op, reg, src, tgt: host_run(hostcheck, op, reg, src, np.ascontiguousarray(tgt), 0.3, 0.1), oracle)
+
+
+@pytest.mark.gpu
+def test_rejected_targets_are_where_fp32_is_lost(gpu, oracle):
+    """The evidence on the B200, through the unchanged C ABI."""
+    from util import call_abi
+    lib, dev = gpu
+
+    def run(op, reg, src, tgt):
+        out = call_abi(lib, op, src, tgt, reg, 0.3, 0.1)
+        assert dev.last_dispatch() == 1
+        return out
+    _rejected_target_evidence(run, oracle)

@@ -35,6 +35,50 @@ def upstream_per_target_ok(a, b, rel_acc=1e-5) -> bool:
     return bool(np.all(m[sel] / p[sel] <= rel_acc))
 
 
+def upstream_per_target_rejected(a, b, rel_acc=1e-5):
+    """Mask of the targets the reference's criterion rejects (see upstream_per_target_ok)."""
+    a = np.asarray(a, dtype=np.float64).reshape(len(a), -1)
+    b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
+    m = np.linalg.norm(a - b, axis=1)
+    p = np.linalg.norm(a + b, axis=1)
+    return (p > 2e-35) & (m > rel_acc * p)
+
+
+class UpstreamRand:
+    """The reference test program's own generator (reference test/testmain.c:87-92): MSVC's LCG on a
+    32-bit int seeded with 0xF0F0F0F0, bits 16..30, modulo RAND_MAX -- with the author's RAND_MAX of
+    32767 (oracle/rand_max_msvc.h)."""
+
+    def __init__(self, seed=0xF0F0F0F0):
+        self.v = seed & 0xFFFFFFFF
+
+    def mrand(self):
+        self.v = (self.v * 214013 + 2531011) & 0xFFFFFFFF
+        signed = self.v - (1 << 32) if self.v >= (1 << 31) else self.v
+        return ((signed >> 16) & 0x7FFF) % 32767
+
+    def ints(self, n):
+        return np.array([self.mrand() for _ in range(n)], dtype=np.float32)
+
+
+def upstream_many_inputs(gen, n=1000, max_float=10.0):
+    """One repeat of the reference's "Many particles with vorticity" inputs, in its order and with its
+    arithmetic (reference test/testsamecpugpuresultmany.h:68-88, :335-341): `(float)mrand() /
+    (float)(RAND_MAX / max_float)` for coordinates and strengths, `(float)mrand() / (float)(RAND_MAX /
+    0.01)` for volumes / areas; particles, then filaments with both ends anywhere in the box, then 2-D
+    particles.  The measurement points of the recipe are the particle positions."""
+    d = np.float32(32767.0) / np.float32(max_float)          # int / float: single precision
+    dv = np.float32(32767.0 / 0.01)                           # int / double, then the cast
+    P = gen.ints(n * 7).reshape(n, 7)
+    P[:, :6] /= d
+    P[:, 6] /= dv
+    F = gen.ints(n * 7).reshape(n, 7) / d
+    P2 = gen.ints(n * 4).reshape(n, 4)
+    P2[:, :3] /= d
+    P2[:, 3] /= dv
+    return np.ascontiguousarray(P), np.ascontiguousarray(F.astype(np.float32)), np.ascontiguousarray(P2)
+
+
 def particles3d(rng, n, box=10.0, vol=None):
     """cvtx_P3D rows as the reference's benchmark / tests build them: coords and vorticity
     uniform in [0, box), volume 0.01 (bench/bencharraysetup.c:43-58) or uniform [0, 0.01)

@@ -60,7 +60,7 @@ def loop_table(text):
 	dem = subprocess.run(["c++filt"], input="\n".join(n for n, _ in fns), capture_output=True, text=True).stdout.splitlines()
 	rows = []
 	for (name, body), d in zip(fns, dem):
-		m = re.search(r"m2m_kernel<cvtx::(\w+(?:<\d+>)?), (\d+), (\d+), (\d+)>", d)
+		m = re.search(r"m2m_kernel<cvtx::(\w+(?:<\d+>)?), (\d+), (\d+), (\d+)[,>]", d)
 		if not m:
 			continue
 		pol, T = m.group(1), int(m.group(2))
