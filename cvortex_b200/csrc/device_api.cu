@@ -17,7 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include "../../include/cvtx_b200.h"
-#include "m2m_kernel.cuh"
+#include "aux_kernels.cuh"
+#include "kernel_table.h"
 #include "runtime.h"
 
 using namespace cvtx;
@@ -94,9 +95,6 @@ int ensure_ready(Device *d) {                   // caller holds d->mu and has do
 }
 
 // ---- launch planning ----------------------------------------------------------
-// One compiled geometry of the pair kernel for one policy: what the planner needs to know about it.
-struct KernelChoice { const void *fn; int T, B; size_t smem; int occ; };
-
 // Source sets below this many tiles are walked in grains (= FP32 chains) of 32 sources instead of
 // 256, so that a 10k x 10k call still cuts into enough equal runs for every resident block.  A
 // property of the SOURCES alone: every shard of a multi-GPU call rounds alike.
@@ -108,42 +106,20 @@ constexpr int kSmallSourceTiles = 64;
 // has to have a next run to hand out.  Runs stay equal; 3 ... 8 measured the same, 16 worse.
 constexpr int kRunsPerSlot = 4;
 constexpr int kMinRunGrains = 24;
-
-// The kernel (function pointer, dynamic shared memory, blocks per SM) of policy P in geometry V
-// (0: T=8 B=128, 1: T=4 B=256, 2: T=2 B=256, 3: T=1 B=128) for chain length `grain`.  The two
-// large-problem geometries exist with the chain length as a compile-time 256 (the form ptxas
-// schedules best) and as a run-time value for small source sets; vector width
-// and accumulator placement are the policy's measured TUNE_* constants.
-template <class P, int T, int B, int MINB, int VW, int OPT, int GRAIN>
-KernelChoice choice_of(int device) {
-	auto kern = m2m_kernel<P, T, B, MINB, VW, OPT, GRAIN>;
-	static int occ_cache[64];                          // per device: the attribute below is per device too
-	const size_t smem = m2m_smem_bytes<P, T, B, OPT>();
-	int &occ = occ_cache[device & 63];
-	if (occ == 0) {
-		if (smem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		int o = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, B, smem) != cudaSuccess || o < 1) { cudaGetLastError(); o = MINB; }
-		occ = o;
-	}
-	KernelChoice c = {(const void *)kern, T, B, smem, occ};
-	return c;
-}
-template <class P> KernelChoice choice(int v, bool grain256, int device) {
-	if (v == 0) return grain256 ? choice_of<P, 8, 128, 2, P::VW8, P::OPT8, 256>(device) : choice_of<P, 8, 128, 2, P::VW8, P::OPT8, 0>(device);
-	if (v == 1) return grain256 ? choice_of<P, 4, 256, 2, P::VW4, P::OPT4, 256>(device) : choice_of<P, 4, 256, 2, P::VW4, P::OPT4, 0>(device);
-	if (v == 2) return choice_of<P, 2, 256, 3, 2, 0, 0>(device);
-	return choice_of<P, 1, 128, 8, 1, 0, 0>(device);
-}
+constexpr int kInKernelFinishPieces = 48;
 
 struct Plan { KernelChoice k; int grain, grid; long long tiles_t, total_grains; };
 
 // Pick the block geometry (targets per thread) and the grid.  The work -- (target tile) x (grain) cells
-// -- is cut into `grid` equal runs; a launch costs (grains per run) x (slots per grain) x (waves of runs)
-// / (the geometry's measured relative efficiency): for large problems that is the op's preferred
-// geometry, for small ones it trades the padding of the last target tile against parallelism.
+// -- is cut into `grid` equal runs.  Every (geometry, grid) candidate is priced in microseconds:
+//   waves x ( prologue + pairs of a run / what a block gets of its SM )  +  the ordered finish of cut tiles
+// where a block's share of the SM depends on how many blocks are resident with it (4 warps alone keep the
+// FP32 pipe ~60 % busy, 8 and more 100 %) and a single resident set of co-resident blocks pays for the
+// uneven pace of the two (+30 %: the slower one finishes alone).  Large problems come out at the op's
+// preferred geometry with kRunsPerSlot runs per resident slot; small ones (10k x 10k: 100 us) at ONE run per
+// SM in a small-tile geometry, which is what an exhaustive sweep finds too (profiles/plan_sweep_r2.txt).
 struct Planner {
-	int device, n_src, n_tgt, sm_count; Plan plan;
+	int device, n_src, n_tgt, sm_count, op, reg; Plan plan;
 	template <class P> void run() {
 		const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
 		static const double cand_eff[4] = {1.0, 0.985, 0.96, 0.79};      // profiles/sweep_ops_r1.txt, ubench_r1.txt
@@ -151,10 +127,12 @@ struct Planner {
 		const int pref = P::PREF_T;
 		const int first = pref >= 8 ? 0 : (pref >= 4 ? 1 : (pref >= 2 ? 2 : 3));
 		const int grain = n_src_tiles < kSmallSourceTiles ? 32 : kSrcTile;
+		// pairs per microsecond one SM sustains on this op at 85 % of its FP32 issue rate (1.965 GHz x 128 lanes)
+		const double sm_rate = 0.85 * 128.0 * 1965.0 / (double)P::LANE_OPS;
 		double best = 1e300;
 		plan = Plan();
 		for (int v = 0; v < 4; ++v) {
-			const KernelChoice k = choice<P>(v, grain == kSrcTile, device);
+			const KernelChoice k = kernel_choice(op, reg, v, grain == kSrcTile, device);
 			if (fT ? k.T != fT : v < first) continue;
 			const long long slots = (long long)k.B * k.T;
 			const long long tiles_t = ((long long)n_tgt + slots - 1) / slots;
@@ -162,18 +140,28 @@ struct Planner {
 			const long long resident = (long long)sm_count * k.occ;
 			long long mult = total / (resident * kMinRunGrains);
 			mult = mult < 1 ? 1 : (mult > kRunsPerSlot ? kRunsPerSlot : mult);
-			long long grid = resident * mult;
-			if (fG > 0) grid = fG;
-			if (grid > total) grid = total;
-			if (grid < 1) grid = 1;
-			const long long per_block = (total + grid - 1) / grid;
-			const long long waves = (grid + resident - 1) / resident;
-			const long long sharing = grid < resident ? (grid + sm_count - 1) / sm_count : k.occ;
-			const double cost = (double)per_block * (double)waves * grain * (double)slots * (double)sharing / cand_eff[v]
-			                    + 4000.0 * (double)waves * (double)slots / 128.0;         // per-block prologue, ~1 us
-			if (cost < best) {
-				best = cost;
-				plan.k = k; plan.grain = grain; plan.grid = (int)grid; plan.tiles_t = tiles_t; plan.total_grains = total;
+			const long long cand_grid[3] = {resident * mult, (long long)sm_count, 2LL * sm_count};
+			for (int gi = 0; gi < 3; ++gi) {
+				long long grid = cand_grid[gi];
+				if (fG > 0) grid = fG;
+				if (grid > total) grid = total;
+				if (grid < 1) grid = 1;
+				if (gi > 0 && (fG > 0 || grid >= cand_grid[0])) continue;
+				const long long per_block = (total + grid - 1) / grid;
+				const long long waves = (grid + resident - 1) / resident;
+				long long together = (grid + sm_count - 1) / sm_count;              // blocks that share an SM
+				if (together > k.occ) together = k.occ;
+				const double warps = (double)together * k.B / 32.0;
+				const double util = warps >= 8.0 ? 1.0 : (warps >= 4.0 ? 0.6 + 0.1 * (warps - 4.0) : 0.15 * warps);
+				const double uneven = (together >= 2 && waves == 1) ? 1.3 : 1.0;
+				const double run_us = (double)per_block * grain * (double)slots * (double)together * uneven / (sm_rate * cand_eff[v] * util);
+				const double pieces = (double)(grid + tiles_t - 1) / (double)tiles_t;      // runs that touch a cut tile
+				const double finish_us = grid <= tiles_t ? 0.0 : (pieces > kInKernelFinishPieces ? 12.0 : 2.0 + 0.4 * pieces);
+				const double cost = (double)waves * (3.0 + run_us) + finish_us;
+				if (cost < best) {
+					best = cost;
+					plan.k = k; plan.grain = grain; plan.grid = (int)grid; plan.tiles_t = tiles_t; plan.total_grains = total;
+				}
 			}
 		}
 	}
@@ -330,7 +318,7 @@ int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tp
 	Info q = {};
 	if (!d || n_src < 0 || n_tgt < 0) return fail(CVTX_B200_ERR_ARGUMENT, "bad device or counts");
 	if (!dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, q)) return fail(CVTX_B200_ERR_UNSUPPORTED, "bad op");
-	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, {}};
+	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, op, op_is_filament(op) ? 0 : REG_WINCKELMANS, {}};
 	{
 		DeviceGuard restore;
 		std::lock_guard<std::mutex> lk(d->mu);
@@ -429,7 +417,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 		return CVTX_B200_OK;
 	}
 
-	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, {}};
+	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, op, reg, {}};
 	dispatch_op(op, reg, pl);
 	const Plan &plan = pl.plan;
 	const int n_src_tiles = (n_src + kSrcTile - 1) / kSrcTile;
@@ -441,7 +429,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 
 	// the arena may still be in use by an earlier call on another stream
 	CUDA_TRY(cudaStreamWaitEvent(st, d->arena_idle, 0));
-	const size_t need_packed = (size_t)n_pad * sizeof(float4);
+	const size_t need_packed = plan.k.can_direct ? 0 : (size_t)n_pad * sizeof(float4);     // no packed copy in direct mode
 	const size_t need_pieces = sizeof(double) * 2 * (size_t)plan.grid * plan.k.T * plan.k.B * q.nout;
 	const size_t need_tickets = sizeof(int) * (size_t)plan.tiles_t;
 	const size_t need_aux = filament ? sizeof(F3DStats) * (size_t)n_src_tiles + 64 : 0;
@@ -462,11 +450,15 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	// aux: [0, 64) the filament mode word, then one F3DStats per packed tile
 	int *mode_word = (int *)d->aux.p;
 	F3DStats *stats = filament ? (F3DStats *)((char *)d->aux.p + 64) : nullptr;
-	pack_sources_kernel<<<n_src_tiles, kSrcTile, 0, st>>>(src_kind(op), src_cols(op), src, n_src, n_pad, (float4 *)d->packedA.p,
-	                                                        records >= 2 ? (float4 *)d->packedB.p : nullptr,
-	                                                        records >= 3 ? (float4 *)d->packedC.p : nullptr, stats);
-	CUDA_TRY(cudaGetLastError());
-	unsigned long long launched = 2;
+	unsigned long long launched = 1;
+	const bool direct = plan.k.can_direct;             // the pair kernel packs the raw rows itself (m2m_kernel.cuh)
+	if (!direct) {
+		pack_sources_kernel<<<n_src_tiles, kSrcTile, 0, st>>>(src_kind(op), src_cols(op), src, n_src, n_pad, (float4 *)d->packedA.p,
+		                                                        records >= 2 ? (float4 *)d->packedB.p : nullptr,
+		                                                        records >= 3 ? (float4 *)d->packedC.p : nullptr, stats);
+		CUDA_TRY(cudaGetLastError());
+		++launched;
+	}
 	if (filament) {
 		f3d_mode_kernel<<<1, 256, 0, st>>>(stats, n_src_tiles, n_src, f3d_mode_override(), mode_word);
 		CUDA_TRY(cudaGetLastError());
@@ -493,9 +485,22 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	args.k = ck.k;
 	const int gm = guard_mode();
 	args.exact_only = (gm == 1 || (gm == 0 && n_src_tiles < kMinTilesOptimistic)) ? 1 : 0;
+	args.direct = direct ? 1 : 0;
+	// pieces per cut target tile ~ runs per tile; beyond this the ordered finish is a kernel of its own
+	const long long runs_per_tile = (plan.grid + plan.tiles_t - 1) / plan.tiles_t;
+	const bool defer = runs_per_tile > kInKernelFinishPieces;
+	args.defer_finish = defer ? 1 : 0;
 	CUDA_TRY(cudaEventRecord(d->k_start, st));
 	void *params[1] = {&args};
 	CUDA_TRY(cudaLaunchKernel(plan.k.fn, dim3(plan.grid), dim3(plan.k.B), params, plan.k.smem, st));
+	if (defer) {
+		const long long gpt = plan.total_grains / plan.tiles_t;
+		const long long warps = plan.tiles_t * (long long)plan.k.T * plan.k.B * q.nout;
+		finish_pieces_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const double *)d->pieces.p, out, n_tgt, q.nout,
+		                                                                            plan.k.T * plan.k.B, gpt, plan.total_grains, plan.grid);
+		CUDA_TRY(cudaGetLastError());
+		++launched;
+	}
 	CUDA_TRY(cudaEventRecord(d->k_stop, st));
 	d->timed = true;
 	CUDA_TRY(cudaEventRecord(d->arena_idle, st));

@@ -1,0 +1,6 @@
+// kernels_p3d_vel_dvort.cu -- instances of m2m_kernel (kernel_inst.cuh); split by op so that the library builds in parallel.
+#include "kernel_inst.cuh"
+
+namespace cvtx {
+KernelChoice choice_p3d_vel_dvort(int reg, int v, bool g, int device) { (void)reg; return choice_by_reg<P3DVelDvort>(reg, v, g, device); }
+}  // namespace cvtx

@@ -1,0 +1,7 @@
+// kernels_p3d_visc_vort.cu -- instances of m2m_kernel (kernel_inst.cuh); split by op so that the library builds in parallel.
+#include "kernel_inst.cuh"
+
+namespace cvtx {
+KernelChoice choice_p3d_visc(int reg, int v, bool g, int device) { (void)reg; return choice_by_eta<P3DVisc>(reg, v, g, device); }
+KernelChoice choice_p3d_vort(int reg, int v, bool g, int device) { (void)reg; return choice_by_reg<P3DVort>(reg, v, g, device); }
+}  // namespace cvtx

@@ -64,6 +64,8 @@ struct M2MArgs {
 	const int *f3d_mode;       // filaments: which fast form (pair_math.cuh f3d_pick_mode), decided while packing
 	PairConsts k;
 	int exact_only;            // 1: always evaluate the guarded pair form (never the optimistic one)
+	int direct;                // 1: no packed copy exists; blocks pack the raw rows of a tile straight into shared memory
+	int defer_finish;          // 1: cut target tiles are summed by finish_pieces_kernel after this launch, not by their last block
 	unsigned long long *block_times;   // diagnostics (tools/kernel_ab): per block {SM id, start ns, end ns}, or null
 };
 
@@ -165,6 +167,29 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 	}
 	__syncthreads();
 
+	// Small source sets and the small-tile geometries (GRAIN == 0 instances) of the particle ops take their
+	// sources straight from the caller's rows: every thread packs a record or two of the step's tile into
+	// shared memory.  A tile is then used by few blocks (few targets) or the whole call is a few microseconds
+	// (10k x 10k), and a separate pack kernel -- a launch, a write and a read of the packed copy, a dependency --
+	// costs more than the two loads per thread it saves here.
+	constexpr bool CAN_DIRECT = GRAIN == 0 && !P::HYBRID;
+	const bool direct = CAN_DIRECT && args.direct;
+	auto fill = [&](int src_tile, int buf) {                            // all threads; followed by __syncthreads()
+		constexpr int KIND = P::NSRC4 == 1 ? SRC_P2D : SRC_P3D, COLS = P::NSRC4 == 1 ? 4 : 7;
+		for (int i = tid; i < S; i += B) {
+			const long j = (long)src_tile * S + i;
+			f4 a, b, c;
+			pad_source(KIND, a, b, c);
+			if (j < args.n_src) {
+				float row[COLS];
+#pragma unroll
+				for (int q = 0; q < COLS; ++q) row[q] = __ldg(args.src_raw + j * COLS + q);
+				pack_source(KIND, row, a, b, c);
+			}
+			tile[buf][0][i] = a;
+			if (NR >= 2) tile[buf][NR >= 2 ? 1 : 0][i] = b;
+		}
+	};
 	auto fetch = [&](int src_tile, int buf) {                           // thread 0 only
 		const size_t off = (size_t)src_tile * S;
 		mbar_expect_tx(&full[buf], kTileBytes * NR);
@@ -178,7 +203,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 		args.block_times[3 * blockIdx.x] = smid; args.block_times[3 * blockIdx.x + 1] = t;
 	}
-	if (tid == 0 && left > 0) fetch(gs / gps, 0);
+	if (!direct && tid == 0 && left > 0) fetch(gs / gps, 0);
 
 	// Two targets share one Vec<2> (packed FP32x2 lanes) when T is even.
 	constexpr int W = (T % 2 == 0) ? (T < VW ? T : VW) : 1;
@@ -197,7 +222,10 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		// this step: grains [gs, gs + n) of tile tt, all inside one source tile
 		int n = gps - gs % gps;
 		n = n < left ? n : left;
-		if (left > n) {                                                 // prefetch the next step's source tile into the other buffer
+		if (CAN_DIRECT && direct) {
+			fill(gs / gps, buf);
+			__syncthreads();
+		} else if (left > n) {                                          // prefetch the next step's source tile into the other buffer
 			const int gs_next = gs + n == gpt ? 0 : gs + n;
 			if (tid == 0) fetch(gs_next / gps, buf ^ 1);
 		}
@@ -226,7 +254,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		}
 		const int lo = (gs % gps) * G, hi = lo + n * G;                 // this step's sources within the tile
 		if (!idle_warp) {
-			mbar_wait(&full[buf], (it >> 1) & 1);
+			if (!direct) mbar_wait(&full[buf], (it >> 1) & 1);
 			const float4 *sA = tile[buf][0];
 			const float4 *sB = tile[buf][NR >= 2 ? 1 : 0];
 			const float4 *sC = tile[buf][NR >= 3 ? 2 : 0];
@@ -411,27 +439,43 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 				}
 				const long long b_first = run_of((long long)tt * gpt, R, args.total_grains);
 				const long long b_last = run_of((long long)(tt + 1) * gpt - 1, R, args.total_grains);
-				__threadfence();
-				__syncthreads();
-				if (tid == 0) s_ticket = atomicAdd(args.tickets + tt, 1);
+				// a tile cut into very many pieces (few targets, many sources) is left to finish_pieces_kernel:
+				// a warp per value there, against one thread per value walking every piece here
+				if (args.defer_finish) { if (tid == 0) s_ticket = -1; }
+				else {
+					__threadfence();
+					__syncthreads();
+					if (tid == 0) s_ticket = atomicAdd(args.tickets + tt, 1);
+				}
 				__syncthreads();
 				if (s_ticket == (int)(b_last - b_first)) {              // last to arrive: add the pieces in run order
 					__threadfence();
+					// T x NOUT values per thread, one piece per run that touched the tile: the loads of a piece (and of the next)
+					// are all in flight before the first add waits, the adds stay in run order
+					constexpr int TB = T > 4 ? 4 : T;
 #pragma unroll 1
-					for (int t = 0; t < T; ++t) {
-						const long i = base + (long)t * B;
-						double sum[P::NOUT];
+					for (int t0 = 0; t0 < T; t0 += TB) {
+						double sum[TB][P::NOUT];
 #pragma unroll
-						for (int c = 0; c < P::NOUT; ++c) sum[c] = 0.0;
+						for (int t = 0; t < TB; ++t)
+#pragma unroll
+							for (int c = 0; c < P::NOUT; ++c) sum[t][c] = 0.0;
+#pragma unroll 2
 						for (long long bb = b_first; bb <= b_last; ++bb) {
 							const long long sl = 2 * bb + (run_begin(bb, R, args.total_grains) / gpt == tt ? 0 : 1);
-							const double *pc = args.pieces + (size_t)sl * (T * B * P::NOUT) + ((size_t)t * B + tid) * P::NOUT;
+							const double *pc = args.pieces + (size_t)sl * (T * B * P::NOUT) + ((size_t)t0 * B + tid) * P::NOUT;
 #pragma unroll
-							for (int c = 0; c < P::NOUT; ++c) sum[c] += __ldcg(pc + c);
+							for (int t = 0; t < TB; ++t)
+#pragma unroll
+								for (int c = 0; c < P::NOUT; ++c) sum[t][c] += __ldcg(pc + (size_t)t * B * P::NOUT + c);
 						}
-						if (i < args.n_tgt) {
 #pragma unroll
-							for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)sum[c];
+						for (int t = 0; t < TB; ++t) {
+							const long i = base + (long)(t0 + t) * B;
+							if (i < args.n_tgt) {
+#pragma unroll
+								for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)sum[t][c];
+							}
 						}
 					}
 					if (tid == 0) args.tickets[tt] = 0;                  // leave the ticket counter ready for the next launch
@@ -448,86 +492,6 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 		args.block_times[3 * blockIdx.x + 2] = t;
 	}
-}
-
-// Raw rows -> packed float4 records, padded with zero-strength records (pad_source) to n_pad, a
-// multiple of kSrcTile.  One block packs one tile.  For filaments each block also leaves the
-// statistics f3d_pick_mode() wants (sum of l^3, longest l, bounding box of the end points) in
-// stats[blockIdx.x]; f3d_mode_kernel combines them in block order.
-struct F3DStats { double sum_len3; float max_len; float lo[3], hi[3]; };
-
-__global__ void __launch_bounds__(kSrcTile) pack_sources_kernel(int kind, int cols, const float *__restrict__ rows, int n, int n_pad,
-                                                                float4 *__restrict__ A, float4 *__restrict__ Bq, float4 *__restrict__ Cq,
-                                                                F3DStats *__restrict__ stats)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	float4 a, b, c;
-	pad_source(kind, a, b, c);
-	const bool real = i < n;
-	if (real) {
-		float row[7];
-		for (int k = 0; k < cols; ++k) row[k] = rows[(size_t)i * cols + k];
-		pack_source(kind, row, a, b, c);
-	}
-	if (i < n_pad) {
-		A[i] = a;
-		if (Bq) Bq[i] = b;
-		if (Cq) Cq[i] = c;
-	}
-	if (stats) {
-		__shared__ F3DStats part[kSrcTile / 32];
-		const float len = real ? sqrtf(c.w) : 0.0f;
-		double l3 = (double)len * len * len;
-		float mx = len;
-		float lo[3], hi[3];
-		const float big = 3.0e38f;
-		lo[0] = real ? fminf(a.x, b.x) : big; lo[1] = real ? fminf(a.y, b.y) : big; lo[2] = real ? fminf(a.z, b.z) : big;
-		hi[0] = real ? fmaxf(a.x, b.x) : -big; hi[1] = real ? fmaxf(a.y, b.y) : -big; hi[2] = real ? fmaxf(a.z, b.z) : -big;
-		for (int o = 16; o > 0; o >>= 1) {                      // fixed shuffle tree: the same sum on every run
-			l3 += __shfl_down_sync(0xffffffffu, l3, o);
-			mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
-			for (int d = 0; d < 3; ++d) {
-				lo[d] = fminf(lo[d], __shfl_down_sync(0xffffffffu, lo[d], o));
-				hi[d] = fmaxf(hi[d], __shfl_down_sync(0xffffffffu, hi[d], o));
-			}
-		}
-		if ((threadIdx.x & 31) == 0) {
-			F3DStats &w = part[threadIdx.x >> 5];
-			w.sum_len3 = l3; w.max_len = mx;
-			for (int d = 0; d < 3; ++d) { w.lo[d] = lo[d]; w.hi[d] = hi[d]; }
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			F3DStats r = part[0];
-			for (int k = 1; k < kSrcTile / 32; ++k) {
-				r.sum_len3 += part[k].sum_len3; r.max_len = fmaxf(r.max_len, part[k].max_len);
-				for (int d = 0; d < 3; ++d) { r.lo[d] = fminf(r.lo[d], part[k].lo[d]); r.hi[d] = fmaxf(r.hi[d], part[k].hi[d]); }
-			}
-			stats[blockIdx.x] = r;
-		}
-	}
-}
-
-// mode[0] = f3d_pick_mode over all filaments: one block, thread t takes blocks t, t + 256, ... in order,
-// then a fixed tree -- the same sums on every run and every device.  `force` >= 0 pins the mode.
-__device__ __forceinline__ void f3d_stats_merge(F3DStats &r, const F3DStats &o) {
-	r.sum_len3 += o.sum_len3; r.max_len = fmaxf(r.max_len, o.max_len);
-	for (int d = 0; d < 3; ++d) { r.lo[d] = fminf(r.lo[d], o.lo[d]); r.hi[d] = fmaxf(r.hi[d], o.hi[d]); }
-}
-__global__ void __launch_bounds__(256) f3d_mode_kernel(const F3DStats *__restrict__ stats, int n_blocks, int n, int force, int *__restrict__ mode)
-{
-	__shared__ F3DStats sh[256];
-	F3DStats r;
-	r.sum_len3 = 0.0; r.max_len = 0.0f;
-	for (int d = 0; d < 3; ++d) { r.lo[d] = 3.0e38f; r.hi[d] = -3.0e38f; }
-	for (int k = threadIdx.x; k < n_blocks; k += 256) f3d_stats_merge(r, stats[k]);
-	sh[threadIdx.x] = r;
-	__syncthreads();
-	for (int o = 128; o > 0; o >>= 1) {
-		if ((int)threadIdx.x < o) f3d_stats_merge(sh[threadIdx.x], sh[threadIdx.x + o]);
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) mode[0] = force >= 0 ? force : f3d_pick_mode(sh[0].sum_len3, (double)n, sh[0].lo, sh[0].hi, sh[0].max_len);
 }
 
 // ---------------------------------------------------------------------------

@@ -17,7 +17,7 @@ def test_m2m_host_matches_oracle_and_counts_bytes(gpu, oracle):
         src, tgt = make_case(op, rng, 3001, 999, self_targets=False)
         before = dev.kernel_launches()
         out, up, down = dev.m2m_host(op, reg, 0, src, tgt, 0.05, 0.2)
-        assert dev.kernel_launches() - before >= 2          # pack + pair (+ reduce)
+        assert dev.kernel_launches() - before >= 1          # the pair kernel (+ pack for large source sets, + ordered finish for few targets)
         assert up == src.nbytes + tgt.nbytes and down == out.nbytes
         want = oracle.m2m(op, src, tgt, reg, 0.05, 0.2)
         assert rel_l2(out.reshape(want.shape), want) <= TOL

@@ -45,7 +45,7 @@ static float run_new(Ctx &c, const char *name, int grid_mult, bool times = false
 	auto kern = m2m_kernel<P, T, BLK, MINB, VW, OPT, GRAIN>;
 	int occ = 0;
 	const size_t dyn = m2m_smem_bytes<P, T, BLK, OPT>();
-	if (dyn > 32768) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+	if (dyn > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, dyn));
 	cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
 	M2MArgs a = {};
@@ -166,6 +166,22 @@ static void sweep(Ctx &c, const char *name, int chunks) {
 #undef ROW
 }
 template <class P>
+static void sweep_f3d(Ctx &c, const char *name) {
+#ifdef F3D_QUICK
+	run_new<P, 4, 256, 2, 2, 0, 256>(c, name, 4);
+	run_new<P, 8, 128, 2, 8, 1, 256>(c, name, 4);
+	return;
+#endif
+#define ROW(T, B, VW) run_new<P, T, B, 2, VW, 0, 256>(c, name, 4); run_new<P, T, B, 2, VW, 1, 256>(c, name, 4);
+	ROW(8, 128, 2) ROW(8, 128, 4) ROW(8, 128, 8)
+	ROW(4, 256, 2) ROW(4, 256, 4)
+#undef ROW
+	run_new<P, 2, 256, 3, 2, 0, 256>(c, name, 4);
+	run_new<P, 2, 256, 3, 2, 1, 256>(c, name, 4);
+	run_new<P, 4, 128, 4, 2, 0, 256>(c, name, 4);
+	run_new<P, 4, 128, 4, 4, 1, 256>(c, name, 4);
+}
+template <class P>
 static void mult_sweep(Ctx &c, const char *name) {
 	run_new<P, 8, 128, 2, 2, 0>(c, name, 1, true);
 	run_new<P, 8, 128, 2, 2, 0>(c, name, 2);
@@ -211,10 +227,36 @@ int main(int argc, char **argv) {
 	CK(cudaMemset(c.C, 0, sizeof(float4) * n));
 	CK(cudaMemcpy(c.tgt, ht.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
 
+	if (c.filter && strstr(c.filter, "f3d")) {
+		// filaments: start uniform in the box, end = start + U(-0.1, 0.1)^3, packed on the host
+		std::vector<float> rows((size_t)n * 7);
+		std::vector<float4> fa(n), fb(n), fc(n);
+		for (int i = 0; i < n; ++i) {
+			float *r = &rows[(size_t)i * 7];
+			for (int k = 0; k < 3; ++k) { r[k] = rnd(); r[3 + k] = r[k] + 0.02f * (rnd() - 5.0f); }
+			r[6] = rnd();
+			pack_source(SRC_F3D, r, fa[i], fb[i], fc[i]);
+			for (int k = 0; k < 6; ++k) ht[(size_t)i * 7 + k] = rnd();       // independent target particles
+		}
+		CK(cudaMemcpy(c.raw, rows.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(c.A, fa.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(c.B, fb.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(c.C, fc.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(c.tgt, ht.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
+		c.filter = nullptr;
+		sweep_f3d<F3DVel>(c, "f3dvel");
+		sweep_f3d<F3DDvort>(c, "f3ddvort");
+		printf("done\n");
+		return 0;
+	}
 #ifndef PART
 #define PART -1
 #endif
+#ifdef FULL_SWEEP
 #define SW(k, POL, REG, nm) if (PART < 0 || PART == (k) % 8) sweep<POL<REG>, cvtx_r1::POL<cvtx_r1::REG>>(c, nm, chunks);
+#else
+#define SW(k, POL, REG, nm)
+#endif
 	SW(0, P3DVel, REG_SINGULAR, "vel-singular") SW(1, P3DVel, REG_WINCKELMANS, "vel-winckelmans")
 	SW(2, P3DVel, REG_PLANETARY, "vel-planetary") SW(3, P3DVel, REG_GAUSSIAN, "vel-gaussian")
 	SW(4, P3DDvort, REG_SINGULAR, "dvort-singular") SW(5, P3DDvort, REG_WINCKELMANS, "dvort-winckelmans")

@@ -1,6 +1,6 @@
-"""Does the planner pick a good geometry for mid-size problems?  Sweeps (targets per thread, source
-chunks) with cvtx_b200_tune and compares the best measured pair-kernel time with the planner's own
-choice.   python tools/plan_sweep.py [n ...]"""
+"""Does the planner pick a good geometry for mid-size problems?  Sweeps (targets per thread, number of
+equal runs = grid size) with cvtx_b200_tune and compares the best measured pair-kernel time with the
+planner's own choice.   python tools/plan_sweep.py [n ...]"""
 import os
 import sys
 
@@ -34,13 +34,13 @@ for n in [int(a) for a in sys.argv[1:]] or [3000, 10000, 30000, 80000]:
         auto = timed(op, reg, src, n, tgt, n, out)
         plan = be.plan(op, 0, n, n)
         results = []
-        n_tiles = (n + 255) // 256
+        sms = be.sm_count(0)
         for T in (8, 4, 2, 1):
-            for chunks in sorted({c for c in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384) if c <= n_tiles}):
+            for chunks in [sms * k for k in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48)]:
                 be.tune(T, chunks)
                 results.append((timed(op, reg, src, n, tgt, n, out, reps=4), T, chunks))
         be.tune(0, 0)
         results.sort()
         best = results[0]
-        print(f"{op}/{reg} n=m={n:6d}: planner {auto * 1e3:8.1f} us {plan} | best swept {best[0] * 1e3:8.1f} us (T={best[1]}, chunks={best[2]})"
+        print(f"{op}/{reg} n=m={n:6d}: planner {auto * 1e3:8.1f} us {plan} | best swept {best[0] * 1e3:8.1f} us (T={best[1]}, runs={best[2]}; next {results[1][0] * 1e3:.1f} us T={results[1][1]} runs={results[1][2]})"
               f" | planner / best = {auto / best[0]:.3f} | ideal at peak rate {n * n / (1574e9 if 'vel' in op else 800e9) * 1e6:7.1f} us", flush=True)
