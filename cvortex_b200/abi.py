@@ -108,6 +108,15 @@ class CvtxLibrary:
             "cvtx_P2D_S2S_visc_dvort": (f, [_vp, _vp, _VFp, f, f]),
             "cvtx_F3D_S2S_vel": (V3f, [_vp, V3f]),
             "cvtx_F3D_S2S_dvort": (V3f, [_vp, _vp]),
+            # many sources on one target, libcvtx.h:151-211, 275-283, 318-360
+            "cvtx_P3D_M2S_vel": (V3f, [_vp, i, V3f, _VFp, f]),
+            "cvtx_P3D_M2S_dvort": (V3f, [_vp, i, _vp, _VFp, f]),
+            "cvtx_P3D_M2S_visc_dvort": (V3f, [_vp, i, _vp, _VFp, f, f]),
+            "cvtx_P3D_M2S_vort": (V3f, [_vp, i, V3f, _VFp, f]),
+            "cvtx_P2D_M2S_vel": (V2f, [_vp, i, V2f, _VFp, f]),
+            "cvtx_P2D_M2S_visc_dvort": (f, [_vp, i, _vp, _VFp, f, f]),
+            "cvtx_F3D_M2S_vel": (V3f, [_vp, i, V3f]),
+            "cvtx_F3D_M2S_dvort": (V3f, [_vp, i, _vp]),
             # the hot path, libcvtx.h:213-248, 285-297, 329-336, 362-370
             "cvtx_P3D_M2M_vel": (None, [_vp, i, _vp, i, _vp, _VFp, f]),
             "cvtx_P3D_M2M_dvort": (None, [_vp, i, _vp, i, _vp, _VFp, f]),
@@ -197,6 +206,25 @@ class CvtxLibrary:
         fil, q = _rows(np.atleast_2d(fil), 7), _rows(np.atleast_2d(q), 7)
         r = self.lib.cvtx_F3D_S2S_dvort(fil.ctypes.data, q.ctypes.data)
         return np.array(r.x[:], dtype=np.float32)
+
+    # ---- many sources on one target (M2S) ----
+    def M2S(self, op: str, src, tgt_row, reg="singular", sigma=1.0, nu=0.0):
+        """cvtx_<op with M2M replaced by M2S>: `src` rows on ONE target row (a point, or a particle row for
+        the dvort ops); returns the output row as a float32 array."""
+        name = "cvtx_" + op.replace("M2M", "M2S")
+        two_d, fil = op.startswith("P2D"), op.startswith("F3D")
+        src = src if isinstance(src, PointerRows) else PointerRows(src, 4 if two_d else 7)
+        particle_target = op.endswith("dvort")
+        if particle_target:
+            row = _rows(np.atleast_2d(tgt_row), 4 if two_d else 7)
+            targ = row.ctypes.data
+        elif two_d:
+            targ = V2f((C.c_float * 2)(*map(float, tgt_row)))
+        else:
+            targ = V3f((C.c_float * 3)(*map(float, tgt_row)))
+        tail = () if fil else ((C.byref(self.vortfunc(reg)), sigma, nu) if op.endswith("visc_dvort") else (C.byref(self.vortfunc(reg)), sigma))
+        r = getattr(self.lib, name)(src.ptrs.ctypes.data, src.shape[0], targ, *tail)
+        return np.array([r], dtype=np.float32) if isinstance(r, float) else np.array(r.x[:], dtype=np.float32)
 
     # ---- the hot path: all-pairs M2M ----
     def _m2m(self, name, src, scols, tgt, tcols, ocols, tail, tgt_is_particles, out=None):

@@ -249,7 +249,7 @@ int cvtx::device_stream(int device, cudaStream_t *stream) {
 	Device *d = get_device(device);
 	if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
 	DeviceGuard restore;
-	std::lock_guard<std::mutex> lk(d->mu);
+	DeviceLock lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
 	*stream = d->stream;
@@ -285,7 +285,7 @@ void cvtx_b200_release(void) {
 		std::lock_guard<std::mutex> lk(g_devices_mu);
 		for (size_t i = 0; i < g_devices.size(); ++i) {
 			Device *d = g_devices[i];
-			std::lock_guard<std::mutex> dl(d->mu);
+			DeviceLock dl(d->mu);
 			if (!d->ready) continue;
 			cudaSetDevice((int)i);
 			cudaDeviceSynchronize();
@@ -321,7 +321,7 @@ int cvtx_b200_plan(int op, int device, int n_src, int n_tgt, int *block, int *tp
 	Planner pl = {device, n_src, n_tgt, d->prop.multiProcessorCount, op, op_is_filament(op) ? 0 : REG_WINCKELMANS, {}};
 	{
 		DeviceGuard restore;
-		std::lock_guard<std::mutex> lk(d->mu);
+		DeviceLock lk(d->mu);
 		CUDA_TRY(cudaSetDevice(device));
 		dispatch_op(op, op_is_filament(op) ? 0 : REG_WINCKELMANS, pl);
 	}
@@ -347,7 +347,7 @@ float cvtx_b200_last_pair_kernel_ms(int device) {
 	Device *d = get_device(device);
 	if (!d) return -1.f;
 	DeviceGuard restore;
-	std::lock_guard<std::mutex> lk(d->mu);
+	DeviceLock lk(d->mu);
 	if (!d->timed) return -1.f;
 	float ms = -1.f;
 	if (cudaSetDevice(device) != cudaSuccess) return -1.f;
@@ -362,7 +362,7 @@ int cvtx_b200_measure_peak(int device, int what, double *ops_per_second)
 	Device *d = get_device(device);
 	if (!d || !ops_per_second || (what != 0 && what != 1)) return fail(CVTX_B200_ERR_ARGUMENT, "bad device, selector or pointer");
 	DeviceGuard restore;
-	std::lock_guard<std::mutex> lk(d->mu);
+	DeviceLock lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
 	float *sink = nullptr;
@@ -409,7 +409,7 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 
 	cudaStream_t st = (cudaStream_t)stream_;
 	DeviceGuard restore;
-	std::lock_guard<std::mutex> lk(d->mu);
+	DeviceLock lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
 	if (n_src == 0) {                                  // no sources: the sums are empty
@@ -518,7 +518,7 @@ int cvtx_b200_f3d_inf_mtrx(int device, void *stream_, const float *fil, int n_fi
 	if (n_fil == 0 || n_mes == 0) return CVTX_B200_OK;
 	if (!fil || !mes || !dir || !out) return fail(CVTX_B200_ERR_ARGUMENT, "null pointer");
 	DeviceGuard restore;
-	std::lock_guard<std::mutex> lk(d->mu);
+	DeviceLock lk(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	if (int rc = ensure_ready(d)) return rc;
 	constexpr int B = 256, W = 2;
@@ -599,7 +599,7 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 		Device *d = get_device(devices[g]);
 		if (!d) return fail(CVTX_B200_ERR_ARGUMENT, "no such CUDA device");
 		{
-			std::lock_guard<std::mutex> lk(d->mu);
+			DeviceLock lk(d->mu);
 			CUDA_TRY(cudaSetDevice(devices[g]));
 			if (int rc = ensure_ready(d)) return rc;
 			streams[g] = d->stream;

@@ -240,7 +240,7 @@ int cvtx_b200_m2m_sharded(int op, int reg, int n_dev, const int *devices, const 
 		rc = device_stream(devs[g], &streams[g]);
 		if (rc != CVTX_B200_OK) break;
 		Device *d = get_device(devs[g]);
-		std::lock_guard<std::mutex> lk(d->mu);
+		DeviceLock lk(d->mu);
 		const cudaError_t e = d->d_src.reserve(srow * (size_t)off[G]);
 		if (e != cudaSuccess) rc = fail(CVTX_B200_ERR_CUDA, std::string("device source buffer: ") + cudaGetErrorString(e));
 		shard[g] = src_shard_dev[g];

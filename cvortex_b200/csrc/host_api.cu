@@ -119,6 +119,21 @@ void copy_rows(void *dst, const void *src, long n, size_t row_bytes) {
 	}
 }
 
+// What a failure on the GPU route does.  Default: message + abort -- a CPU result is never substituted
+// silently.  CVTX_B200_ON_FAILURE=host (read once) is the opt-in for hosts that would rather lose speed than the
+// session (the reference's behaviour, src/P3D.cpp:353-364, but never silent): the failure is reported on stderr
+// every time and the caller's host loop runs.
+bool failure_goes_to_host(const char *entry, int rc) {
+	static const bool to_host = [] { const char *e = std::getenv("CVTX_B200_ON_FAILURE"); return e && !std::strcmp(e, "host"); }();
+	if (!to_host) return false;
+	std::fprintf(stderr, "cvortex: %s failed on the GPU path (status %d): %s\n"
+	                     "cvortex: CVTX_B200_ON_FAILURE=host -> running the HOST loops for this call.\n",
+	             entry, rc, cvtx_b200_last_error());
+	cudaGetLastError();
+	g_last_dispatch = 0;
+	return true;
+}
+
 // The GPU route of every M2M entry point.  Returns false when the call is not
 // the GPU's to take (nothing enabled / user-defined regularisation), in which
 // case the caller runs the host loops; aborts on a GPU failure.
@@ -150,17 +165,35 @@ bool gpu_m2m(const char *entry, int op, const cvtx_VortFunc *kernel,
 	if (e == cudaSuccess) e = hs.tgt.reserve(trow * (size_t)n_tgt);
 	if (e != cudaSuccess) {
 		fail(CVTX_B200_ERR_CUDA, std::string("pinned staging: ") + cudaGetErrorString(e));
+		if (failure_goes_to_host(entry, CVTX_B200_ERR_CUDA)) return false;
 		gpu_failure(entry, CVTX_B200_ERR_CUDA);
 	}
 	if (n_src > 0) gather_rows(hs.src.p, src_ptrs, n_src, srow);
 	if (tgt_ptrs) gather_rows(hs.tgt.p, tgt_ptrs, n_tgt, trow);
 	else copy_rows(hs.tgt.p, tgt_flat, n_tgt, trow);
 	const int rc = run_staged(op, reg, devs, n_src > 0 ? n_src : 0, n_tgt, (float *)result, sigma, nu, nullptr, nullptr);
-	if (rc != CVTX_B200_OK) gpu_failure(entry, rc);
+	if (rc != CVTX_B200_OK) {
+		if (failure_goes_to_host(entry, rc)) return false;
+		gpu_failure(entry, rc);
+	}
 	return true;
 }
 
 }  // namespace
+
+// Below this many sources a one-target call stays in the host loop: the GPU route costs ~0.1 ms of
+// gather + copies + launch + sync whatever the size, the serial host loop ~50 ns per source.
+constexpr int kM2SMinSources = 4096;
+
+bool cvtx::gpu_m2s(const char *entry, int op, const char *reg_name, const void *const *src_ptrs, int n_src,
+                   const void *tgt_row, float *result, float sigma, float nu)
+{
+	if (n_src < kM2SMinSources) return false;
+	cvtx_VortFunc k;
+	std::memset(&k, 0, sizeof k);
+	if (reg_name) std::strncpy(k.cl_kernel_name_ext, reg_name, sizeof(k.cl_kernel_name_ext) - 1);
+	return gpu_m2m(entry, op, reg_name ? &k : nullptr, src_ptrs, n_src, tgt_row, nullptr, 1, result, sigma, nu);
+}
 
 extern "C" {
 
@@ -349,7 +382,7 @@ CVTX_API void cvtx_F3D_inf_mtrx(const cvtx_F3D **array_start, const int num_fila
 	ok = ok && step(hs.src.reserve(fb), "pinned filaments") && step(hs.tgt.reserve(2 * pb), "pinned points")
 	     && step(hs.out.reserve(row_bytes * (size_t)slab_rows), "pinned result slab");
 	if (ok) {
-		std::lock_guard<std::mutex> dl(d->mu);
+		DeviceLock dl(d->mu);
 		ok = step(d->d_src.reserve(fb), "device filaments") && step(d->d_tgt.reserve(2 * pb), "device points")
 		     && step(d->d_out.reserve(row_bytes * (size_t)slab_rows), "device result slab");
 	}

@@ -18,6 +18,8 @@
 #include <cassert>
 #include "export.h"
 #include "host_scalar.h"
+#include "host_hooks.h"
+#include "op_table.h"
 
 namespace {
 
@@ -233,6 +235,11 @@ void host_f3d_inf_mtrx(const cvtx_F3D **a, int n, const bsv_V3f *x, const bsv_V3
 }  // namespace cvtx
 
 // ---- exported scalar entry points -------------------------------------------
+using cvtx::gpu_m2s;
+using cvtx::note_dispatch;
+using cvtx::OP_P3D_VEL; using cvtx::OP_P3D_DVORT; using cvtx::OP_P3D_VISC; using cvtx::OP_P3D_VORT;
+using cvtx::OP_P2D_VEL; using cvtx::OP_P2D_VISC; using cvtx::OP_F3D_VEL; using cvtx::OP_F3D_DVORT;
+
 extern "C" {
 
 CVTX_API bsv_V3f cvtx_P3D_S2S_vel(const cvtx_P3D *self, const bsv_V3f mes_point, const cvtx_VortFunc *kernel, float regularisation_radius) {
@@ -266,24 +273,42 @@ CVTX_API void cvtx_P3D_S2M_vort(const cvtx_P3D *self, const bsv_V3f *mes_start, 
 }
 
 CVTX_API bsv_V3f cvtx_P3D_M2S_vel(const cvtx_P3D **array_start, const int num_particles, const bsv_V3f mes_point, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	bsv_V3f r;
+	if (gpu_m2s("cvtx_P3D_M2S_vel", OP_P3D_VEL, kernel->cl_kernel_name_ext, (const void *const *)array_start, num_particles, &mes_point, r.x, regularisation_radius, 0.f)) return r;
+	note_dispatch(0, 0);
 	return st(m2s_p3d_vel(array_start, num_particles, ld(mes_point), kernel, regularisation_radius));
 }
 CVTX_API bsv_V3f cvtx_P3D_M2S_dvort(const cvtx_P3D **array_start, const int num_particles, const cvtx_P3D *induced_particle, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	bsv_V3f r;
+	if (gpu_m2s("cvtx_P3D_M2S_dvort", OP_P3D_DVORT, kernel->cl_kernel_name_ext, (const void *const *)array_start, num_particles, induced_particle, r.x, regularisation_radius, 0.f)) return r;
+	note_dispatch(0, 0);
 	return st(m2s_p3d_dvort(array_start, num_particles, induced_particle, kernel, regularisation_radius));
 }
 CVTX_API bsv_V3f cvtx_P3D_M2S_visc_dvort(const cvtx_P3D **array_start, const int num_particles, const cvtx_P3D *induced_particle, const cvtx_VortFunc *kernel, float regularisation_radius, float kinematic_visc) {
+	bsv_V3f r;
+	if (gpu_m2s("cvtx_P3D_M2S_visc_dvort", OP_P3D_VISC, kernel->cl_kernel_name_ext, (const void *const *)array_start, num_particles, induced_particle, r.x, regularisation_radius, kinematic_visc)) return r;
+	note_dispatch(0, 0);
 	return st(m2s_p3d_visc(array_start, num_particles, induced_particle, kernel, regularisation_radius, kinematic_visc));
 }
 CVTX_API bsv_V3f cvtx_P3D_M2S_vort(const cvtx_P3D **array_start, const int num_particles, const bsv_V3f mes_point, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	bsv_V3f r;
+	if (gpu_m2s("cvtx_P3D_M2S_vort", OP_P3D_VORT, kernel->cl_kernel_name_ext, (const void *const *)array_start, num_particles, &mes_point, r.x, regularisation_radius, 0.f)) return r;
+	note_dispatch(0, 0);
 	return st(m2s_p3d_vort(array_start, num_particles, ld(mes_point), kernel, regularisation_radius));
 }
 
 CVTX_API bsv_V3f cvtx_F3D_S2S_vel(const cvtx_F3D *self, const bsv_V3f mes_point) { return st(f3d_vel(self, ld(mes_point))); }
 CVTX_API bsv_V3f cvtx_F3D_S2S_dvort(const cvtx_F3D *self, const cvtx_P3D *induced_particle) { return st(f3d_dvort(self, induced_particle)); }
 CVTX_API bsv_V3f cvtx_F3D_M2S_vel(const cvtx_F3D **array_start, const int num_filaments, const bsv_V3f mes_point) {
+	bsv_V3f r;
+	if (gpu_m2s("cvtx_F3D_M2S_vel", OP_F3D_VEL, nullptr, (const void *const *)array_start, num_filaments, &mes_point, r.x, 0.f, 0.f)) return r;
+	note_dispatch(0, 0);
 	return st(m2s_f3d_vel(array_start, num_filaments, ld(mes_point)));
 }
 CVTX_API bsv_V3f cvtx_F3D_M2S_dvort(const cvtx_F3D **array_start, const int num_filaments, const cvtx_P3D *induced_particle) {
+	bsv_V3f r;
+	if (gpu_m2s("cvtx_F3D_M2S_dvort", OP_F3D_DVORT, nullptr, (const void *const *)array_start, num_filaments, induced_particle, r.x, 0.f, 0.f)) return r;
+	note_dispatch(0, 0);
 	return st(m2s_f3d_dvort(array_start, num_filaments, induced_particle));
 }
 CVTX_API bsv_V2f cvtx_P2D_S2S_vel(const cvtx_P2D *self, const bsv_V2f mes_point, const cvtx_VortFunc *kernel, float regularisation_radius) {
@@ -298,6 +323,9 @@ CVTX_API void cvtx_P2D_S2M_vel(const cvtx_P2D *self, const bsv_V2f *mes_start, c
 	for (int i = 0; i < num_mes; ++i) result_array[i] = cvtx_P2D_S2S_vel(self, mes_start[i], kernel, regularisation_radius);
 }
 CVTX_API bsv_V2f cvtx_P2D_M2S_vel(const cvtx_P2D **array_start, const int num_particles, const bsv_V2f mes_point, const cvtx_VortFunc *kernel, float regularisation_radius) {
+	bsv_V2f r;
+	if (gpu_m2s("cvtx_P2D_M2S_vel", OP_P2D_VEL, kernel->cl_kernel_name_ext, (const void *const *)array_start, num_particles, &mes_point, r.x, regularisation_radius, 0.f)) return r;
+	note_dispatch(0, 0);
 	return m2s_p2d_vel(array_start, num_particles, mes_point, kernel, regularisation_radius);
 }
 CVTX_API float cvtx_P2D_S2S_visc_dvort(const cvtx_P2D *self, const cvtx_P2D *induced_particle, const cvtx_VortFunc *kernel, float regularisation_radius, float kinematic_visc) {
@@ -308,6 +336,9 @@ CVTX_API void cvtx_P2D_S2M_visc_dvort(const cvtx_P2D *self, const cvtx_P2D **ind
 	for (int i = 0; i < num_induced; ++i) result_array[i] = cvtx_P2D_S2S_visc_dvort(self, induced_start[i], kernel, regularisation_radius, kinematic_visc);
 }
 CVTX_API float cvtx_P2D_M2S_visc_dvort(const cvtx_P2D **array_start, const int num_particles, const cvtx_P2D *induced_particle, const cvtx_VortFunc *kernel, float regularisation_radius, float kinematic_visc) {
+	float r;
+	if (gpu_m2s("cvtx_P2D_M2S_visc_dvort", OP_P2D_VISC, kernel->cl_kernel_name_ext, (const void *const *)array_start, num_particles, induced_particle, &r, regularisation_radius, kinematic_visc)) return r;
+	note_dispatch(0, 0);
 	return m2s_p2d_visc(array_start, num_particles, induced_particle, kernel, regularisation_radius, kinematic_visc);
 }
 

@@ -233,10 +233,12 @@ template <int W> CVTX_HD Vec<W> vfms(Vec<W> a, float b, Vec<W> c) { return vfma(
 template <int W> CVTX_HD Vec<W> vrsqrt(Vec<W> a) { Vec<W> r; for (int i = 0; i < W; ++i) r.set(i, mufu_rsqrt(a.lane(i))); return r; }
 template <int W> CVTX_HD Vec<W> vrcp(Vec<W> a) { Vec<W> r; for (int i = 0; i < W; ++i) r.set(i, mufu_rcp(a.lane(i))); return r; }
 template <int W> CVTX_HD Vec<W> vex2(Vec<W> a) { Vec<W> r; for (int i = 0; i < W; ++i) r.set(i, mufu_ex2(a.lane(i))); return r; }
-// c > 0 ? v : 0      (the coincident-pair rule)
+// c == 0 ? 0 : v     (the coincident-pair rule; c = r^2 >= 0).  Written as the rule itself, not as c > 0: a NaN
+// r^2 -- a NaN coordinate in a source or a target -- must keep its term, as the reference's exact-equality test
+// does (bsv_V3f_isequal: NaN != NaN), so that a diverging simulation shows up as NaN and not as a finite result.
 template <int W> CVTX_HD Vec<W> keep_if_pos(Vec<W> c, Vec<W> v) {
 	Vec<W> r;
-	for (int i = 0; i < W; ++i) r.set(i, c.lane(i) > 0.0f ? v.lane(i) : 0.0f);
+	for (int i = 0; i < W; ++i) r.set(i, c.lane(i) == 0.0f ? 0.0f : v.lane(i));
 	return r;
 }
 // the same rule where the unguarded v is inf / NaN whenever the rule would fire: G = false

@@ -129,6 +129,14 @@ Grid cvtx::remesh::grid_from_bounds(int dim, int kind, int half, float h, const 
 	return g;
 }
 
+// The sort route materialises every share ((2 half + 1)^D per particle) and indexes them with 32 bits; the
+// dense route never writes one.  Only the former has a particle limit per call.
+bool cvtx::remesh::too_many_shares(int dim, const Grid &g, int bits, long n) {
+	if (dense_route(dim, g, bits, n)) return false;
+	const double stencil = dim == 3 ? (2.0 * g.half + 1) * (2.0 * g.half + 1) * (2.0 * g.half + 1) : (2.0 * g.half + 1) * (2.0 * g.half + 1);
+	return (double)n * stencil > 2147483647.0;
+}
+
 bool cvtx::remesh::dense_route(int dim, const Grid &g, int bits, long n) {
 	double cells = 1.0;
 	for (int a = 0; a < dim; ++a) cells *= (double)g.top[a] + 1.0;
@@ -495,6 +503,11 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 		int created = 0;
 		size_t n_nodes = 0;
 		const int rc = device_redistribute_from_host(devs[0], D, kind, h, (const void *const *)in, n_in, negligible, out, max_out, &created, &n_nodes);
+		if (rc == CVTX_B200_ERR_ARGUMENT) {
+			// a limit of this implementation (grid or share count), not a device failure: say so and create nothing
+			std::fprintf(stderr, "cvortex: %s: %s; no particles created.\n", entry, cvtx_b200_last_error());
+			return 0;
+		}
 		if (rc != CVTX_B200_OK) gpu_failure(entry, rc);
 		if (trace_on())
 			std::fprintf(stderr, "cvortex trace: %s n=%d -> %zu nodes -> %d particles; %.3f ms (device: nodes + pruning)\n", entry, n_in, n_nodes,
@@ -506,16 +519,16 @@ int redistribute(const char *entry, const Particle **in, int n_in, Particle *out
 		uint32_t max_index = 0;
 		const int half = kind >= 0 ? kHalfWidth[kind] : (int)roundf(rf->radius);
 		g = place_grid(D, kind, half, h, (const void *const *)in, rows.data(), n_in, ROW, &max_index);
-		const double stencil = D == 3 ? (2.0 * half + 1) * (2.0 * half + 1) * (2.0 * half + 1) : (2.0 * half + 1) * (2.0 * half + 1);
-		if ((double)n_in * stencil > 2147483647.0) {
-			std::fprintf(stderr, "cvortex: %s: %d particles x %.0f stencil nodes exceed the 2^31 shares one call can hold; aborting.\n", entry, n_in, stencil);
-			std::abort();
-		}
 		if (code_bits(D, max_index) < 0) {
-			std::fprintf(stderr, "cvortex: %s: grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D); aborting.\n", entry);
-			std::abort();
+			std::fprintf(stderr, "cvortex: %s: grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D); no particles created.\n", entry);
+			return 0;
 		}
 		const int bits = code_bits(D, max_index);
+		const double stencil = D == 3 ? (2.0 * half + 1) * (2.0 * half + 1) * (2.0 * half + 1) : (2.0 * half + 1) * (2.0 * half + 1);
+		if (too_many_shares(D, g, bits, n_in) || (kind < 0 && (double)n_in * stencil > 2147483647.0)) {
+			std::fprintf(stderr, "cvortex: %s: %d particles on a sparse grid exceed the 2^31 shares one call can sort; no particles created.\n", entry, n_in);
+			return 0;
+		}
 		if (kind < 0) host_nodes_user<D>(rows.data(), n_in, g, rf, &nodes);
 		else if (dense_route(D, g, bits, n_in)) {
 			switch (kind) {

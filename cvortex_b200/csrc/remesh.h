@@ -40,6 +40,7 @@ int code_bits(int dim, uint32_t max_index);
 // benchmark puts 150 particles in a cell: few nodes, long walks).  Otherwise every share is
 // written out and sorted by node.  Both give the same bits.
 bool dense_route(int dim, const Grid &g, int bits, long n);
+bool too_many_shares(int dim, const Grid &g, int bits, long n);     // the sort route's limit (2^31 shares); the dense route has none
 
 // The host-array entry points on `device`: particles (array of pointers to cvtx_P3D / cvtx_P2D)
 // in, created particles out (out_rows may be null: count only).  Node build and pruning both

@@ -656,9 +656,9 @@ int device_redistribute_from_host(int device, int dim, int kind, float h, const 
 	const Grid g = place_grid(dim, kind, kHalfWidth[kind], h, particles, (float *)hs.src.p, n, row_floats, &max_index);
 	const int bits = code_bits(dim, max_index);
 	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
-	if ((double)n * (dim == 3 ? 125.0 : 25.0) > 2147483647.0) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles for one redistribution call (2^31 shares)");
+	if (too_many_shares(dim, g, bits, n)) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles on a sparse grid for one redistribution call (the sort route holds 2^31 shares; the dense route has no limit)");
 
-	std::lock_guard<std::mutex> device_lock(d->mu);
+	DeviceLock device_lock(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 	const double t1 = omp_get_wtime();
 	CUDA_TRY(d->remesh[ROWS].reserve(sizeof(float) * row_floats * (size_t)n));
@@ -699,7 +699,7 @@ int device_redistribute(int device, void *stream, int dim, int kind, const float
 	if (int rc = device_stream(device, &own)) return rc;
 	cudaStream_t st = stream ? (cudaStream_t)stream : own;
 	Device *d = get_device(device);
-	std::lock_guard<std::mutex> device_lock(d->mu);
+	DeviceLock device_lock(d->mu);
 	CUDA_TRY(cudaSetDevice(device));
 
 	// bounds of the particle set -> grid placement (same formulas as the host-array route)
@@ -721,7 +721,7 @@ int device_redistribute(int device, void *stream, int dim, int kind, const float
 	const Grid g = grid_from_bounds(dim, kind, kHalfWidth[kind], h, lo, hi, sum, n, &max_index);
 	const int bits = code_bits(dim, max_index);
 	if (bits < 0) return fail(CVTX_B200_ERR_ARGUMENT, "grid too large for the node codes (more than 2^21 nodes per axis in 3-D, 2^31 in 2-D)");
-	if ((double)n * (dim == 3 ? 125.0 : 25.0) > 2147483647.0) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles for one redistribution call (2^31 shares)");
+	if (too_many_shares(dim, g, bits, n)) return fail(CVTX_B200_ERR_ARGUMENT, "too many particles on a sparse grid for one redistribution call (the sort route holds 2^31 shares; the dense route has no limit)");
 
 	const bool want = out_dev != nullptr;
 	if (bits <= 32)
@@ -776,24 +776,23 @@ extern "C" CVTX_B200_API int cvtx_b200_pedrizzetti_relaxation(int reg, int devic
 	if (int rc = device_stream(device, &own)) return rc;
 	cudaStream_t st = stream ? (cudaStream_t)stream : own;
 	Device *d = get_device(device);
-	float *points = nullptr, *field = nullptr;
-	{
-		std::lock_guard<std::mutex> device_lock(d->mu);
-		CUDA_TRY(cudaSetDevice(device));
-		CUDA_TRY(d->remesh[RELAX_POINTS].reserve(sizeof(float) * 3 * (size_t)n));
-		CUDA_TRY(d->remesh[RELAX_FIELD].reserve(sizeof(float) * 3 * (size_t)n));
-		points = (float *)d->remesh[RELAX_POINTS].p;
-		field = (float *)d->remesh[RELAX_FIELD].p;
-		particle_positions<<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_dev, n, points);
-	}
+	// points / field are per-device scratch: locked for the whole call (the lock is recursive, cvtx_b200_m2m takes it
+	// too), and the stream waits for whatever an earlier call on another stream still has in flight on the arena
+	DeviceGuard restore;
+	DeviceLock device_lock(d->mu);
+	CUDA_TRY(cudaSetDevice(device));
+	CUDA_TRY(cudaStreamWaitEvent(st, d->arena_idle, 0));
+	CUDA_TRY(d->remesh[RELAX_POINTS].reserve(sizeof(float) * 3 * (size_t)n));
+	CUDA_TRY(d->remesh[RELAX_FIELD].reserve(sizeof(float) * 3 * (size_t)n));
+	float *points = (float *)d->remesh[RELAX_POINTS].p, *field = (float *)d->remesh[RELAX_FIELD].p;
+	particle_positions<<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_dev, n, points);
+	CUDA_TRY(cudaGetLastError());
 	// the vorticity field the particles induce at their own positions: the all-pairs kernel
 	if (int rc = cvtx_b200_m2m(CVTX_B200_P3D_VORT, reg, device, st, rows_dev, n, points, n, field, sigma, 0.f)) return rc;
-	{
-		std::lock_guard<std::mutex> device_lock(d->mu);
-		CUDA_TRY(cudaSetDevice(device));
-		relax_blend<<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_dev, field, n, fdt);
-		CUDA_TRY(cudaGetLastError());
-	}
+	CUDA_TRY(cudaSetDevice(device));
+	relax_blend<<<blocks_for((size_t)n), kBlock, 0, st>>>(rows_dev, field, n, fdt);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaEventRecord(d->arena_idle, st));
 	count_launches(2);
 	return CVTX_B200_OK;
 }

@@ -22,8 +22,10 @@ struct Buffer {
 	void release();
 };
 
+// Per-device state.  `mu` is recursive: an entry point that keeps its scratch buffers locked for the whole call
+// (relaxation: points / field) runs cvtx_b200_m2m, which takes the lock itself, under it.
 struct Device {
-	std::mutex mu;
+	std::recursive_mutex mu;
 	bool ready = false;
 	cudaDeviceProp prop;
 	// arena of cvtx_b200_m2m
@@ -36,6 +38,8 @@ struct Device {
 	// work arrays of the grid redistribution (remesh_device.cu)
 	Buffer remesh[32];
 };
+
+using DeviceLock = std::lock_guard<std::recursive_mutex>;
 
 // Library-wide pinned (portable) staging: sources, targets and results of ONE
 // all-pairs call at a time.  Hold `mu` from the first write into src/tgt until

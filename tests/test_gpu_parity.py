@@ -286,3 +286,48 @@ def test_points_on_a_vortex_line_follow_the_reference(gpu, oracle, op):
     assert np.all(call_abi(lib, op, fil, tgt, "singular", 0.3, 0.1) == 0)
     if op == "F3D_M2M_vel":
         assert np.all(lib.F3D_inf_mtrx(fil, pts, np.ones((4, 3), np.float32)) == 0)
+
+
+@pytest.mark.parametrize("op,reg", op_cases() + vort_cases())
+def test_one_target_calls_run_on_the_gpu_above_the_crossover(gpu, oracle, op, reg):
+    """cvtx_*_M2S_* (reference: a serial loop over the sources, src/P3D.cpp:230-322): from 4096 sources up the
+    call is the all-pairs kernel with one target; below, and with every accelerator off, the host loop.
+    Either way the reference's result."""
+    lib, dev = gpu
+    rng = np.random.default_rng(seed_of("m2s", op, reg))
+    base = "P3D_M2M_vel" if op == "P3D_M2M_vort" else op
+    src, tgt = make_case(base, rng, 50_000, 1, self_targets=False)
+    want = np.asarray(oracle.m2m(op, src, tgt, reg, 0.3, 0.1), np.float64).ravel()
+    f64 = np.asarray(oracle.m2m(op, src, tgt, reg, 0.3, 0.1, f64=True), np.float64).ravel()
+    got = lib.M2S(op, src, tgt[0], reg, 0.3, 0.1)
+    assert dev.last_dispatch() == 1, "a 50k-source one-target call did not take the CUDA path"
+    assert_parity(got, want, f64, is_strict(op, reg), f"{op}/{reg} M2S 50k sources")
+    small = lib.M2S(op, src[:1000], tgt[0], reg, 0.3, 0.1)
+    assert dev.last_dispatch() == 0, "a 1000-source one-target call should stay in the host loop"
+    assert rel_l2(small, np.asarray(oracle.m2m(op, src[:1000], tgt, reg, 0.3, 0.1), np.float64).ravel()) <= TOL
+
+
+@pytest.mark.parametrize("op,reg", [c for c in op_cases() if not c[0].startswith("F3D")])
+def test_nan_coordinates_propagate_like_the_reference(gpu, oracle, op, reg):
+    """A NaN coordinate is not a coincident pair: the reference's exact-equality test lets the term through
+    (NaN != NaN, src/P3D.cpp:58,94,127, src/P2D.cpp:57,178), so a NaN source poisons every target and a NaN
+    target only itself.  The kernels' coincidence rule must do the same in both pair forms and at both
+    sizes of the optimistic switch (`r2 > 0` returned finite results here)."""
+    lib, dev = gpu
+    rng = np.random.default_rng(seed_of("nan", op, reg))
+    for n, m in ((6000, 700), (600, 300)):
+        src, tgt = make_case(op, rng, n, m, self_targets=True)
+        tgt = tgt.copy()
+        tgt[5, 0] = np.nan
+        with np.errstate(all="ignore"):
+            want = np.asarray(oracle.m2m(op, src, tgt, reg, 0.3, 0.1)).reshape(m, -1)
+        got = np.asarray(call_abi(lib, op, src, tgt, reg, 0.3, 0.1)).reshape(m, -1)
+        assert dev.last_dispatch() == 1
+        assert np.array_equal(np.isnan(got), np.isnan(want)), (op, reg, n, np.isnan(got).sum(), np.isnan(want).sum())
+        assert np.isnan(got[5]).any() and np.isfinite(np.delete(got, 5, axis=0)).all()
+        src2 = src.copy()
+        src2[n // 2, 1] = np.nan
+        with np.errstate(all="ignore"):
+            want = np.asarray(oracle.m2m(op, src2, tgt[:64], reg, 0.3, 0.1)).reshape(64, -1)
+        got = np.asarray(call_abi(lib, op, src2, np.ascontiguousarray(tgt[:64]), reg, 0.3, 0.1)).reshape(64, -1)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), (op, reg, n, "NaN source")
