@@ -22,6 +22,8 @@ point cloud, dvort targets are the particles themselves.  Seeds are fixed.
           bounded target sample of the same workload (all sources x 4096 strided targets).
   parity  the GPU results on those same 4096 targets against the reference's outputs and
           against the FP64 oracle (relative L2 per output array; N = 1 only).
+  inlib_multi_gpu  (N > 1) the same step from ONE process with all N accelerators enabled through the
+          reference's own cvtx_accelerator_enable: sharded upload + NCCL all-gather inside the library.
   extra   the other BASELINE configs and the north-star headline (cvtx_P3D_M2M_vel,
           Winckelmans, 1M) measured the same way at reduced step counts.
 
@@ -438,6 +440,51 @@ class Bench:
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / steps,
                 "api": "cvtx_*_M2M_* C ABI, host arrays of pointers; per rank when N > 1"}
 
+    # ---- ONE process, every GPU of the box, through the reference's ABI ------------------------
+    def inlib_multi_gpu(self, name, steps):
+        """What a C / Julia caller gets from one process: every accelerator switched on with the reference's own
+        cvtx_accelerator_enable, host arrays of pointers in, host arrays out.  Inside the library the sources
+        cross PCIe once in total (device g uploads rows [g n/G, (g+1) n/G)), the shards are all-gathered over
+        NCCL / NVLink, every device runs the pair kernel on its target shard.  Called on rank 0 only, between
+        two barriers, while the other ranks idle."""
+        from cvortex_b200.abi import PointerRows
+        n, m, ops = WORKLOADS[name]
+        n_acc = min(self.lib.num_accelerators(), self.world)
+        P, TP, X = make_inputs(n, m, ops)
+        srcs = PointerRows(P, P.shape[1])
+        host_t, host_o = {}, {}
+        for op, _ in ops:
+            rows = np.ascontiguousarray(TP if op in PARTICLE_TARGETS else X)
+            host_t[op] = PointerRows(rows, rows.shape[1]) if op in PARTICLE_TARGETS else rows
+            host_o[op] = np.empty((m, out_cols(op)), dtype=np.float32)
+
+        def step():
+            for op, reg in ops:
+                fn = getattr(self.lib, op)
+                if op.startswith("F3D"):
+                    fn(srcs, host_t[op], out=host_o[op])
+                elif op.endswith("visc_dvort"):
+                    fn(srcs, host_t[op], reg, SIGMA, NU, out=host_o[op])
+                else:
+                    fn(srcs, host_t[op], reg, SIGMA, out=host_o[op])
+                assert self.be.last_dispatch() == 1
+        try:
+            for k in range(n_acc):
+                self.lib.accelerator_enable(k)
+            step()
+            used = self.be.last_devices_used()
+            step()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            dt = time.perf_counter() - t0
+        finally:
+            self.api.use_only(self.local_rank)
+        return {"value": float(n) * m * len(ops) * steps / dt / 1e9, "unit": "Gpair/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
+                "devices_used": used, "exchange": self.be.exchange_backend(),
+                "api": "cvtx_*_M2M_* C ABI from ONE process, all accelerators enabled, host arrays of pointers; "
+                       "sharded upload + NCCL all-gather of the source rows inside libcvortex.so"}
+
     # ---- roofline of a measured workload ---------------------------------------------------
     def peaks(self):
         if not hasattr(self, "_peaks"):
@@ -555,6 +602,14 @@ def main():
 
     e2e = None if args.no_e2e else B.e2e(args.workload, args.steps)
 
+    # ---- the same workload from ONE process driving all N GPUs through the library (N > 1)
+    inlib = None
+    if world > 1 and not args.no_e2e:
+        B.barrier()
+        if rank == 0:
+            inlib = B.inlib_multi_gpu(args.workload, max(1, min(args.steps, 3)))
+        B.barrier()
+
     # ---- cpu_baseline + in-run parity on the same target sample (N = 1 only)
     cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
@@ -615,6 +670,7 @@ def main():
             "config": workload_config(args.workload, n, m, ops, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(main_launches),
             "roofline": B.roofline(main_kern), "cpu_baseline": cpu, "parity": parity, "fused_vel_dvort": fused,
+            "inlib_multi_gpu": inlib,
             "extra": extra,
         }
         print(json.dumps(line), flush=True)

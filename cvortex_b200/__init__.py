@@ -15,3 +15,6 @@ from . import _native  # noqa: F401
 
 __all__ = ["api", "abi", "device", "sharding"]
 __version__ = "0.3.8+b200.1"
+
+# In a Python process the NCCL that libcvortex.so opens at run time must be the one torch uses (see _native).
+_native.preload_python_nccl()

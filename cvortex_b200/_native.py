@@ -29,7 +29,30 @@ def build(jobs: int = 4, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def preload_python_nccl() -> None:
+    """libcvortex.so opens ``libnccl.so.2`` at run time, when a call first spans several devices.  In a Python
+    process that will also import torch, the NCCL that must win is the one torch was built against (the
+    ``nvidia-nccl`` wheel next to it): the loader keeps ONE library per soname, and a system NCCL loaded first
+    leaves torch with unresolved symbols (seen: ``ncclDevCommCreate``).  Loading the wheel's copy here, before
+    anything else asks for the soname, makes both use it.  No wheel -> nothing to do: C hosts get the system one."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        roots = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+    except (ImportError, ValueError):
+        roots = []
+    for root in roots:
+        path = os.path.join(root, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            try:
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load() -> C.CDLL:
+    preload_python_nccl()
     if not os.path.exists(LIB_PATH):
         raise NativeLibraryError(
             f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
