@@ -114,7 +114,7 @@ struct Plan { KernelChoice k; int grain, grid; long long tiles_t, total_grains; 
 // -- is cut into `grid` equal runs.  Every (geometry, grid) candidate is priced in microseconds:
 //   waves x ( prologue + pairs of a run / what a block gets of its SM )  +  the ordered finish of cut tiles
 // where a block's share of the SM depends on how many blocks are resident with it (4 warps alone keep the
-// FP32 pipe ~60 % busy, 8 and more 100 %) and a single resident set of co-resident blocks pays for the
+// FP32 pipe ~60 % busy, 8 warps 93 %, 16 and more 100 %) and a single resident set of co-resident blocks pays for the
 // uneven pace of the two (+30 %: the slower one finishes alone).  Large problems come out at the op's
 // preferred geometry with kRunsPerSlot runs per resident slot; small ones (10k x 10k: 100 us) at ONE run per
 // SM in a small-tile geometry, which is what an exhaustive sweep finds too (profiles/plan_sweep_r2.txt).
@@ -151,8 +151,11 @@ struct Planner {
 				const long long waves = (grid + resident - 1) / resident;
 				long long together = (grid + sm_count - 1) / sm_count;              // blocks that share an SM
 				if (together > k.occ) together = k.occ;
-				const double warps = (double)together * k.B / 32.0;
-				const double util = warps >= 8.0 ? 1.0 : (warps >= 4.0 ? 0.6 + 0.1 * (warps - 4.0) : 0.15 * warps);
+				// FP32-pipe utilisation by resident warps per SM (measured on the T = 4 / T = 2 geometries run with one
+				// block per SM, profiles/sweep_ops_r2.txt), relative to the geometry at its own full occupancy, which
+				// is what cand_eff and the TUNE constants were measured at
+				auto by_warps = [](double w) { return w >= 16.0 ? 1.0 : (w >= 12.0 ? 0.97 : (w >= 8.0 ? 0.93 : (w >= 4.0 ? 0.6 : 0.15 * w))); };
+				const double util = by_warps((double)together * k.B / 32.0) / by_warps((double)k.occ * k.B / 32.0);
 				const double uneven = (together >= 2 && waves == 1) ? 1.3 : 1.0;
 				const double run_us = (double)per_block * grain * (double)slots * (double)together * uneven / (sm_rate * cand_eff[v] * util);
 				const double pieces = (double)(grid + tiles_t - 1) / (double)tiles_t;      // runs that touch a cut tile

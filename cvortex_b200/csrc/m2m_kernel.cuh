@@ -125,8 +125,10 @@ __device__ __noinline__ void exact_subchain(const float *__restrict__ src_raw, l
 // evaluated stage by stage (more independent instructions in flight, more registers).
 // OPT (bit set): 1 = the FP64 accumulators live in shared memory instead of registers (T x NACC x 2 registers
 // handed back to the pair loop's schedule; one LDS.64 + DADD + STS.64 per sum and chain);
-// 2 = the pair loops are written `#pragma unroll 8` over the chain instead of an explicit 8-wide body.
-enum { M2M_SMEM_ACC = 1, M2M_PLAIN_LOOP = 2 };
+// 2 = the pair loops are written `#pragma unroll 8` over the chain instead of an explicit 8-wide body;
+// 4 = filament ops: the sub-chains a target's flag rejects are only marked (and their fast sums dropped) inside the
+// sub-chain loop; the reference-arithmetic re-evaluation -- an out-of-line call -- happens once per chain, after it.
+enum { M2M_SMEM_ACC = 1, M2M_PLAIN_LOOP = 2, M2M_DEFER_EXACT = 4 };
 // dynamic shared memory a launch of m2m_kernel<P, T, B, .., OPT> needs (beyond 48 KB in total the launcher has to
 // raise cudaFuncAttributeMaxDynamicSharedMemorySize first)
 template <class P, int T, int B, int OPT> constexpr size_t m2m_smem_bytes() { return (OPT & M2M_SMEM_ACC) ? sizeof(double) * T * P::NACC * B : 0; }
@@ -266,6 +268,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 #pragma unroll
 					for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
 				if constexpr (P::HYBRID) {
+					unsigned long long redo_mask = 0;                      // bit t * 8 + s: target slot t, sub-chain s of this chain
 #pragma unroll 1
 					for (int s0 = j0; s0 < j0 + G; s0 += F3D_SUB) {
 						Vec<W> sub[NV][P::NACC], flag[NV];
@@ -299,6 +302,19 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 						bool redo = false;
 #pragma unroll
 						for (int t = 0; t < T; ++t) redo |= !(flag[t / W].lane(t % W) > 0.0f);
+						if ((OPT & M2M_DEFER_EXACT) && redo) {
+							// mark (target slot, sub-chain) and drop the fast sums of the rejected slots
+							const int sidx = (s0 - j0) / F3D_SUB;
+#pragma unroll
+							for (int t = 0; t < T; ++t) {
+								if (!(flag[t / W].lane(t % W) > 0.0f)) {
+									redo_mask |= 1ull << (t * 8 + sidx);
+#pragma unroll
+									for (int c = 0; c < P::NACC; ++c) sub[t / W][c].set(t % W, 0.0f);
+								}
+							}
+							redo = false;
+						}
 						if (redo) {
 							const long js = (long)(gs / gps) * S + s0;
 							const long je = js + F3D_SUB < (long)args.n_src ? js + F3D_SUB : (long)args.n_src;
@@ -318,6 +334,35 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 						for (int v = 0; v < NV; ++v)
 #pragma unroll
 							for (int c = 0; c < P::NACC; ++c) acc[v][c] = vadd(acc[v][c], sub[v][c]);
+					}
+					if ((OPT & M2M_DEFER_EXACT) && redo_mask) {
+						// the rejected sub-chains of this chain in the reference's own arithmetic, in source order
+#pragma unroll 1
+						for (int t = 0; t < T; ++t) {
+							const unsigned bits = (unsigned)(redo_mask >> (t * 8)) & 0xffu;
+							if (!bits) continue;
+							long i = (long)tt * (B * T) + tid + (long)t * B;
+							i = i < args.n_tgt ? i : (long)args.n_tgt - 1;
+							float add[P::NACC];
+#pragma unroll
+							for (int c = 0; c < P::NACC; ++c) add[c] = 0.0f;
+							for (int sidx = 0; sidx < G / F3D_SUB; ++sidx) {
+								if (!((bits >> sidx) & 1u)) continue;
+								const long js = (long)(gs / gps) * S + j0 + sidx * F3D_SUB;
+								const long je = js + F3D_SUB < (long)args.n_src ? js + F3D_SUB : (long)args.n_src;
+								float e[P::NACC];
+								exact_subchain<P>(args.src_raw, js, je, args.tgt + i * P::TCOLS, e);
+#pragma unroll
+								for (int c = 0; c < P::NACC; ++c) add[c] = __fadd_rn(add[c], e[c]);
+							}
+							// (dynamic t: one select per slot instead of a register-indexed write)
+#pragma unroll
+							for (int tt2 = 0; tt2 < T; ++tt2)
+								if (tt2 == t) {
+#pragma unroll
+									for (int c = 0; c < P::NACC; ++c) acc[tt2 / W][c].set(tt2 % W, __fadd_rn(acc[tt2 / W][c].lane(tt2 % W), add[c]));
+								}
+						}
 					}
 				} else {
 					bool guarded = true;

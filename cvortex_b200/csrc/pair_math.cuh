@@ -904,8 +904,9 @@ struct F3DVel {
 	static constexpr int NSRC4 = 3, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 34, SFU_OPS = 3;           // of fast<W, F3D_NEW>; the F3D_REF form: 44 / 3
 	static constexpr bool OPTIMISTIC = false, HYBRID = true;
-	// TUNE (profiles/kernel_ab_f3d_r2.txt): 4 targets per thread, 845 against 828 Gpair/s with 8
-	static constexpr int VW8 = 8, OPT8 = 1, VW4 = 4, OPT4 = 1;
+	// TUNE (profiles/kernel_ab_f3d_r2.txt): 4 targets per thread, 850 against 840 Gpair/s with 8; 5 = shared-memory
+	// accumulators + the reference-arithmetic tier once per chain (M2M_DEFER_EXACT)
+	static constexpr int VW8 = 8, OPT8 = 5, VW4 = 2, OPT4 = 5;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 
 	template <int W, int MODE> CVTX_HD static void fast(const Vec<W> *tg, const f4 a, const f4 b, const f4 c, Vec<W> *acc,
@@ -986,8 +987,8 @@ struct F3DDvort {
 	static constexpr int NSRC4 = 3, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 4;
 	static constexpr int LANE_OPS = 41, SFU_OPS = 4;           // of fast<W, F3D_NEW>; the F3D_REF form: 46 / 3
 	static constexpr bool OPTIMISTIC = false, HYBRID = true;
-	// TUNE (profiles/kernel_ab_f3d_r2.txt): 4 targets per thread, 696 against 655 Gpair/s with 8
-	static constexpr int VW8 = 8, OPT8 = 1, VW4 = 2, OPT4 = 1;
+	// TUNE (profiles/kernel_ab_f3d_r2.txt): 4 targets per thread, 705 against 672 Gpair/s with 8
+	static constexpr int VW8 = 8, OPT8 = 5, VW4 = 2, OPT4 = 5;
 	CVTX_HD static void load_target(const float *row, float *tg) { tg[0] = row[0]; tg[1] = row[1]; tg[2] = row[2]; }
 
 	template <int W, int MODE> CVTX_HD static void fast(const Vec<W> *tg, const f4 a, const f4 b, const f4 c, Vec<W> *acc,

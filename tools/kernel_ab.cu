@@ -168,8 +168,14 @@ static void sweep(Ctx &c, const char *name, int chunks) {
 template <class P>
 static void sweep_f3d(Ctx &c, const char *name) {
 #ifdef F3D_QUICK
-	run_new<P, 4, 256, 2, 2, 0, 256>(c, name, 4);
+	run_new<P, 4, 256, 2, 2, 1, 256>(c, name, 4);
+	run_new<P, 4, 256, 2, 2, 5, 256>(c, name, 4);
+	run_new<P, 4, 256, 2, 4, 1, 256>(c, name, 4);
+	run_new<P, 4, 256, 2, 4, 5, 256>(c, name, 4);
 	run_new<P, 8, 128, 2, 8, 1, 256>(c, name, 4);
+	run_new<P, 8, 128, 2, 8, 5, 256>(c, name, 4);
+	run_new<P, 2, 256, 3, 2, 1, 256>(c, name, 4);
+	run_new<P, 2, 256, 3, 2, 5, 256>(c, name, 4);
 	return;
 #endif
 #define ROW(T, B, VW) run_new<P, T, B, 2, VW, 0, 256>(c, name, 4); run_new<P, T, B, 2, VW, 1, 256>(c, name, 4);
