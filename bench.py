@@ -305,6 +305,9 @@ class Bench:
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.dev)
+            # a host-side group for waits that must leave the GPUs alone (an NCCL barrier is a kernel that spins
+            # on every waiting rank's GPU; without MPS it takes every other time slice from another process's work there)
+            self.cpu_group = dist.new_group(backend="gloo")
         api.initialise(require_gpu=True)
         api.use_only(self.local_rank)
         self.be, self.lib = api.backend(), api.library()
@@ -315,6 +318,12 @@ class Bench:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        """Rendezvous on the host only: nothing is launched on any GPU while ranks wait here."""
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, x, op="max"):
         if self.world == 1:
@@ -446,7 +455,7 @@ class Bench:
         cvtx_accelerator_enable, host arrays of pointers in, host arrays out.  Inside the library the sources
         cross PCIe once in total (device g uploads rows [g n/G, (g+1) n/G)), the shards are all-gathered over
         NCCL / NVLink, every device runs the pair kernel on its target shard.  Called on rank 0 only, between
-        two barriers, while the other ranks idle."""
+        two host-side barriers, while the other ranks idle with nothing queued on their GPUs."""
         from cvortex_b200.abi import PointerRows
         n, m, ops = WORKLOADS[name]
         n_acc = min(self.lib.num_accelerators(), self.world)
@@ -606,9 +615,10 @@ def main():
     inlib = None
     if world > 1 and not args.no_e2e:
         B.barrier()
+        B.host_barrier()
         if rank == 0:
             inlib = B.inlib_multi_gpu(args.workload, max(1, min(args.steps, 3)))
-        B.barrier()
+        B.host_barrier()                 # the other ranks wait on the host: their GPUs are rank 0's for this measurement
 
     # ---- cpu_baseline + in-run parity on the same target sample (N = 1 only)
     cpu, parity = None, None
