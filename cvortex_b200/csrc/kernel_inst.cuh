@@ -26,8 +26,12 @@ KernelChoice choice_of(int device) {
 template <class P> KernelChoice choice(int v, bool grain256, int device) {
 	if (v == 0) return grain256 ? choice_of<P, 8, 128, 2, P::VW8, P::OPT8, 256>(device) : choice_of<P, 8, 128, 2, P::VW8, P::OPT8, 0>(device);
 	if (v == 1) return grain256 ? choice_of<P, 4, 256, 2, P::VW4, P::OPT4, 256>(device) : choice_of<P, 4, 256, 2, P::VW4, P::OPT4, 0>(device);
-	if (v == 2) return choice_of<P, 2, 256, 3, 2, 0, 0>(device);
-	return choice_of<P, 1, 128, 8, 1, 0, 0>(device);
+	// (the filament ops evaluate their reference-arithmetic tier once per chain in EVERY geometry: where it is added
+	// decides the FP32 rounding of a flagged target's chain, and a result may not depend on the geometry)
+	constexpr int SMALL = P::HYBRID ? M2M_DEFER_EXACT : 0;
+	static_assert(!P::HYBRID || ((P::OPT8 & M2M_DEFER_EXACT) && (P::OPT4 & M2M_DEFER_EXACT)), "filament geometries must agree on the tier order");
+	if (v == 2) return choice_of<P, 2, 256, 3, 2, SMALL, 0>(device);
+	return choice_of<P, 1, 128, 8, 1, SMALL, 0>(device);
 }
 
 template <template <int> class POLICY> KernelChoice choice_by_reg(int reg, int v, bool grain256, int device) {

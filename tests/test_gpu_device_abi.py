@@ -352,3 +352,19 @@ def test_points_on_a_filament_axis_get_the_reference_bits(gpu, oracle, op, mode)
                 assert np.array_equal(got == 0, want == 0)
     finally:
         dev.f3d_mode(-1)
+
+
+@pytest.mark.parametrize("op,reg", op_cases() + vort_cases())
+def test_a_target_alone_gets_the_bits_it_gets_in_a_crowd(gpu, oracle, op, reg):
+    """Few-target calls take other geometries, other grids, in-kernel packing and the ordered finish as a kernel
+    of its own (finish_pieces_kernel); a target's result may not depend on any of that: one target alone, the same
+    target among 7 and among 3000, on both sides of the small-source switch."""
+    _, dev = gpu
+    base = "P3D_M2M_vel" if op == "P3D_M2M_vort" else op
+    for n in (100_000, 5000):
+        rng = np.random.default_rng(n)
+        src, tgt = make_case(base, rng, n, 3000, self_targets=True)
+        crowd, _, _ = dev.m2m_host(op, reg, 0, src, tgt, 0.05, 0.2)
+        for m in (1, 7, 33):
+            few, _, _ = dev.m2m_host(op, reg, 0, src, np.ascontiguousarray(tgt[:m]), 0.05, 0.2)
+            assert np.array_equal(few.view(np.uint32), crowd[:m].view(np.uint32)), (op, reg, n, m, np.abs(few - crowd[:m]).max())
