@@ -633,7 +633,7 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
 		CUDA_TRY(cudaSetDevice(devices[g]));
 		CUDA_TRY(cudaStreamSynchronize(streams[g]));
-		if (hi > lo) std::memcpy((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
+		if (hi > lo) copy_parallel((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
 	}
 	if (h2d_bytes) *h2d_bytes = up;
 	if (d2h_bytes) *d2h_bytes = down;

@@ -95,7 +95,7 @@ namespace {
 	if (n == 0) {
 		const char *env = std::getenv("CVTX_B200_GATHER_THREADS");
 		n = env ? std::atoi(env) : 0;
-		if (n <= 0) { n = omp_get_num_procs(); if (n > 4) n = 4; }
+		if (n <= 0) { n = omp_get_num_procs(); if (n > 8) n = 8; }
 		if (n < 1) n = 1;
 	}
 	return n;
@@ -118,6 +118,10 @@ void copy_rows(void *dst, const void *src, long n, size_t row_bytes) {
 		std::memcpy((char *)dst + lo, (const char *)src + lo, len);
 	}
 }
+
+}  // namespace
+void cvtx::copy_parallel(void *dst, const void *src, size_t bytes) { copy_rows(dst, src, 1, bytes); }
+namespace {
 
 // What a failure on the GPU route does.  Default: message + abort -- a CPU result is never substituted
 // silently.  CVTX_B200_ON_FAILURE=host (read once) is the opt-in for hosts that would rather lose speed than the

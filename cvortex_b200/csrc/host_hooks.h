@@ -9,6 +9,7 @@ namespace cvtx {
 std::vector<int> enabled_accelerators();                     // devices the caller has switched on
 void note_dispatch(int on_gpu, int n_devices);               // feeds cvtx_b200_last_dispatch()
 void gather_rows(void *dst, const void *const *ptrs, long n, size_t row_bytes);
+void copy_parallel(void *dst, const void *src, size_t bytes);   // memcpy in 1 MB pieces over the gather threads
 // One-target (M2S) calls: the reference evaluates them in a SERIAL loop over the sources
 // (src/P3D.cpp:230-322, src/P2D.cpp:99-119,214-231, src/F3D.cpp:87-128).  From kM2SMinSources sources up,
 // with an accelerator enabled and a built-in regularisation, they are the all-pairs kernel with one

@@ -79,3 +79,34 @@ def test_sharded_sources_are_all_gathered_inside_the_library(gpu, oracle, torch_
     print(f"{G} device(s); exchange backend: {backend}")
     if G > 1:
         assert "nccl" in backend or "peer" in backend
+
+
+def test_the_enabled_set_can_change_between_calls(gpu, oracle):
+    """cvtx_accelerator_enable / disable between calls ("re-create the communicator lazily"): every
+    subset of devices returns the single-device bits, in any order of switching, and finalise / initialise in
+    between starts over cleanly."""
+    lib, dev = gpu
+    n_acc = lib.num_accelerators()
+    if n_acc < 2:
+        pytest.skip("one GPU on this box")
+    rng = np.random.default_rng(5)
+    n, m = 90_000, 40_000
+    P = particles3d(rng, n, vol=0.01)
+    one = lib.P3D_M2M_visc_dvort(P, P[:m], "winckelmans", 0.02, 1.0)
+    assert dev.last_devices_used() == 1
+    try:
+        for subset in ([0, 1], list(range(n_acc)), [n_acc - 1], [1, 0][:2], list(range(0, n_acc, 2)) or [0]):
+            for k in range(n_acc):
+                (lib.accelerator_enable if k in subset else lib.accelerator_disable)(k)
+            got = lib.P3D_M2M_visc_dvort(P, P[:m], "winckelmans", 0.02, 1.0)
+            assert dev.last_dispatch() == 1 and dev.last_devices_used() == len(set(subset)), (subset, dev.last_devices_used())
+            assert np.array_equal(got, one), subset
+        lib.finalise()
+        lib.initialise()
+        for k in range(n_acc):
+            lib.accelerator_enable(k)
+        got = lib.P3D_M2M_visc_dvort(P, P[:m], "winckelmans", 0.02, 1.0)
+        assert np.array_equal(got, one)
+    finally:
+        for k in range(n_acc):
+            (lib.accelerator_enable if k == 0 else lib.accelerator_disable)(k)
