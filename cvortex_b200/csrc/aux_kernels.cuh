@@ -26,9 +26,13 @@ __global__ void __launch_bounds__(256) finish_pieces_kernel(const double *__rest
 	if (i >= n_tgt) return;
 	const long long b_first = run_of(tt * gpt, R, total_grains), b_last = run_of((tt + 1) * gpt - 1, R, total_grains);
 	if (b_first == b_last) return;                                                       // one run covered the tile and wrote it
+	// (only the first run can have entered the tile from the one before it: every later run starts inside it --
+	// one 128-bit division per warp instead of one per piece)
+	const long long first_sl = 2 * b_first + (run_begin(b_first, R, total_grains) / gpt == tt ? 0 : 1);
 	double s = 0.0;
+#pragma unroll 4
 	for (long long bb = b_first + lane; bb <= b_last; bb += 32) {
-		const long long sl = 2 * bb + (run_begin(bb, R, total_grains) / gpt == tt ? 0 : 1);
+		const long long sl = bb == b_first ? first_sl : 2 * bb;
 		s += __ldcg(pieces + (size_t)sl * per_tile + v);
 	}
 	for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);

@@ -140,8 +140,13 @@ struct Planner {
 			const long long resident = (long long)sm_count * k.occ;
 			long long mult = total / (resident * kMinRunGrains);
 			mult = mult < 1 ? 1 : (mult > kRunsPerSlot ? kRunsPerSlot : mult);
-			const long long cand_grid[3] = {resident * mult, (long long)sm_count, 2LL * sm_count};
-			for (int gi = 0; gi < 3; ++gi) {
+			// a step = one source tile against one target tile.  However few of a block's target slots are real, the
+			// warps that have one walk the tile's 256 sources one after the other and the tile has to arrive first:
+			// ~7 us for one target per thread (profiles/few_sweep_r2.txt), more with more targets per thread
+			const long long gps = kSrcTile / grain;
+			const double step_floor_us = 2.5 + 4.5 * (double)k.T * (double)P::LANE_OPS / 21.0;
+			const long long cand_grid[5] = {resident * mult, (long long)sm_count, 2LL * sm_count, 4LL * sm_count, 8LL * sm_count};
+			for (int gi = 0; gi < 5; ++gi) {
 				long long grid = cand_grid[gi];
 				if (fG > 0) grid = fG;
 				if (grid > total) grid = total;
@@ -157,10 +162,13 @@ struct Planner {
 				auto by_warps = [](double w) { return w >= 16.0 ? 1.0 : (w >= 12.0 ? 0.97 : (w >= 8.0 ? 0.93 : (w >= 4.0 ? 0.6 : 0.15 * w))); };
 				const double util = by_warps((double)together * k.B / 32.0) / by_warps((double)k.occ * k.B / 32.0);
 				const double uneven = (together >= 2 && waves == 1) ? 1.3 : 1.0;
-				const double run_us = (double)per_block * grain * (double)slots * (double)together * uneven / (sm_rate * cand_eff[v] * util);
+				double run_us = (double)per_block * grain * (double)slots * (double)together * uneven / (sm_rate * cand_eff[v] * util);
+				const double steps = (double)((per_block + gps - 1) / gps);
+				if (run_us < steps * step_floor_us) run_us = steps * step_floor_us;
 				const double pieces = (double)(grid + tiles_t - 1) / (double)tiles_t;      // runs that touch a cut tile
 				const double finish_us = grid <= tiles_t ? 0.0 : (pieces > kInKernelFinishPieces ? 12.0 : 2.0 + 0.4 * pieces);
-				const double cost = (double)waves * (3.0 + run_us) + finish_us;
+				// + what every run costs whatever it does (block launch and retirement, its FP64 piece): 30 ns
+				const double cost = (double)waves * (3.0 + run_us) + finish_us + 0.03 * (double)grid;
 				if (cost < best) {
 					best = cost;
 					plan.k = k; plan.grain = grain; plan.grid = (int)grid; plan.tiles_t = tiles_t; plan.total_grains = total;

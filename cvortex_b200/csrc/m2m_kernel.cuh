@@ -505,9 +505,11 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 						for (int t = 0; t < TB; ++t)
 #pragma unroll
 							for (int c = 0; c < P::NOUT; ++c) sum[t][c] = 0.0;
+						// (only the first run can have entered the tile from the one before it: every later run starts inside it)
+						const long long first_sl = 2 * b_first + (run_begin(b_first, R, args.total_grains) / gpt == tt ? 0 : 1);
 #pragma unroll 2
 						for (long long bb = b_first; bb <= b_last; ++bb) {
-							const long long sl = 2 * bb + (run_begin(bb, R, args.total_grains) / gpt == tt ? 0 : 1);
+							const long long sl = bb == b_first ? first_sl : 2 * bb;
 							const double *pc = args.pieces + (size_t)sl * (T * B * P::NOUT) + ((size_t)t0 * B + tid) * P::NOUT;
 #pragma unroll
 							for (int t = 0; t < TB; ++t)
