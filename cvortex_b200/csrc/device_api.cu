@@ -107,6 +107,7 @@ constexpr int kSmallSourceTiles = 64;
 constexpr int kRunsPerSlot = 4;
 constexpr int kMinRunGrains = 24;
 constexpr int kInKernelFinishPieces = 48;
+constexpr size_t kZeroCopyResultBytes = 512u << 10;      // results up to this size are stored to pinned host memory by the kernel
 
 struct Plan { KernelChoice k; int grain, grid; long long tiles_t, total_grains; };
 
@@ -630,11 +631,15 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
 		if (hi == lo) continue;
 		Device *d = get_device(devices[g]);
+		// small results are written by the kernel straight into the pinned staging area (unified addressing: the
+		// host pointer is valid on the device): the D2H copy of a 10k x 10k call costs as much as a tenth of its kernel
+		const bool zero_copy = orow * (size_t)(hi - lo) <= kZeroCopyResultBytes;
+		float *result = zero_copy ? (float *)((char *)hs.out.p + orow * lo) : (float *)d->d_out.p;
 		if (int rc = cvtx_b200_m2m(op, reg, devices[g], streams[g], (const float *)d->d_src.p, n_src,
-		                           (const float *)d->d_tgt.p, (int)(hi - lo), (float *)d->d_out.p, sigma, nu))
+		                           (const float *)d->d_tgt.p, (int)(hi - lo), result, sigma, nu))
 			return rc;
 		CUDA_TRY(cudaSetDevice(devices[g]));
-		CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo), cudaMemcpyDeviceToHost, streams[g]));
+		if (!zero_copy) CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo), cudaMemcpyDeviceToHost, streams[g]));
 		down += orow * (size_t)(hi - lo);
 	}
 	for (int g = 0; g < G; ++g) {
