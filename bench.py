@@ -25,7 +25,8 @@ point cloud, dvort targets are the particles themselves.  Seeds are fixed.
   inlib_multi_gpu  (N > 1) the same step from ONE process with all N accelerators enabled through the
           reference's own cvtx_accelerator_enable: sharded upload + NCCL all-gather inside the library.
   extra   the other BASELINE configs and the north-star headline (cvtx_P3D_M2M_vel,
-          Winckelmans, 1M) measured the same way at reduced step counts.
+          Winckelmans, 1M) measured the same way at reduced step counts, each with its own parity
+          sample (512 stride-sampled targets against all sources; N = 1 only).
 
 With N > 1 the targets are sharded over the ranks (total work fixed: "strong" scaling).
 `--impl reference` times the unmodified reference CPU path instead (rank 0 only).
@@ -49,6 +50,7 @@ if ROOT not in sys.path:
 
 SIGMA, NU = 0.02, 1.0
 CPU_SAMPLE_TARGETS = 4096            # all N sources x M' = 4096 stride-sampled targets, both CPU legs
+CPU_EXTRA_SAMPLE_TARGETS = 512       # the parity sample of the `extra` configs (4M sources x 512 targets = 2e9 pairs per op on the CPU)
 WORKLOADS = {
     # name: (n sources, n targets, [(op, reg)])      -- BASELINE.json configs[0..4] + the north-star headline
     "p3d_vel_winckelmans_10k": (10_000, 10_000, [("P3D_M2M_vel", "winckelmans")]),                                   # configs[0]
@@ -554,6 +556,28 @@ class Bench:
         }
 
 
+def parity_sample(torch, dev, ref, outs):
+    """The GPU results of a workload (full device-resident outputs of its last step) on the reference leg's own
+    target sample, against the reference's outputs (already computed by ref.pass_()) and against the FP64 oracle."""
+    idx_t = torch.from_numpy(ref.idx).to(dev)
+    parity = {"targets": int(len(ref.idx)), "sample": "all sources x stride-sampled targets, the same sample the CPU leg ran",
+              "tolerance": 1e-5, "per_op": {}}
+    worst_ref, worst_f64 = 0.0, 0.0
+    for op, reg in ref.ops:
+        got = outs[op][idx_t].cpu().numpy().reshape(len(ref.idx), -1)
+        f64 = ref.f64(op, reg)
+        e_ref, e_f64, r_f64 = rel_l2(got, ref.outputs[op]), rel_l2(got, f64), rel_l2(ref.outputs[op], f64)
+        parity["per_op"][f"{op}/{reg}"] = {"rel_l2_vs_ref": e_ref, "rel_l2_vs_f64": e_f64, "ref_rel_l2_vs_f64": r_f64,
+                                           "finite": bool(np.all(np.isfinite(got)))}
+        worst_ref, worst_f64 = max(worst_ref, e_ref), max(worst_f64, e_f64)
+    parity["rel_l2_vs_ref"], parity["rel_l2_vs_f64"] = worst_ref, worst_f64
+    # within tolerance of the reference, or -- where the FP32 reference is itself further than that from FP64
+    # (filaments with short segments) -- at least as close to FP64 as the reference is
+    parity["ok"] = bool(all(v["finite"] and (v["rel_l2_vs_ref"] <= 1e-5 or v["rel_l2_vs_f64"] <= 1.1 * v["ref_rel_l2_vs_f64"] + 5e-7)
+                            for v in parity["per_op"].values()))
+    return parity
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -629,19 +653,7 @@ def main():
         secs = ref.pass_()
         cpu = {"value": ref.pairs / secs / 1e9, "unit": "Gpair/s", "cores": ref.cores, "kind": ref.kind,
                "sample": ref.describe(secs)}
-        idx_t = torch.from_numpy(ref.idx).to(B.dev)
-        parity = {"targets": int(len(ref.idx)), "sample": "the cpu_baseline's targets: all sources x stride-sampled targets",
-                  "tolerance": 1e-5, "per_op": {}}
-        worst_ref, worst_f64 = 0.0, 0.0
-        for op, reg in ops:
-            got = main_res["outs"][op][idx_t].cpu().numpy().reshape(len(ref.idx), -1)
-            f64 = ref.f64(op, reg)
-            e_ref, e_f64, r_f64 = rel_l2(got, ref.outputs[op]), rel_l2(got, f64), rel_l2(ref.outputs[op], f64)
-            parity["per_op"][f"{op}/{reg}"] = {"rel_l2_vs_ref": e_ref, "rel_l2_vs_f64": e_f64, "ref_rel_l2_vs_f64": r_f64,
-                                               "finite": bool(np.all(np.isfinite(got)))}
-            worst_ref, worst_f64 = max(worst_ref, e_ref), max(worst_f64, e_f64)
-        parity["rel_l2_vs_ref"], parity["rel_l2_vs_f64"] = worst_ref, worst_f64
-        parity["ok"] = bool(worst_ref <= 1e-5 and all(v["finite"] for v in parity["per_op"].values()))
+        parity = parity_sample(torch, B.dev, ref, main_res["outs"])
         del ref
     main_kern = main_res["kern"]
     main_launches = main_res["launches"]
@@ -661,13 +673,23 @@ def main():
         for name, steps, warm, wfrac, with_e2e in plan:
             if name == args.workload:
                 continue
-            r = B.resident(name, steps, warm, warm_fraction=wfrac)
+            want_parity = world == 1 and not args.no_cpu_baseline
+            r = B.resident(name, steps, warm, warm_fraction=wfrac, keep_outputs=want_parity)
             e = B.e2e(name, steps) if (with_e2e and not args.no_e2e) else None
             if r is None:
                 continue
             entry = {"value": r["value"], "unit": "Gpair/s", "ms_per_step": r["ms_per_step"], "steps": steps, "n_gpus": r["n_gpus"],
                      "config": workload_config(name, *WORKLOADS[name], world=r["n_gpus"]),
                      "kernels": B.kernel_fractions(r["kern"]) if rank == 0 else None, "e2e": e}
+            if want_parity:
+                # a smaller sample than the headline's 4096 targets: the 4M-source configs cost the CPU 4 ns per pair
+                en, em, eops = WORKLOADS[name]
+                xref = ReferenceCpu(en, em, eops, CPU_EXTRA_SAMPLE_TARGETS if en >= 100_000 else em)
+                xref.pass_()
+                entry["parity"] = parity_sample(torch, B.dev, xref, r["outs"])
+                del xref
+                for k in ("outs", "tgts", "src_local", "sharded"):
+                    r.pop(k, None)
             if wfrac < 1.0:
                 entry["warmup_note"] = f"{warm} warm-up passes on 1/{int(round(1 / wfrac))} of this rank's targets (a full pass takes ~10 s)"
             extra[name] = entry
