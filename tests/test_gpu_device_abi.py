@@ -368,3 +368,30 @@ def test_a_target_alone_gets_the_bits_it_gets_in_a_crowd(gpu, oracle, op, reg):
         for m in (1, 7, 33):
             few, _, _ = dev.m2m_host(op, reg, 0, src, np.ascontiguousarray(tgt[:m]), 0.05, 0.2)
             assert np.array_equal(few.view(np.uint32), crowd[:m].view(np.uint32)), (op, reg, n, m, np.abs(few - crowd[:m]).max())
+
+
+def test_unaligned_source_rows_give_the_same_bits(gpu, torch_cuda):
+    """Small source sets are packed inside the pair kernel from the caller's raw rows (M2MArgs::direct), which need
+    not be 16-byte aligned: same bits at every alignment, also for a last tile that is not full."""
+    torch = torch_cuda
+    _, dev = gpu
+    rng = np.random.default_rng(77)
+    st = torch.cuda.current_stream().cuda_stream
+    for op, reg, cols, tcols in (("P3D_M2M_vel", "winckelmans", 7, 3), ("P2D_M2M_vel", "gaussian", 4, 2), ("P3D_M2M_dvort", "gaussian", 7, 7)):
+        for n in (1, 3, 255, 257, 5001, 9999):
+            m = 700
+            P = rng.uniform(0, 10, (n, cols)).astype(np.float32)
+            X = rng.uniform(0, 10, (m, tcols)).astype(np.float32)
+            aligned = torch.from_numpy(P).cuda()
+            store = torch.empty(n * cols + 8, dtype=torch.float32, device="cuda")
+            outs = []
+            for shift in (0, 1, 2, 3):
+                view = store[shift:shift + n * cols].view(n, cols)
+                view.copy_(aligned)
+                out = torch.full((m, 3 if cols == 7 else 2), float("nan"), device="cuda")
+                dev.m2m(op, reg, 0, st, view, n, torch.from_numpy(X).cuda(), m, out, 0.05, 0.0)
+                torch.cuda.synchronize()
+                outs.append(out.cpu().numpy())
+            for o in outs[1:]:
+                assert np.array_equal(o.view(np.uint32), outs[0].view(np.uint32)), (op, reg, n)
+            assert np.all(np.isfinite(outs[0]))
