@@ -233,6 +233,23 @@ int main(int argc, char **argv) {
 	CK(cudaMemset(c.C, 0, sizeof(float4) * n));
 	CK(cudaMemcpy(c.tgt, ht.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
 
+	if (c.filter && strstr(c.filter, "guards")) {
+		// the ops whose coincident-pair guard is a real selection, in their tuned instances (A/B of pair_math.cuh's
+		// CVTX_GUARD_BY_MASK: build this tool once with -DCVTX_GUARD_BY_MASK=0 and once with =1)
+		c.filter = nullptr;
+		run_new<P3DVisc<REG_WINCKELMANS>, 8, 128, 2, 8, 1, 256>(c, "visc-winckelmans", 4);
+		run_new<P3DVisc<REG_GAUSSIAN>, 4, 256, 2, 2, 1, 256>(c, "visc-gaussian", 4);
+		run_new<P3DVisc<REG_GAUSSIAN>, 8, 128, 2, 2, 1, 256>(c, "visc-gaussian", 4);
+		run_new<P2DVisc<REG_GAUSSIAN>, 8, 128, 2, 2, 0, 256>(c, "p2dvisc-gaussian", 4);
+		run_new<P2DVisc<REG_GAUSSIAN>, 4, 256, 2, 2, 1, 256>(c, "p2dvisc-gaussian", 4);
+		run_new<P2DVisc<REG_WINCKELMANS>, 4, 256, 2, 2, 0, 256>(c, "p2dvisc-winckelmans", 4);
+		run_new<P2DVisc<REG_WINCKELMANS>, 8, 128, 2, 8, 0, 256>(c, "p2dvisc-winckelmans", 4);
+		run_new<P3DDvort<REG_WINCKELMANS>, 4, 256, 2, 2, 1, 256>(c, "dvort-winckelmans", 4);
+		run_new<P3DDvort<REG_WINCKELMANS>, 8, 128, 2, 8, 0, 256>(c, "dvort-winckelmans", 4);
+		run_new<P3DVelDvort<REG_WINCKELMANS>, 4, 256, 2, 2, 1, 256>(c, "veldvort-winckelmans", 4);
+		printf("done\n");
+		return 0;
+	}
 	if (c.filter && strstr(c.filter, "f3d")) {
 		// filaments: start uniform in the box, end = start + U(-0.1, 0.1)^3, packed on the host
 		std::vector<float> rows((size_t)n * 7);
