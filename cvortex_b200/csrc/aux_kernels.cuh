@@ -39,6 +39,89 @@ __global__ void __launch_bounds__(256) finish_pieces_kernel(const double *__rest
 	if (lane == 0) out[i * nout + c] = (float)s;
 }
 
+// ---- box-cutoff ops on spatially coherent orders (m2m_kernel.cuh, sparse_tiles_kernel) ----------------------
+// Bounding box of the REAL records of every packed source tile (NaN coordinates are ignored: such a source is outside
+// every cutoff cube, as in the reference).  box[tile] = {lo x, y, z, hi x, y, z}; an empty tile gets an inverted box.
+__global__ void __launch_bounds__(kSrcTile) source_tile_boxes_kernel(const float4 *__restrict__ A, int n_src, float *__restrict__ box)
+{
+	__shared__ float part[kSrcTile / 32][6];
+	const int i = blockIdx.x * kSrcTile + threadIdx.x;
+	const float big = 3.0e38f;
+	float v[6] = {big, big, big, -big, -big, -big};
+	if (i < n_src) {
+		const float4 a = A[i];
+		v[0] = v[3] = a.x; v[1] = v[4] = a.y; v[2] = v[5] = a.z;
+		for (int d = 0; d < 3; ++d) if (!(v[d] == v[d])) { v[d] = big; v[3 + d] = -big; }
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		for (int d = 0; d < 3; ++d) {
+			v[d] = fminf(v[d], __shfl_down_sync(0xffffffffu, v[d], o));
+			v[3 + d] = fmaxf(v[3 + d], __shfl_down_sync(0xffffffffu, v[3 + d], o));
+		}
+	if ((threadIdx.x & 31) == 0) for (int d = 0; d < 6; ++d) part[threadIdx.x >> 5][d] = v[d];
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		float r = part[0][threadIdx.x];
+		for (int k = 1; k < kSrcTile / 32; ++k) r = threadIdx.x < 3 ? fminf(r, part[k][threadIdx.x]) : fmaxf(r, part[k][threadIdx.x]);
+		box[(size_t)blockIdx.x * 6 + threadIdx.x] = r;
+	}
+}
+
+// One block per target tile of `slots` consecutive targets: its bounding box, then for every source tile whether the
+// two boxes come closer than the cutoff on all three axes (in double: never drops a tile that holds a pair with
+// |d| < cutoff); bit s of mask[tile][s / 32].  *active counts the marked pairs over all target tiles.
+__global__ void __launch_bounds__(256) target_tile_masks_kernel(const float *__restrict__ tgt, int tcols, int n_tgt, int slots,
+                                                                const float *__restrict__ src_box, int n_src_tiles, float cutoff,
+                                                                unsigned *__restrict__ mask, int words, unsigned long long *__restrict__ active)
+{
+	__shared__ float part[8][6];
+	__shared__ float tb[6];
+	__shared__ unsigned s_count[8];
+	const int tid = threadIdx.x;
+	const long first = (long)blockIdx.x * slots;
+	const float big = 3.0e38f;
+	float v[6] = {big, big, big, -big, -big, -big};
+	for (long i = first + tid; i < first + slots && i < n_tgt; i += 256)
+		for (int d = 0; d < 3; ++d) {
+			const float x = tgt[i * tcols + d];
+			if (x == x) { v[d] = fminf(v[d], x); v[3 + d] = fmaxf(v[3 + d], x); }
+		}
+	for (int o = 16; o > 0; o >>= 1)
+		for (int d = 0; d < 3; ++d) {
+			v[d] = fminf(v[d], __shfl_down_sync(0xffffffffu, v[d], o));
+			v[3 + d] = fmaxf(v[3 + d], __shfl_down_sync(0xffffffffu, v[3 + d], o));
+		}
+	if ((tid & 31) == 0) for (int d = 0; d < 6; ++d) part[tid >> 5][d] = v[d];
+	__syncthreads();
+	if (tid < 6) {
+		float r = part[0][tid];
+		for (int k = 1; k < 8; ++k) r = tid < 3 ? fminf(r, part[k][tid]) : fmaxf(r, part[k][tid]);
+		tb[tid] = r;
+	}
+	__syncthreads();
+	const double c = (double)cutoff * (1.0 + 1e-6);
+	unsigned mine = 0;
+	for (int w0 = 0; w0 < words * 32; w0 += 256) {
+		const int s = w0 + tid;
+		bool meet = false;
+		if (s < n_src_tiles && cutoff > 0.0f) {
+			const float *b = src_box + (size_t)s * 6;
+			meet = true;
+			for (int d = 0; d < 3; ++d)
+				if ((double)b[d] - (double)tb[3 + d] > c || (double)tb[d] - (double)b[3 + d] > c) meet = false;
+		}
+		const unsigned bits = __ballot_sync(0xffffffffu, meet);
+		if ((tid & 31) == 0 && (s >> 5) < words) { mask[(size_t)blockIdx.x * words + (s >> 5)] = bits; mine += __popc(bits); }
+	}
+	if ((tid & 31) == 0) s_count[tid >> 5] = mine;
+	__syncthreads();
+	if (tid == 0) {
+		unsigned long long n = 0;
+		for (int k = 0; k < 8; ++k) n += s_count[k];
+		if (n) atomicAdd(active, n);
+	}
+}
+
 // Raw rows -> packed float4 records, padded with zero-strength records (pad_source) to n_pad, a
 // multiple of kSrcTile.  One block packs one tile.  For filaments each block also leaves the
 // statistics f3d_pick_mode() wants (sum of l^3, longest l, bounding box of the end points) in

@@ -32,6 +32,7 @@ thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_T{0}, g_force_chunks{0};
 std::atomic<int> g_guard_mode{-1};
+std::atomic<int> g_sparse_route{1};
 std::atomic<int> g_f3d_mode{-2};                              // -2 = not set: CVTX_B200_F3D_MODE decides; -1 auto, 0 new, 1 reference form                           // -1 = not set: CVTX_B200_GUARDED decides, read once
 std::mutex g_devices_mu;
 std::vector<Device *> g_devices;
@@ -183,6 +184,12 @@ struct Planner {
 // a self-interaction call re-evaluates one chain per target, which is noise among thousands of
 // chains and half the work among two.
 constexpr int kMinTilesOptimistic = 16;
+
+// CVTX_B200_SPARSE=0 switches the sparse-tile route of the box-cutoff op off (tests, A/B measurements)
+bool sparse_route_enabled() {
+	static const bool on = [] { const char *e = getenv("CVTX_B200_SPARSE"); return !(e && e[0] == '0'); }();
+	return on && g_sparse_route.load() != 0;
+}
 
 // 0 = by size (the default), 1 = guarded form only, 2 = optimistic form at any size
 int guard_mode() {
@@ -353,6 +360,8 @@ void cvtx_b200_f3d_mode(int mode) { g_f3d_mode = (mode == 0 || mode == 1) ? mode
 
 void cvtx_b200_guarded_only(int mode) { g_guard_mode = (mode == 1 || mode == 2) ? mode : 0; }
 
+void cvtx_b200_sparse_route(int on) { g_sparse_route = on ? 1 : 0; }
+
 const char *cvtx_b200_last_error(void) { return g_err.c_str(); }
 
 float cvtx_b200_last_pair_kernel_ms(int device) {
@@ -444,7 +453,14 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	const size_t need_packed = plan.k.can_direct ? 0 : (size_t)n_pad * sizeof(float4);     // no packed copy in direct mode
 	const size_t need_pieces = sizeof(double) * 2 * (size_t)plan.grid * plan.k.T * plan.k.B * q.nout;
 	const size_t need_tickets = sizeof(int) * (size_t)plan.tiles_t;
-	const size_t need_aux = filament ? sizeof(F3DStats) * (size_t)n_src_tiles + 64 : 0;
+	// cvtx_P3D_M2M_vort on enough targets and a packed source set: the sparse-tile route is tried (m2m_kernel.cuh)
+	constexpr int kSparseSlots = 8 * 128;                                // sparse_tiles_kernel<P, 8, 128>: targets per tile
+	const long long sparse_tiles_t = ((long long)n_tgt + kSparseSlots - 1) / kSparseSlots;
+	const bool try_sparse = op == OP_P3D_VORT && !plan.k.can_direct && sparse_tiles_t >= 2LL * d->prop.multiProcessorCount
+	                        && g_force_T.load() == 0 && g_force_chunks.load() == 0 && sparse_route_enabled();
+	const int sparse_words = (n_src_tiles + 31) / 32;
+	const size_t need_aux = filament ? sizeof(F3DStats) * (size_t)n_src_tiles + 64
+	                      : (try_sparse ? 64 + sizeof(float) * 6 * (size_t)n_src_tiles + sizeof(unsigned) * (size_t)sparse_tiles_t * sparse_words : 0);
 	if (need_packed > d->packedA.cap || (records >= 2 && need_packed > d->packedB.cap) || (records >= 3 && need_packed > d->packedC.cap)
 	    || need_pieces > d->pieces.cap || need_tickets > d->tickets.cap || need_aux > d->aux.cap) {
 		CUDA_TRY(cudaDeviceSynchronize());             // growing frees memory earlier launches may still read
@@ -503,6 +519,27 @@ int cvtx_b200_m2m(int op, int reg, int device, void *stream_, const float *src, 
 	const bool defer = runs_per_tile > kInKernelFinishPieces;
 	args.defer_finish = defer ? 1 : 0;
 	CUDA_TRY(cudaEventRecord(d->k_start, st));
+	if (try_sparse) {
+		// aux: [0, 8) the count of (target tile, source tile) pairs whose boxes meet, [64, ..) source tile boxes, then the masks
+		unsigned long long *gate = (unsigned long long *)d->aux.p;
+		float *boxes = (float *)((char *)d->aux.p + 64);
+		unsigned *mask = (unsigned *)(boxes + 6 * (size_t)n_src_tiles);
+		CUDA_TRY(cudaMemsetAsync(gate, 0, sizeof(unsigned long long), st));
+		source_tile_boxes_kernel<<<n_src_tiles, kSrcTile, 0, st>>>((const float4 *)d->packedA.p, n_src, boxes);
+		target_tile_masks_kernel<<<(unsigned)sparse_tiles_t, 256, 0, st>>>(tgt, q.tcols, n_tgt, kSparseSlots, boxes, n_src_tiles, ck.k.c3,
+		                                                                    mask, sparse_words, gate);
+		CUDA_TRY(cudaGetLastError());
+		SparseArgs sa = {};
+		sa.srcA = (const float4 *)d->packedA.p; sa.srcB = (const float4 *)d->packedB.p; sa.n_src_tiles = n_src_tiles;
+		sa.tgt = tgt; sa.n_tgt = n_tgt; sa.out = out; sa.mask = mask; sa.words = sparse_words; sa.gate = gate;
+		sa.sparse_max = (unsigned long long)(0.3 * (double)sparse_tiles_t * (double)n_src_tiles);
+		sa.k = ck.k;
+		void *sparams[1] = {&sa};
+		CUDA_TRY(cudaLaunchKernel(vort_sparse_fn(reg), dim3((unsigned)sparse_tiles_t), dim3(128), sparams, 0, st));
+		args.sparse_gate = gate;
+		args.sparse_max = sa.sparse_max;
+		launched += 3;
+	}
 	void *params[1] = {&args};
 	CUDA_TRY(cudaLaunchKernel(plan.k.fn, dim3(plan.grid), dim3(plan.k.B), params, plan.k.smem, st));
 	if (defer) {

@@ -23,4 +23,7 @@ struct KernelChoice {
 // variant: 0 = 8 x 128, 1 = 4 x 256, 2 = 2 x 256, 3 = 1 x 128.  (op, reg) must be a supported pair (op_table.h).
 KernelChoice kernel_choice(int op, int reg, int variant, bool grain256, int device);
 
+// sparse_tiles_kernel<P3DVort<reg>, 8, 128> (m2m_kernel.cuh): the box-cutoff op on spatially coherent particle orders.
+const void *vort_sparse_fn(int reg);
+
 }  // namespace cvtx

@@ -67,6 +67,10 @@ struct M2MArgs {
 	int direct;                // 1: no packed copy exists; blocks pack the raw rows of a tile straight into shared memory
 	int defer_finish;          // 1: cut target tiles are summed by finish_pieces_kernel after this launch, not by their last block
 	unsigned long long *block_times;   // diagnostics (tools/kernel_ab): per block {SM id, start ns, end ns}, or null
+	// cvtx_P3D_M2M_vort only: *sparse_gate = (target tile, source tile) pairs whose boxes meet; at or below sparse_max the
+	// call belongs to sparse_tiles_kernel and this kernel returns at once (null: no such gate)
+	const unsigned long long *sparse_gate;
+	unsigned long long sparse_max;
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 	constexpr int UNROLL = CVTX_UNROLL;
 	constexpr uint32_t kTileBytes = S * sizeof(float4);
 	constexpr int NR = P::NSRC4;
+	if (args.sparse_gate && *args.sparse_gate <= args.sparse_max) return;      // sparse_tiles_kernel has done this call
 
 	__shared__ __align__(128) float4 tile[2][NR][S];
 	__shared__ __align__(8) uint64_t full[2];
@@ -538,6 +543,119 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 		unsigned long long t;
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 		args.block_times[3 * blockIdx.x + 2] = t;
+	}
+}
+
+// ---------------------------------------------------------------------------
+// Box-cutoff ops (cvtx_P3D_M2M_vort: only sources inside the 5-sigma cube around a target count, reference
+// src/P3D.cpp:298-322) on particles whose ORDER is spatially coherent -- what cvtx_P3D_redistribute_on_grid returns
+// (ascending Morton code) and what cvtx_P3D_pedrizzetti_relaxation is called on.  Then a tile of 256 consecutive
+// sources is a small cube, a tile of 1024 consecutive targets another, and all but a few per cent of the
+// (target tile, source tile) pairs cannot hold a single pair inside the cutoff.  target_tile_masks_kernel
+// (aux_kernels.cuh) marks the pairs whose boxes meet; here ONE block per target tile streams only the marked source
+// tiles through the same TMA double buffer and the same guarded pair loop, one FP32 chain per tile flushed into
+// FP64 in source order -- the chains m2m_kernel forms, minus chains that are exact zeros: the same bits.  The
+// call goes here when the marked pairs are at most sparse_max (30 % of all), to m2m_kernel otherwise; both
+// kernels are launched and read the count, the one that is not concerned returns at once.
+struct SparseArgs {
+	const float4 *srcA, *srcB;
+	int n_src_tiles;
+	const float *tgt; int n_tgt;
+	float *out;
+	const unsigned *mask; int words;           // [target tiles][words]: bit s of a row = source tile s is marked
+	const unsigned long long *gate; unsigned long long sparse_max;
+	PairConsts k;
+};
+
+template <class P, int T, int B>
+__global__ void __launch_bounds__(B, 2) sparse_tiles_kernel(const SparseArgs args)
+{
+	constexpr int S = kSrcTile, UNROLL = 8, W = 2, NV = T / W;
+	constexpr uint32_t kTileBytes = S * sizeof(float4);
+	static_assert(P::NSRC4 == 2 && !P::HYBRID && !P::OPTIMISTIC && T % 2 == 0, "box-cutoff particle policies");
+	if (*args.gate > args.sparse_max) return;                            // dense: m2m_kernel does this call
+	__shared__ __align__(128) float4 tile[2][2][S];
+	__shared__ __align__(8) uint64_t full[2];
+	__shared__ int s_tile[2];
+	const int tid = threadIdx.x, tt = blockIdx.x;
+	const unsigned *row = args.mask + (size_t)tt * args.words;
+	auto next_marked = [&](int from) {                                   // first marked source tile >= from, or -1 (thread 0)
+		for (int w = from >> 5; w < args.words; ++w) {
+			unsigned bits = __ldg(row + w);
+			if (w == (from >> 5)) bits &= ~0u << (from & 31);
+			if (bits) { const int s = w * 32 + __ffs(bits) - 1; return s < args.n_src_tiles ? s : -1; }
+		}
+		return -1;
+	};
+	auto fetch = [&](int src_tile, int buf) {
+		const size_t off = (size_t)src_tile * S;
+		mbar_expect_tx(&full[buf], kTileBytes * 2);
+		bulk_g2s(tile[buf][0], args.srcA + off, kTileBytes, &full[buf]);
+		bulk_g2s(tile[buf][1], args.srcB + off, kTileBytes, &full[buf]);
+	};
+	if (tid == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		mbar_fence_init();
+		s_tile[0] = next_marked(0);
+		if (s_tile[0] >= 0) fetch(s_tile[0], 0);
+	}
+	__syncthreads();
+
+	Vec<W> tg[NV][P::NTGT];
+	double dacc[T][P::NACC];
+	const long base = (long)tt * (B * T) + tid;
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		long i = base + (long)t * B;
+		i = i < args.n_tgt ? i : (long)args.n_tgt - 1;
+		float one[P::NTGT];
+		P::load_target(args.tgt + i * P::TCOLS, one);
+#pragma unroll
+		for (int c = 0; c < P::NTGT; ++c) tg[t / W][c].set(t % W, one[c]);
+#pragma unroll
+		for (int c = 0; c < P::NACC; ++c) dacc[t][c] = 0.0;
+	}
+	for (int it = 0;; ++it) {
+		const int buf = it & 1;
+		const int cur = s_tile[buf];
+		if (cur < 0) break;
+		if (tid == 0) {                                                  // the marked tile after this one goes into the other buffer
+			const int nxt = next_marked(cur + 1);
+			s_tile[buf ^ 1] = nxt;
+			if (nxt >= 0) fetch(nxt, buf ^ 1);
+		}
+		mbar_wait(&full[buf], (it >> 1) & 1);
+		const float4 *sA = tile[buf][0], *sB = tile[buf][1];
+		Vec<W> acc[NV][P::NACC];
+#pragma unroll
+		for (int v = 0; v < NV; ++v)
+#pragma unroll
+			for (int c = 0; c < P::NACC; ++c) acc[v][c] = bc<W>(0.0f);
+#pragma unroll 1
+		for (int j = 0; j < S; j += UNROLL) {
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u) {
+				const float4 a = sA[j + u], b = sB[j + u];
+#pragma unroll
+				for (int v = 0; v < NV; ++v) P::template pair<W, true>(tg[v], a, b, acc[v], args.k);
+			}
+		}
+#pragma unroll
+		for (int t = 0; t < T; ++t)
+#pragma unroll
+			for (int c = 0; c < P::NACC; ++c) dacc[t][c] += (double)acc[t / W][c].lane(t % W);
+		__syncthreads();                                                  // tile[buf] and s_tile[buf] are free again; s_tile[buf ^ 1] is visible
+	}
+#pragma unroll
+	for (int t = 0; t < T; ++t) {
+		const long i = base + (long)t * B;
+		if (i < args.n_tgt) {
+			double res[P::NOUT];
+			P::finish(args.tgt + i * P::TCOLS, dacc[t], res, args.k);
+#pragma unroll
+			for (int c = 0; c < P::NOUT; ++c) args.out[i * P::NOUT + c] = (float)res[c];
+		}
 	}
 }
 

@@ -70,6 +70,7 @@ class DeviceBackend:
         lib.cvtx_b200_tune.restype, lib.cvtx_b200_tune.argtypes = None, [i, i]
         lib.cvtx_b200_guarded_only.restype, lib.cvtx_b200_guarded_only.argtypes = None, [i]
         lib.cvtx_b200_f3d_mode.restype, lib.cvtx_b200_f3d_mode.argtypes = None, [i]
+        lib.cvtx_b200_sparse_route.restype, lib.cvtx_b200_sparse_route.argtypes = None, [i]
         lib.cvtx_b200_last_dispatch.restype = i
         lib.cvtx_b200_last_devices_used.restype = i
         lib.cvtx_b200_last_error.restype = C.c_char_p
@@ -137,6 +138,10 @@ class DeviceBackend:
         """Tests / experiments (cvtx_b200_f3d_mode): 0 = cancellation-free filament form, 1 = the
         reference's formula, -1 = chosen per call from the filaments (the default)."""
         self.lib.cvtx_b200_f3d_mode(int(mode))
+
+    def sparse_route(self, on: bool) -> None:
+        """Tests / experiments (cvtx_b200_sparse_route): the tile-skipping route of cvtx_P3D_M2M_vort on or off."""
+        self.lib.cvtx_b200_sparse_route(1 if on else 0)
 
     def last_dispatch(self) -> int:
         return int(self.lib.cvtx_b200_last_dispatch())

@@ -186,6 +186,11 @@ CVTX_B200_API void cvtx_b200_tune(int force_tgt_per_thread, int force_chunks);
  * restores the default; CVTX_B200_GUARDED=0|1|2 in the environment sets the
  * initial mode. */
 CVTX_B200_API void cvtx_b200_guarded_only(int mode);
+/* Experiments and tests only.  cvtx_P3D_M2M_vort counts only the sources inside the 5-sigma cube around a target
+ * (reference src/P3D.cpp:298-322).  On spatially coherent particle orders -- what the redistribution returns --
+ * most (target tile, source tile) pairs cannot hold such a source and are skipped (same bits);
+ * on = 0 switches that route off, on = 1 (the default) on.  CVTX_B200_SPARSE=0 in the environment does the same. */
+CVTX_B200_API void cvtx_b200_sparse_route(int on);
 /* Experiments and tests only.  The filament ops pick their fast pair form per call from the
  * filaments themselves: 0 pins the cancellation-free form, 1 the
  * reference's formula, anything else restores the automatic choice.  CVTX_B200_F3D_MODE=0|1

@@ -395,3 +395,48 @@ def test_unaligned_source_rows_give_the_same_bits(gpu, torch_cuda):
             for o in outs[1:]:
                 assert np.array_equal(o.view(np.uint32), outs[0].view(np.uint32)), (op, reg, n)
             assert np.all(np.isfinite(outs[0]))
+
+
+@pytest.mark.parametrize("reg", ["winckelmans", "gaussian", "planetary"])
+def test_vorticity_on_a_spatially_ordered_cloud_skips_tiles_and_keeps_the_bits(gpu, oracle, torch_cuda, reg):
+    """cvtx_P3D_M2M_vort counts only sources inside the 5-sigma cube around a target (reference src/P3D.cpp:298-322).
+    On particles in a spatially coherent order -- what the redistribution returns, what the relaxation is called on --
+    most (target tile, source tile) pairs cannot hold such a source; sparse_tiles_kernel streams only the others.
+    Same chains, so the bits of the all-tiles kernel; several times faster; a random order takes the all-tiles
+    kernel as before; the oracle agrees on a sample."""
+    torch = torch_cuda
+    _, dev = gpu
+    rng = np.random.default_rng(31)
+    n = 330_000
+    P = particles3d(rng, n, vol=0.01)
+    cell = np.floor(P[:, :3] / 0.5).astype(np.int64)                      # 20^3 cells of the 10^3 box, x fastest
+    ordered = np.ascontiguousarray(P[np.argsort(cell[:, 0] + 20 * (cell[:, 1] + 20 * cell[:, 2]), kind="stable")])
+    st = torch.cuda.current_stream().cuda_stream
+    sigma = 0.03                                                          # cutoff cube 0.3 wide: 3e-5 of the box
+
+    def run(rows, sparse):
+        dev.sparse_route(sparse)
+        src = torch.from_numpy(rows).cuda()
+        tgt = src[:, :3].contiguous()
+        out = torch.full((n, 3), float("nan"), device="cuda")
+        best = 1e9
+        for _ in range(2):
+            dev.m2m("P3D_M2M_vort", reg, 0, st, src, n, tgt, n, out, sigma)
+            torch.cuda.synchronize()
+            best = min(best, dev.last_pair_kernel_ms(0))
+        return out.cpu().numpy(), best
+    try:
+        dense, t_dense = run(ordered, False)
+        sparse, t_sparse = run(ordered, True)
+        print(f"vort/{reg} on {n} cell-ordered particles: all tiles {t_dense:.2f} ms, marked tiles only {t_sparse:.2f} ms")
+        assert np.array_equal(sparse.view(np.uint32), dense.view(np.uint32))
+        assert t_sparse < 0.5 * t_dense
+        idx = np.arange(0, n, 1500)
+        want = oracle.m2m("P3D_M2M_vort", ordered, np.ascontiguousarray(ordered[idx, :3]), reg, sigma)
+        assert rel_l2(sparse[idx], want) <= 1e-5
+        rnd_off, t_off = run(P, False)
+        rnd_on, t_on = run(P, True)
+        assert np.array_equal(rnd_on.view(np.uint32), rnd_off.view(np.uint32))
+        assert t_on < 1.15 * t_off                                        # the route is declined: the boxes + masks cost little
+    finally:
+        dev.sparse_route(True)
