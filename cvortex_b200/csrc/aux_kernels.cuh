@@ -39,6 +39,28 @@ __global__ void __launch_bounds__(256) finish_pieces_kernel(const double *__rest
 	if (lane == 0) out[i * nout + c] = (float)s;
 }
 
+// ---- small calls: the host rows are READ by the device instead of being copied to it ------------------------------
+// Two byte ranges (source rows, target rows) from the pinned staging area into device memory, 16 bytes per load, every
+// byte read once.  A 10k x 10k call moves 400 KB: two copy-engine transfers cost it ~20 us each in engine start-up and
+// the hand-over to the compute engine, a kernel reading through the mapped pointer starts like any other launch and
+// runs at the link's rate.  Sizes are multiples of 4 (rows of floats), the buffers 256-byte aligned.
+__global__ void __launch_bounds__(256) upload_rows_kernel(const void *__restrict__ a_src, void *__restrict__ a_dst, size_t a_bytes,
+                                                          const void *__restrict__ b_src, void *__restrict__ b_dst, size_t b_bytes)
+{
+	// ONE 16-byte unit per thread: every read of the call is on the link at once (a loop of dependent load -> store
+	// rounds pays the link's ~2.5 us round trip once per round)
+	const size_t a16 = a_bytes / 16, b16 = b_bytes / 16;
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < a16) ((uint4 *)a_dst)[i] = __ldcs((const uint4 *)a_src + i);
+	else if (i < a16 + b16) ((uint4 *)b_dst)[i - a16] = __ldcs((const uint4 *)b_src + (i - a16));
+	else {
+		const size_t k = i - a16 - b16;                                    // the last few threads: the ranges' tails, word by word
+		const size_t ta = (a_bytes % 16) / 4, tb = (b_bytes % 16) / 4;
+		if (k < ta) ((unsigned *)a_dst)[a16 * 4 + k] = ((const unsigned *)a_src)[a16 * 4 + k];
+		else if (k < ta + tb) ((unsigned *)b_dst)[b16 * 4 + (k - ta)] = ((const unsigned *)b_src)[b16 * 4 + (k - ta)];
+	}
+}
+
 // ---- box-cutoff ops on spatially coherent orders (m2m_kernel.cuh, sparse_tiles_kernel) ----------------------
 // Bounding box of the REAL records of every packed source tile (NaN coordinates are ignored: such a source is outside
 // every cutoff cube, as in the reference).  box[tile] = {lo x, y, z, hi x, y, z}; an empty tile gets an inverted box.

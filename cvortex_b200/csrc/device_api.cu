@@ -9,6 +9,7 @@
 // set was split for load balance), all asynchronous on the caller's stream.
 // No CPU path lives here: errors are returned, never papered over.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -109,6 +110,7 @@ constexpr int kRunsPerSlot = 4;
 constexpr int kMinRunGrains = 24;
 constexpr int kInKernelFinishPieces = 48;
 constexpr size_t kZeroCopyResultBytes = 512u << 10;      // results up to this size are stored to pinned host memory by the kernel
+constexpr size_t kKernelUploadBytes = 4u << 20;          // inputs up to this size are read from pinned host memory by a kernel (upload_rows_kernel)
 
 struct Plan { KernelChoice k; int grain, grid; long long tiles_t, total_grains; };
 
@@ -184,6 +186,13 @@ struct Planner {
 // a self-interaction call re-evaluates one chain per target, which is noise among thousands of
 // chains and half the work among two.
 constexpr int kMinTilesOptimistic = 16;
+
+// CVTX_B200_TRACE=1: every staged call prints where its wall-clock time went (stderr, microseconds)
+bool trace_enabled() {
+	static const bool on = [] { const char *e = getenv("CVTX_B200_TRACE"); return e && e[0] == '1'; }();
+	return on;
+}
+double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // CVTX_B200_SPARSE=0 switches the sparse-tile route of the box-cutoff op off (tests, A/B measurements)
 bool sparse_route_enabled() {
@@ -608,8 +617,10 @@ int cvtx_b200_m2m_host(int op, int reg, int device, const float *src, int n_src,
 	CUDA_TRY(cudaSetDevice(device));
 	CUDA_TRY(hs.src.reserve(sb));
 	CUDA_TRY(hs.tgt.reserve(tb));
+	const double t0 = trace_enabled() ? now_us() : 0.0;
 	if (sb) std::memcpy(hs.src.p, src, sb);
 	std::memcpy(hs.tgt.p, tgt, tb);
+	if (trace_enabled()) std::fprintf(stderr, "cvtx trace: rows into the staging area %.1f us (%zu bytes)\n", now_us() - t0, sb + tb);
 	return run_staged(op, reg, std::vector<int>(1, device), n_src, n_tgt, out, sigma, nu, h2d_bytes, d2h_bytes);
 }
 
@@ -635,6 +646,9 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 	std::vector<int> devices(devices_in.begin(), devices_in.begin() + (n_tgt < (int)devices_in.size() ? (n_tgt > 0 ? n_tgt : 1) : (int)devices_in.size()));
 	const int G = (int)devices.size();
 	const size_t srow = sizeof(float) * src_cols(op), trow = sizeof(float) * q.tcols, orow = sizeof(float) * q.nout;
+	const bool trace = trace_enabled();
+	const double t_in = trace ? now_us() : 0.0;
+	double t_up = 0.0, t_launched = 0.0, t_done = 0.0;
 	CUDA_TRY(cudaSetDevice(devices[0]));
 	CUDA_TRY(hs.out.reserve(orow * (size_t)n_tgt));
 	std::vector<cudaStream_t> streams(G, nullptr);
@@ -659,11 +673,22 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 		full[g] = d->d_src.p;
 		shard[g] = (const char *)d->d_src.p + srow * (size_t)soff[g];
 		const size_t sb = srow * (size_t)(soff[g + 1] - soff[g]);
-		if (sb) CUDA_TRY(cudaMemcpyAsync((void *)shard[g], (const char *)hs.src.p + srow * (size_t)soff[g], sb, cudaMemcpyHostToDevice, streams[g]));
-		if (hi > lo) CUDA_TRY(cudaMemcpyAsync(d->d_tgt.p, (const char *)hs.tgt.p + trow * lo, trow * (size_t)(hi - lo), cudaMemcpyHostToDevice, streams[g]));
-		up += sb + trow * (size_t)(hi - lo);
+		const size_t tb = trow * (size_t)(hi - lo);
+		if (G == 1 && sb + tb <= kKernelUploadBytes) {
+			// one device, little data: one launch that reads both ranges through the mapped staging pointers
+			const size_t units = sb / 16 + tb / 16 + 8;                        // + the tails of both ranges
+			const unsigned blocks = (unsigned)((units + 255) / 256);
+			upload_rows_kernel<<<blocks, 256, 0, streams[g]>>>(hs.src.p, (void *)shard[g], sb, hs.tgt.p, d->d_tgt.p, tb);
+			CUDA_TRY(cudaGetLastError());
+			count_launches(1);
+		} else {
+			if (sb) CUDA_TRY(cudaMemcpyAsync((void *)shard[g], (const char *)hs.src.p + srow * (size_t)soff[g], sb, cudaMemcpyHostToDevice, streams[g]));
+			if (tb) CUDA_TRY(cudaMemcpyAsync(d->d_tgt.p, (const char *)hs.tgt.p + trow * lo, tb, cudaMemcpyHostToDevice, streams[g]));
+		}
+		up += sb + tb;
 	}
 	if (int rc = all_gather_rows(devices, streams, shard, soff, full, srow)) return rc;
+	if (trace) { if (getenv("CVTX_B200_TRACE_SYNC")) cudaStreamSynchronize(streams[0]); t_up = now_us(); }
 	for (int g = 0; g < G; ++g) {
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
 		if (hi == lo) continue;
@@ -679,12 +704,18 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 		if (!zero_copy) CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo), cudaMemcpyDeviceToHost, streams[g]));
 		down += orow * (size_t)(hi - lo);
 	}
+	if (trace) t_launched = now_us();
 	for (int g = 0; g < G; ++g) {
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
 		CUDA_TRY(cudaSetDevice(devices[g]));
 		CUDA_TRY(cudaStreamSynchronize(streams[g]));
+		if (trace && g == G - 1) t_done = now_us();
 		if (hi > lo) copy_parallel((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
 	}
+	if (trace)
+		std::fprintf(stderr, "cvtx trace: %d x %d on %d device(s): uploads enqueued%s %.1f us, launches %.1f, wait %.1f, result copy %.1f; pair kernel %.1f us\n",
+		             n_src, n_tgt, G, getenv("CVTX_B200_TRACE_SYNC") ? " and done" : "", t_up - t_in, t_launched - t_up, t_done - t_launched, now_us() - t_done,
+		             1e3 * (double)cvtx_b200_last_pair_kernel_ms(devices[0]));
 	if (h2d_bytes) *h2d_bytes = up;
 	if (d2h_bytes) *d2h_bytes = down;
 	return CVTX_B200_OK;

@@ -440,3 +440,4 @@ def test_vorticity_on_a_spatially_ordered_cloud_skips_tiles_and_keeps_the_bits(g
         assert t_on < 1.3 * t_off                                         # the route is declined: the boxes + masks cost little
     finally:
         dev.sparse_route(True)
+

@@ -358,3 +358,30 @@ def test_random_shapes_against_the_oracle(gpu, oracle):
         # division: up to ~4.5x the reference's own distance from FP64 has been seen)
         slack = 6.0 if (op, reg) == ("P3D_M2M_dvort", "gaussian") else 3.0
         assert_parity(got, f32, f64, "f3d" if op.startswith("F3D") else False, f"draw {k}: {op}/{reg} n={n} m={m} sigma={sigma}", slack=slack)
+
+
+@pytest.mark.parametrize("n", [5_000, 70_000])
+def test_pointer_arrays_in_any_order_give_the_rows_they_point_to(gpu, n):
+    """The ABI takes arrays of POINTERS (libcvtx.h:213-248).  The gather copies runs of consecutive rows as blocks
+    (host_api.cu, gather_span) -- what the reference's benchmark passes is one run -- and must still follow every
+    pointer: reversed, shuffled, partly consecutive and repeated pointers against the same rows passed in order."""
+    from cvortex_b200.abi import PointerRows
+    lib, dev = gpu
+    rng = np.random.default_rng(n)
+    rows = particles3d(rng, n)
+    tgt = particles3d(rng, 700)
+    orders = {
+        "reversed": np.arange(n)[::-1],
+        "shuffled": rng.permutation(n),
+        "runs": np.concatenate([np.arange(a, min(a + 37, n)) for a in rng.permutation(np.arange(0, n, 37))]),
+        "repeated": np.repeat(np.arange(0, n, 2), 2)[:n],
+    }
+    for name, order in orders.items():
+        want = lib.P3D_M2M_dvort(np.ascontiguousarray(rows[order]), tgt, "winckelmans", 0.05)
+        assert dev.last_dispatch() == 1
+        scattered = PointerRows(rows, 7)
+        scattered.ptrs = np.ascontiguousarray(scattered.ptrs[order])
+        tptr = PointerRows(tgt, 7)
+        tptr.ptrs = np.ascontiguousarray(tptr.ptrs[::-1])
+        got = lib.P3D_M2M_dvort(scattered, tptr, "winckelmans", 0.05)
+        assert np.array_equal(got[::-1].view(np.uint32), want.view(np.uint32)), name

@@ -37,10 +37,13 @@ static void report(Ctx &c, const char *name, const char *variant, int regs, int 
 	fflush(stdout);
 }
 
+static int g_grid_abs = 0, g_grain = 0, g_direct = 0;      // "small" mode: explicit grid, run-time grain, in-kernel packing
+
 template <class P, int T, int BLK, int MINB, int VW, int OPT = 0, int GRAIN = 0>
 static float run_new(Ctx &c, const char *name, int grid_mult, bool times = false, int reps = 3) {
-	char variant[64];
-	snprintf(variant, sizeof variant, "r2 T=%d B=%d/%d VW=%d O%d G%d x%d", T, BLK, MINB, VW, OPT, GRAIN, grid_mult);
+	char variant[96];
+	if (g_grid_abs) snprintf(variant, sizeof variant, "r2 T=%d B=%d/%d VW=%d O%d G%d grid=%d grain=%d%s", T, BLK, MINB, VW, OPT, GRAIN, g_grid_abs, g_grain ? g_grain : kSrcTile, g_direct ? " direct" : "");
+	else snprintf(variant, sizeof variant, "r2 T=%d B=%d/%d VW=%d O%d G%d x%d", T, BLK, MINB, VW, OPT, GRAIN, grid_mult);
 	if (c.filter && !strstr(name, c.filter) && !strstr(variant, c.filter)) return 0.f;
 	auto kern = m2m_kernel<P, T, BLK, MINB, VW, OPT, GRAIN>;
 	int occ = 0;
@@ -52,9 +55,11 @@ static float run_new(Ctx &c, const char *name, int grid_mult, bool times = false
 	a.srcA = c.A; a.srcB = c.B; a.srcC = c.C; a.src_raw = c.raw; a.n_src = c.n; a.n_src_tiles = c.n / kSrcTile; a.grain = kSrcTile;
 	const long long tiles_t = (c.n + BLK * T - 1) / (BLK * T);
 	a.total_grains = tiles_t * a.n_src_tiles;
+	if (g_grain) { a.grain = g_grain; a.total_grains *= kSrcTile / g_grain; }
+	a.direct = g_direct;
 	a.tgt = c.tgt; a.n_tgt = c.n; a.out = c.out; a.pieces = c.pieces; a.tickets = c.tickets; a.f3d_mode = c.mode;
 	a.k = P::make_consts(0.02f, 1.0f);
-	const int grid = occ * c.sms * grid_mult;
+	const int grid = g_grid_abs ? g_grid_abs : occ * c.sms * grid_mult;
 	unsigned long long *bt = nullptr;
 	if (times) { CK(cudaMalloc(&bt, sizeof(unsigned long long) * 3 * grid)); a.block_times = bt; }
 	float best = 1e30f;
@@ -90,6 +95,7 @@ static float run_new(Ctx &c, const char *name, int grid_mult, bool times = false
 			bmin = sm_blocks[sm] < bmin ? sm_blocks[sm] : bmin; bmax = sm_blocks[sm] > bmax ? sm_blocks[sm] : bmax;
 			emin = sm_end[sm] < emin ? sm_end[sm] : emin; emax = sm_end[sm] > emax ? sm_end[sm] : emax;
 		}
+		if (g_grid_abs) printf("    occupancy %d blocks/SM; ", occ);
 		printf("    block times: span %.3f ms; per block min %.3f mean %.3f max %.3f ms; blocks per SM %d..%d; SMs finish at %.3f..%.3f ms\n",
 		       (double)(t1 - t0) * 1e-6, dmin, dsum / grid, dmax, bmin, bmax, emin, emax);
 		// slowest and fastest few blocks with their SM
@@ -233,6 +239,29 @@ int main(int argc, char **argv) {
 	CK(cudaMemset(c.C, 0, sizeof(float4) * n));
 	CK(cudaMemcpy(c.tgt, ht.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
 
+	if (c.filter && strstr(c.filter, "small")) {
+		// the 10k x 10k regime: which geometry / grain / grid, and where the launch's time goes
+		c.filter = nullptr;
+		std::vector<float> rows((size_t)n * 7);
+		for (int i = 0; i < n; ++i) { float *r = &rows[(size_t)i * 7]; r[0] = hA[i].x; r[1] = hA[i].y; r[2] = hA[i].z; r[3] = hB[i].x; r[4] = hB[i].y; r[5] = hB[i].z; r[6] = 0.01f; }
+		CK(cudaMemcpy(c.raw, rows.data(), sizeof(float) * 7 * n, cudaMemcpyHostToDevice));
+		typedef P3DVel<REG_WINCKELMANS> PW;
+		const int grids[3] = {c.sms, 2 * c.sms, 4 * c.sms};
+		for (int direct = 0; direct < 2; ++direct) for (int gr = 0; gr < 2; ++gr) for (int gi = 0; gi < 3; ++gi) {
+			g_direct = direct; g_grain = gr ? 32 : 0; g_grid_abs = grids[gi];
+			const bool t = gi == 0;
+			run_new<PW, 1, 128, 8, 1, 0, 0>(c, "vel-w", 1, t, 5);
+			run_new<PW, 2, 256, 3, 2, 0, 0>(c, "vel-w", 1, t, 5);
+			run_new<PW, 4, 256, 2, PW::VW4, PW::OPT4, 0>(c, "vel-w", 1, t, 5);
+			run_new<PW, 8, 128, 2, PW::VW8, PW::OPT8, 0>(c, "vel-w", 1, t, 5);
+			if (!direct && !gr) {
+				run_new<PW, 4, 256, 2, PW::VW4, PW::OPT4, 256>(c, "vel-w", 1, t, 5);
+				run_new<PW, 8, 128, 2, PW::VW8, PW::OPT8, 256>(c, "vel-w", 1, t, 5);
+			}
+		}
+		printf("done\n");
+		return 0;
+	}
 	if (c.filter && strstr(c.filter, "guards")) {
 		// the ops whose coincident-pair guard is a real selection, in their tuned instances (A/B of pair_math.cuh's
 		// CVTX_GUARD_BY_MASK: build this tool once with -DCVTX_GUARD_BY_MASK=0 and once with =1)
