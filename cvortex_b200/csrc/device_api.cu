@@ -689,19 +689,30 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 	}
 	if (int rc = all_gather_rows(devices, streams, shard, soff, full, srow)) return rc;
 	if (trace) { if (getenv("CVTX_B200_TRACE_SYNC")) cudaStreamSynchronize(streams[0]); t_up = now_us(); }
+	// A caller whose result array is page-locked itself (cudaHostAlloc / cudaHostRegister) gets the result written
+	// there directly -- by the kernel or by the D2H copy -- and no second copy on the host (10 us of a 10k x 10k call).
+	char *landing = (char *)hs.out.p;
+	bool direct_out = false;
+	{
+		cudaPointerAttributes pa = {};
+		if (G == 1 && cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer == (void *)out) {
+			landing = (char *)out;
+			direct_out = true;
+		} else cudaGetLastError();
+	}
 	for (int g = 0; g < G; ++g) {
 		const long lo = (long)n_tgt * g / G, hi = (long)n_tgt * (g + 1) / G;
 		if (hi == lo) continue;
 		Device *d = get_device(devices[g]);
-		// small results are written by the kernel straight into the pinned staging area (unified addressing: the
+		// small results are written by the kernel straight into page-locked host memory (unified addressing: the
 		// host pointer is valid on the device): the D2H copy of a 10k x 10k call costs as much as a tenth of its kernel
 		const bool zero_copy = orow * (size_t)(hi - lo) <= kZeroCopyResultBytes;
-		float *result = zero_copy ? (float *)((char *)hs.out.p + orow * lo) : (float *)d->d_out.p;
+		float *result = zero_copy ? (float *)(landing + orow * lo) : (float *)d->d_out.p;
 		if (int rc = cvtx_b200_m2m(op, reg, devices[g], streams[g], (const float *)d->d_src.p, n_src,
 		                           (const float *)d->d_tgt.p, (int)(hi - lo), result, sigma, nu))
 			return rc;
 		CUDA_TRY(cudaSetDevice(devices[g]));
-		if (!zero_copy) CUDA_TRY(cudaMemcpyAsync((char *)hs.out.p + orow * lo, d->d_out.p, orow * (size_t)(hi - lo), cudaMemcpyDeviceToHost, streams[g]));
+		if (!zero_copy) CUDA_TRY(cudaMemcpyAsync(landing + orow * lo, d->d_out.p, orow * (size_t)(hi - lo), cudaMemcpyDeviceToHost, streams[g]));
 		down += orow * (size_t)(hi - lo);
 	}
 	if (trace) t_launched = now_us();
@@ -710,7 +721,7 @@ int cvtx::run_staged(int op, int reg, const std::vector<int> &devices_in, int n_
 		CUDA_TRY(cudaSetDevice(devices[g]));
 		CUDA_TRY(cudaStreamSynchronize(streams[g]));
 		if (trace && g == G - 1) t_done = now_us();
-		if (hi > lo) copy_parallel((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
+		if (hi > lo && !direct_out) copy_parallel((char *)out + orow * lo, (const char *)hs.out.p + orow * lo, orow * (size_t)(hi - lo));
 	}
 	if (trace)
 		std::fprintf(stderr, "cvtx trace: %d x %d on %d device(s): uploads enqueued%s %.1f us, launches %.1f, wait %.1f, result copy %.1f; pair kernel %.1f us\n",

@@ -385,3 +385,21 @@ def test_pointer_arrays_in_any_order_give_the_rows_they_point_to(gpu, n):
         tptr.ptrs = np.ascontiguousarray(tptr.ptrs[::-1])
         got = lib.P3D_M2M_dvort(scattered, tptr, "winckelmans", 0.05)
         assert np.array_equal(got[::-1].view(np.uint32), want.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("m", [3_000, 60_000])
+def test_a_page_locked_result_array_is_written_directly(gpu, torch_cuda, m):
+    """A result array the caller page-locked itself receives the result without the host-side copy out of the
+    library's staging area: stored by the kernel (small results) or by the device-to-host copy (large ones).  Same
+    bits as into pageable memory, also at an offset inside the allocation, and nothing outside the result is touched."""
+    torch = torch_cuda
+    lib, dev = gpu
+    rng = np.random.default_rng(m)
+    src = particles3d(rng, 5_000)
+    mes = points(rng, m, 3)
+    want = lib.P3D_M2M_vel(src, mes, "winckelmans", 0.05)
+    assert dev.last_dispatch() == 1
+    pinned = torch.full((m + 7, 3), -7.0, dtype=torch.float32).pin_memory().numpy()
+    got = lib.P3D_M2M_vel(src, mes, "winckelmans", 0.05, out=pinned[5:5 + m])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.all(pinned[:5] == -7.0) and np.all(pinned[5 + m:] == -7.0)
