@@ -22,6 +22,10 @@
  *           (same bits either way); the pruning of weak nodes runs on the host.
  *           Relaxation is one cvtx_P3D_M2M_vort call plus a per-particle blend.
  *
+ * Attribution: the API restated here -- names, signatures, struct layouts -- is that of
+ * cvortex by H. J. A. Bird (https://github.com/hjabird/cvortex), MIT License,
+ * Copyright (c) 2018 HJA Bird.  The implementation behind it in this tree is new.
+ *
  * Struct sizes relied on across the ABI (static_asserted in the library):
  *   cvtx_P3D 28, cvtx_F3D 28, cvtx_P2D 16, cvtx_VortFunc 80 (LP64),
  *   bsv_V3f 12, bsv_V2f 8.
