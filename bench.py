@@ -278,7 +278,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "Gpair/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(name, n, m, ops, world):
@@ -590,6 +590,19 @@ def parity_sample(torch, dev, ref, outs):
     return parity
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the process's real stdout (see main)."""
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, text)
+    else:
+        os.write(_REAL_STDOUT, text)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -605,6 +618,13 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line at the first
+    # communicator when the box exports NCCL_DEBUG): everything this process and its libraries print goes to stderr,
+    # and only emit() below writes to the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
@@ -718,7 +738,7 @@ def main():
             "inlib_multi_gpu": inlib,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         B.dist.barrier()
         B.dist.destroy_process_group()
