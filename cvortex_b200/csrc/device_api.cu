@@ -34,7 +34,7 @@ std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_T{0}, g_force_chunks{0};
 std::atomic<int> g_guard_mode{-1};
 std::atomic<int> g_sparse_route{1};
-std::atomic<int> g_f3d_mode{-2};                              // -2 = not set: CVTX_B200_F3D_MODE decides; -1 auto, 0 new, 1 reference form                           // -1 = not set: CVTX_B200_GUARDED decides, read once
+std::atomic<int> g_f3d_mode{-2};                              // -2 = not set: CVTX_B200_F3D_MODE decides; -1 auto, 0 new, 1 wide                           // -1 = not set: CVTX_B200_GUARDED decides, read once
 std::mutex g_devices_mu;
 std::vector<Device *> g_devices;
 int g_device_count = -2;                                       // -2 = not probed yet

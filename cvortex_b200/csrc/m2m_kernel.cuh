@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 	Vec<W> tg[NV][P::NTGT];
 	double dacc[SACC ? 1 : T][P::NACC];
 	const bool optimistic = P::OPTIMISTIC && !args.exact_only;
-	int f3d_mode = F3D_REF;
+	int f3d_mode = F3D_WIDE;
 	if (P::HYBRID) f3d_mode = *args.f3d_mode;
 
 	bool fresh = true;                                                  // the next step starts a target tile
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(B, MINB) m2m_kernel(const M2MArgs args)
 								for (int u = 0; u < UNROLL; ++u) {
 									const float4 a = sA[s0 + j + u], b = sB[s0 + j + u], c = sC[s0 + j + u];
 #pragma unroll
-									for (int v = 0; v < NV; ++v) P::template fast<W, F3D_REF>(tg[v], a, b, c, sub[v], flag[v], args.k);
+									for (int v = 0; v < NV; ++v) P::template fast<W, F3D_WIDE>(tg[v], a, b, c, sub[v], flag[v], args.k);
 								}
 							}
 						}

@@ -824,13 +824,18 @@ template <int W> CVTX_HD void cross_rounded(Vec<W> ux, Vec<W> uy, Vec<W> uz, Vec
 // root -- op for op what src/F3D.cpp:34-85 does, so points on a vortex line get the reference's bits.
 // The decision is per target and per fixed sub-chain of the source order, never per thread: a result
 // does not depend on which other targets share a thread, on the launch geometry or on the shard.
-// A call whose filaments are long against the region they live in would take the slow tier all the
-// time; for those the fast form is the reference's formula with MUFU (`fast<W, F3D_REF>`, the first
-// version of this kernel) with only the axis test in the flag.  Which of the two is a property of
-// the SOURCES alone (f3d_pick_mode, decided on the device while packing), so every shard of a
-// multi-GPU call makes the same choice.
+// A call whose filaments are long against the region they live in (a vortex ring, a lifting line:
+// most filament sets in practice) would take the slow tier all the time.  For those the fast form
+// selects per pair (`fast<W, F3D_WIDE>`): outside the sphere 1/(|r1||r2| + r1.r2) as above, inside it
+// the same quantity as (|r1||r2| - r1.r2)/|c|^2 -- a sum of positive terms THERE over the cross
+// product's own square -- so nothing cancels anywhere off the axis and only the axis test feeds the
+// flag; one more MUFU and a select per pair.  (The first version of this kernel evaluated the
+// reference's formula with MUFU in this regime: its t2 cancels for short segments and amplified the
+// 1 - 2 ulp of MUFU.RSQ to 2 - 3x the reference's own distance from FP64 -- 4e-5 on one short filament
+// seen from afar.)  Which of the two is a property of the SOURCES alone (f3d_pick_mode, decided on the
+// device while packing), so every shard of a multi-GPU call makes the same choice.
 // ---------------------------------------------------------------------------
-enum F3DMode { F3D_NEW = 0, F3D_REF = 1 };
+enum F3DMode { F3D_NEW = 0, F3D_WIDE = 1 };
 constexpr int F3D_SUB = 32;
 
 // running per-lane minimum that keeps a NaN once it has seen one (one FMNMX3.NAN on sm_100)
@@ -881,15 +886,15 @@ CVTX_HD V3r r_cross(V3r a, V3r b) {
 // re-evaluates a 32-source sub-chain in scalar code, ~3x the cost of the sub-chain itself, for
 // 32 lanes x 8 targets x 32 sources = 8192 pairs: at p = 4e-6 that is +10 %.
 CVTX_HD int f3d_pick_mode(double sum_len3, double n, const float *lo, const float *hi, float max_len) {
-	if (!(n > 0.0)) return F3D_REF;
+	if (!(n > 0.0)) return F3D_WIDE;
 	double vol = 1.0;
 	for (int i = 0; i < 3; ++i) {
 		const double e = (double)hi[i] - (double)lo[i];
 		vol *= e > (double)max_len ? e : (double)max_len;
 	}
-	if (!(vol > 0.0)) return F3D_REF;
+	if (!(vol > 0.0)) return F3D_WIDE;
 	const double p = 0.5235987755982988 * sum_len3 / (n * vol);      // (pi/6) <l^3> / V
-	return p < 4e-6 ? F3D_NEW : F3D_REF;
+	return p < 4e-6 ? F3D_NEW : F3D_WIDE;
 }
 
 // ===========================================================================
@@ -902,7 +907,7 @@ CVTX_HD int f3d_pick_mode(double sum_len3, double n, const float *lo, const floa
 // ===========================================================================
 struct F3DVel {
 	static constexpr int NSRC4 = 3, TCOLS = 3, NTGT = 3, NACC = 3, NOUT = 3, CHAIN = 0, PREF_T = 4;
-	static constexpr int LANE_OPS = 34, SFU_OPS = 3;           // of fast<W, F3D_NEW>; the F3D_REF form: 44 / 3
+	static constexpr int LANE_OPS = 34, SFU_OPS = 3;           // of fast<W, F3D_NEW>; the F3D_WIDE form: 39 / 4
 	static constexpr bool OPTIMISTIC = false, HYBRID = true;
 	// TUNE (profiles/kernel_ab_f3d_r2.txt): 4 targets per thread, 850 against 840 Gpair/s with 8; 5 = shared-memory
 	// accumulators + the reference-arithmetic tier once per chain (M2M_DEFER_EXACT)
@@ -931,23 +936,31 @@ struct F3DVel {
 			const Vec<W> margin = vfma(n1, -tl, c2);                                              // > 0: off the axis
 			for (int i = 0; i < W; ++i) flag.set(i, min3_nan(flag.lane(i), d12.lane(i), margin.lane(i)));
 		} else {
+			// the reference's geometry -- r2 = x - b, c = r1 x r2 rounded as it rounds it -- so that next to an end
+			// point and next to the axis the error of c is the reference's own; the scalar factor t2/|c|^2 without
+			// its cancellation: 1/(|r1||r2| + r1.r2) outside the sphere, (|r1||r2| - r1.r2)/|c|^2 inside
 			const Vec<W> qx = vsub(tg[0], b.x), qy = vsub(tg[1], b.y), qz = vsub(tg[2], b.z);     // r2
-			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);                 // r0 = r1 - r2 (exact)
 			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
-			const Vec<W> d1 = vfma(pz, oz, vfma(py, oy, vmul(px, ox)));
-			const Vec<W> d2 = vfma(qz, oz, vfma(qy, oy, vmul(qx, ox)));
+			const Vec<W> d12 = vfma(pz, qz, vfma(py, qy, vmul(px, qx)));                          // r1 . r2
 			Vec<W> cx, cy, cz;
 			cross_rounded(px, py, pz, qx, qy, qz, k.c0, cx, cy, cz);                              // c = r1 x r2
 			const Vec<W> c2 = vfma(cz, cz, vfma(cy, cy, vmul(cx, cx)));
-			const Vec<W> t1 = vmul(vrcp(c2), a.w);
-			const Vec<W> t2 = vfms(d1, vrsqrt(n1), vmul(d2, vrsqrt(n2)));
-			const Vec<W> kk = vmul(t1, t2);
+			const Vec<W> rs1 = vrsqrt(n1), rs2 = vrsqrt(n2);
+			// (|r1||r2| +- r1.r2 as explicit FMAs: ptxas fuses a packed product into a following packed sum and leaves
+			// the scalar one alone -- the T = 1 geometry would round differently from the others)
+			const Vec<W> q1 = vmul(n1, rs1), q2 = vmul(n2, rs2);
+			const Vec<W> out = vrcp(vfma(q1, q2, d12)), in = vmul(vfms(q1, q2, d12), vrcp(c2));
+			// a target ON an end point has c = 0 and n1 = 0 (or r2 = 0): margin = 0 or -tl n1, never positive
+			const Vec<W> margin = vfma(n1, -tl, c2);
+			Vec<W> im;
+			for (int i = 0; i < W; ++i) {
+				im.set(i, d12.lane(i) > 0.0f ? out.lane(i) : in.lane(i));
+				flag.set(i, min2_nan(flag.lane(i), margin.lane(i)));
+			}
+			const Vec<W> kk = vmul(vmul(vadd(rs1, rs2), a.w), im);                                // G/4pi Kf
 			acc[0] = vfma(kk, cx, acc[0]);
 			acc[1] = vfma(kk, cy, acc[1]);
 			acc[2] = vfma(kk, cz, acc[2]);
-			// a target ON an end point has c = 0 and n1 = 0 (or r2 = 0): margin = 0 or -tl n1, never positive
-			const Vec<W> margin = vfma(n1, -tl, c2);
-			for (int i = 0; i < W; ++i) flag.set(i, min2_nan(flag.lane(i), margin.lane(i)));
 		}
 	}
 
@@ -985,7 +998,7 @@ struct F3DVel {
 // ===========================================================================
 struct F3DDvort {
 	static constexpr int NSRC4 = 3, TCOLS = 7, NTGT = 3, NACC = 4, NOUT = 3, CHAIN = 0, PREF_T = 4;
-	static constexpr int LANE_OPS = 41, SFU_OPS = 4;           // of fast<W, F3D_NEW>; the F3D_REF form: 46 / 3
+	static constexpr int LANE_OPS = 41, SFU_OPS = 4;           // of fast<W, F3D_NEW>; the F3D_WIDE form: 55 / 5
 	static constexpr bool OPTIMISTIC = false, HYBRID = true;
 	// TUNE (profiles/kernel_ab_f3d_r2.txt): 4 targets per thread, 705 against 672 Gpair/s with 8
 	static constexpr int VW8 = 8, OPT8 = 5, VW4 = 2, OPT4 = 5;
@@ -1017,24 +1030,34 @@ struct F3DDvort {
 			const Vec<W> margin = vfma(ln, -k.c1, x2);
 			for (int i = 0; i < W; ++i) flag.set(i, min3_nan(flag.lane(i), d12.lane(i), margin.lane(i)));
 		} else {
+			// the reference's geometry (r2 = x - b, r0 = r1 - r2, X = r1 x r0 rounded as it rounds it), the scalar
+			// factors without their cancellations (see F3DVel)
 			const Vec<W> qx = vsub(tg[0], b.x), qy = vsub(tg[1], b.y), qz = vsub(tg[2], b.z);     // r2
-			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);                 // r0 = r1 - r2 (exact)
+			const Vec<W> ox = vsub(px, qx), oy = vsub(py, qy), oz = vsub(pz, qz);                 // r0 = r1 - r2
 			const Vec<W> n2 = vfma(qz, qz, vfma(qy, qy, vmul(qx, qx)));
-			const Vec<W> d1 = vfma(pz, oz, vfma(py, oy, vmul(px, ox)));
-			const Vec<W> d2 = vfma(qz, oz, vfma(qy, oy, vmul(qx, ox)));
+			const Vec<W> d12 = vfma(pz, qz, vfma(py, qy, vmul(px, qx)));                          // r1 . r2
+			const Vec<W> d1 = vfma(pz, oz, vfma(py, oy, vmul(px, ox)));                           // r0 . r1
 			Vec<W> xx, xy, xz;
 			cross_rounded(px, py, pz, ox, oy, oz, k.c0, xx, xy, xz);                              // X = r1 x r0
 			const Vec<W> x2 = vfma(xz, xz, vfma(xy, xy, vmul(xx, xx)));
 			const Vec<W> rs1 = vrsqrt(n1), rs2 = vrsqrt(n2), rsx = vrsqrt(x2);
-			const Vec<W> t212 = vfms(d1, rs1, vmul(d2, rs2));
-			const Vec<W> sa = vmul(vneg(vmul(t212, a.w)), vmul(rsx, rsx));
-			const Vec<W> t222 = vmul(vmul(x2, rsx), vsub(rs1, rs2));
+			const Vec<W> q1 = vmul(n1, rs1), q2 = vmul(n2, rs2);
+			const Vec<W> qs = vadd(q1, q2), P = vmul(rs1, rs2);
+			const Vec<W> iq = vrcp(qs);                                                           // 1/(|r1| + |r2|)
+			const Vec<W> out = vrcp(vfma(q1, q2, d12)), in = vmul(vfms(q1, q2, d12), vmul(rsx, rsx));      // t212/(|X|^2 (1/|r1| + 1/|r2|))
+			const Vec<W> margin = vfma(vmul(n1, c.w), -k.c1, x2);
+			Vec<W> im;
+			for (int i = 0; i < W; ++i) {
+				im.set(i, d12.lane(i) > 0.0f ? out.lane(i) : in.lane(i));
+				flag.set(i, min2_nan(flag.lane(i), margin.lane(i)));
+			}
+			const Vec<W> sa = vmul(vmul(qs, P), vmul(im, -a.w));                                  // -t1 Kf
 			acc[0] = vfma(sa, ox, acc[0]);
 			acc[1] = vfma(sa, oy, acc[1]);
 			acc[2] = vfma(sa, oz, acc[2]);
-			acc[3] = vfma(t222, b.w, acc[3]);
-			const Vec<W> margin = vfma(vmul(n1, c.w), -k.c1, x2);
-			for (int i = 0; i < W; ++i) flag.set(i, min2_nan(flag.lane(i), margin.lane(i)));
+			const Vec<W> s12 = vfma(d1, 2.0f, -c.w);                                              // r0 . (r1 + r2) = |r1|^2 - |r2|^2
+			const Vec<W> bv = vmul(vmul(vmul(x2, rsx), P), vmul(s12, iq));                        // -t222
+			acc[3] = vfma(bv, -b.w, acc[3]);
 		}
 	}
 

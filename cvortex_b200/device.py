@@ -136,7 +136,7 @@ class DeviceBackend:
 
     def f3d_mode(self, mode: int) -> None:
         """Tests / experiments (cvtx_b200_f3d_mode): 0 = cancellation-free filament form, 1 = the
-        reference's formula, -1 = chosen per call from the filaments (the default)."""
+        form that selects per pair (long / few filaments), -1 = chosen per call from the filaments (the default)."""
         self.lib.cvtx_b200_f3d_mode(int(mode))
 
     def sparse_route(self, on: bool) -> None:

@@ -192,8 +192,9 @@ CVTX_B200_API void cvtx_b200_guarded_only(int mode);
  * on = 0 switches that route off, on = 1 (the default) on.  CVTX_B200_SPARSE=0 in the environment does the same. */
 CVTX_B200_API void cvtx_b200_sparse_route(int on);
 /* Experiments and tests only.  The filament ops pick their fast pair form per call from the
- * filaments themselves: 0 pins the cancellation-free form, 1 the
- * reference's formula, anything else restores the automatic choice.  CVTX_B200_F3D_MODE=0|1
+ * filaments themselves: 0 pins the cancellation-free form for short
+ * filaments, 1 the form that selects per pair (long filaments, few filaments), anything else
+ * restores the automatic choice.  CVTX_B200_F3D_MODE=0|1
  * in the environment sets the initial value. */
 CVTX_B200_API void cvtx_b200_f3d_mode(int mode);
 /* Which route the most recent cvtx_*_M2M_* call of the public ABI took:

@@ -47,7 +47,7 @@ template <int W> struct Runner {
 		for (long j = n; j < npad; ++j) pad_source(kind, A[j], B[j], C[j]);
 		for (long j = 0; j < n; ++j) pack_source(kind, src + cols * j, A[j], B[j], C[j]);
 		const PairConsts k = P::make_consts(sigma, nu);
-		int mode = F3D_REF;
+		int mode = F3D_WIDE;
 		if constexpr (P::HYBRID) { mode = pick_f3d_mode(src, n); g_last_f3d_mode = mode; }
 #pragma omp parallel for schedule(static)
 		for (long i0 = 0; i0 < m; i0 += W) {
@@ -78,7 +78,7 @@ template <int W> struct Runner {
 						for (int c = 0; c < P::NACC; ++c) sub[c] = bc<W>(0.0f);
 						for (long j = s0; j < s0 + F3D_SUB; ++j) {
 							if (mode == F3D_NEW) P::template fast<W, F3D_NEW>(tg, A[j], B[j], C[j], sub, flag, k);
-							else P::template fast<W, F3D_REF>(tg, A[j], B[j], C[j], sub, flag, k);
+							else P::template fast<W, F3D_WIDE>(tg, A[j], B[j], C[j], sub, flag, k);
 						}
 						for (int l = 0; l < W; ++l) {
 							if (flag.lane(l) > 0.0f) continue;

@@ -291,7 +291,7 @@ def test_optimistic_chains_give_the_bits_of_the_guarded_form(gpu, oracle, op, re
 # ---- filaments, second version: fast form + per-target reference tier (pair_math.cuh FILAMENTS) ----
 @pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
 def test_filament_forms_and_the_per_call_choice(gpu, oracle, op):
-    """Short segments -> the cancellation-free form by itself, long ones -> the reference's formula; pinned
+    """Short segments -> the cancellation-free form by itself, long ones -> the form that selects per pair; pinned
     either way the answer stays within tolerance (the slow tier takes what the fast form must not), and the
     result is the same for every launch geometry and every cut of the work."""
     from util import filaments

@@ -277,9 +277,10 @@ def test_short_filaments_hold_the_stated_tolerance(hostcheck, oracle, op, seg):
 
 
 @pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
-def test_long_filaments_take_the_reference_formula(hostcheck, oracle, op):
+def test_long_filaments_take_the_form_that_selects_per_pair(hostcheck, oracle, op):
     """The reference's own test recipe (both ends anywhere in the box): most points lie inside a filament's
-    sphere, so the per-call choice falls on the reference's formula and parity is plain 1e-5."""
+    sphere, so the per-call choice falls on the form that picks the non-cancelling expression per pair
+    (F3D_WIDE), only the axis goes to the slow tier, and parity is plain 1e-5."""
     from util import filaments, particles3d
     rng = np.random.default_rng(6)
     fil, tgt = filaments(rng, 1000), particles3d(rng, 1000)
@@ -290,6 +291,27 @@ def test_long_filaments_take_the_reference_formula(hostcheck, oracle, op):
     # pinned to the cancellation-free form it still answers correctly, through the slow tier
     got0, redo0, _ = _f3d_run(hostcheck, op, fil, tgt, 0)
     assert redo0 > 1000 and rel_l2(got0, oracle.m2m(op, fil, tgt)) <= 1e-5
+
+
+@pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
+@pytest.mark.parametrize("n", [1, 2, 4, 40])
+def test_a_few_short_filaments_seen_from_afar(hostcheck, oracle, op, n):
+    """One to a few short segments (0.1 in a box of 10) and points all over the box: the filaments' own
+    bounding box says nothing about where the points are, so the per-call choice is F3D_WIDE.  The segment is
+    1/50 of the distance, the reference's t2 cancels to 1/50 of its terms and sits 4e-6 ... 1.5e-5 from FP64;
+    the first version of this kernel evaluated that formula with MUFU.RSQ and was 2 - 3x further out (found by
+    random draws on the GPU).  Neither fast form cancels in its scalar factor (F3D_WIDE keeps the reference's cross product and with it
+    the reference's error of c, once instead of three times): inside 1e-5 of FP64 and closer than the reference."""
+    from util import filaments, particles3d
+    for seed in range(6):
+        rng = np.random.default_rng(100 * n + seed)
+        fil, tgt = filaments(rng, n, seg=0.1), particles3d(rng, 1500)
+        tgt = tgt if op.endswith("dvort") else np.ascontiguousarray(tgt[:, :3])
+        f32, f64 = oracle.m2m(op, fil, tgt), oracle.m2m(op, fil, tgt, f64=True)
+        for mode in (-1, 0, 1):
+            got, _, used = _f3d_run(hostcheck, op, fil, tgt, mode)
+            e_gpu, e_ref = rel_l2(got, f64), rel_l2(f32, f64)
+            assert e_gpu <= 1e-5 and e_gpu <= e_ref + 2e-7, (n, seed, mode, used, e_gpu, e_ref)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -329,5 +351,5 @@ def test_filament_mode_is_a_property_of_the_sources_alone(hostcheck):
         _, _, mode = _f3d_run(hostcheck, "F3D_M2M_vel", fil, points(rng, m, 3, box), -1)
         modes.add(mode)
     assert modes == {0}
-    line, _ = vortex_line((0.6, 0.8, 0))           # a straight line of filaments: volume-less cloud -> reference formula
+    line, _ = vortex_line((0.6, 0.8, 0))           # a straight line of filaments: volume-less cloud -> the per-pair selecting form
     assert _f3d_run(hostcheck, "F3D_M2M_vel", line, points(rng, 50, 3), -1)[2] == 1

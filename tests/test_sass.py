@@ -56,10 +56,12 @@ def test_loops_match_the_declared_work_per_pair(loops):
             continue                                  # zeta = 0: the compiler deletes the loop body
         if name.startswith("F3D"):
             # filament tiers: the declared work is the cancellation-free form's; the loop also carries one scalar
-            # multiply per SOURCE (tau l^2), i.e. 1/T per pair.  The reference-formula loop: 41 / 47 lane-ops, 3 MUFU.
-            want = {"new": (info["lane_ops"], info["sfu_ops"]), "ref": ({"F3DVel": 41, "F3DDvort": 47}[name], 3)}[row["form"]]
+            # multiply per SOURCE (tau l^2), i.e. 1/T per pair.  The loop that selects per pair (F3D_WIDE): the
+            # reference's rounded cross product, 39 / 55 lane-ops, 4 / 5 MUFU, a compare + select next to the flag's minimum.
+            wide = {"F3DVel": (39, 4), "F3DDvort": (55, 5)}[name]
+            want = {"new": (info["lane_ops"], info["sfu_ops"], 1.0), "wide": (wide[0], wide[1], 2.0)}[row["form"]]
             assert want[0] <= row["lane_ops"] <= want[0] + 1.0 / row["T"] + 1e-9, (row, info)
-            assert row["mufu"] == want[1] and row["alu"] == 1.0, (row, info)
+            assert row["mufu"] == want[1] and row["alu"] == want[2], (row, info)
             seen += 1
             continue
         assert row["lane_ops"] == info["lane_ops"], (row, info)

@@ -76,9 +76,9 @@ def loop_table(text):
 			form = "guarded" if alu else "plain"
 			if pol.startswith("F3D"):
 				# filament tiers (pair_math.cuh FILAMENTS): every fast pair feeds its target's flag through exactly one
-				# NaN-keeping minimum -- FMNMX3 in the cancellation-free form, FMNMX in the reference's formula
+				# NaN-keeping minimum -- FMNMX3 in the cancellation-free form, FMNMX in the form that selects per pair
 				pairs = max(sum(v for k, v in c.items() if k.startswith("FMNMX") and ".NAN" in k), 1)
-				form = "new" if any(k.startswith("FMNMX3") for k in c) else "ref"
+				form = "new" if any(k.startswith("FMNMX3") for k in c) else "wide"
 			total = len(loop)
 			rest = collections.Counter({k: v for k, v in c.items() if not re.match(r"F(FMA|MUL|ADD)", k) and not k.startswith(("MUFU", "LDS"))})
 			rows.append({"kernel": d, "policy": pol, "T": T, "form": form, "pairs": pairs,
