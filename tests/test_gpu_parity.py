@@ -356,13 +356,23 @@ def test_random_shapes_against_the_oracle(gpu, oracle):
         if op == "P3D_M2M_vort" and np.linalg.norm(f64) == 0:
             assert np.all(np.asarray(got) == 0), (k, op, reg, n, m)
             continue
+        if np.abs(f64).max() < 1e-30:
+            # a Gaussian tail and nothing else (a few targets, every source 12+ sigma away): the sums are FP32 denormals
+            # or close to them, which MUFU.EX2 flushes to zero and the CPU's expf rounds to a few bits -- zero either way
+            assert np.abs(np.asarray(got)).max() < 1e-30, (k, op, reg, n, m)
+            continue
         # non-strict: a draw may be dominated by one near pair (Gaussian) or by short segments (filaments), where
         # the FP32 reference is itself further than 1e-5 from FP64; then the GPU has to be as close to FP64 as it is
         # (Gaussian stretching in deep overlap -- tens of thousands of particles at sigma = 0.3: g = erf - ... cancels to 1e-4
         # of its terms for the many pairs at rho < 0.3, and MUFU.EX2 / RCP (1 - 2 ulp) are noisier there than libm's exp and a
         # division: up to ~4.5x the reference's own distance from FP64 has been seen)
         slack = 6.0 if (op, reg) == ("P3D_M2M_dvort", "gaussian") else 3.0
-        assert_parity(got, f32, f64, "f3d" if op.startswith("F3D") else False, f"draw {k}: {op}/{reg} n={n} m={m} sigma={sigma}", slack=slack)
+        # filaments: the two-sided filament bar when the array is a sum over enough pairs to be a statistic; with a handful
+        # of pairs (one short filament seen from a few points) the error is the rounding of ONE cross product r1 x r2,
+        # which enters once here and three times with the other sign there -- a coin flip which of the two is closer to
+        # FP64 (0.5x ... 2.8x seen), both inside 2e-5
+        rule = ("f3d" if n * m >= 2000 else False) if op.startswith("F3D") else False
+        assert_parity(got, f32, f64, rule, f"draw {k}: {op}/{reg} n={n} m={m} sigma={sigma}", slack=slack)
 
 
 @pytest.mark.parametrize("n", [5_000, 70_000])
