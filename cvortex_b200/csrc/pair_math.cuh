@@ -885,8 +885,14 @@ CVTX_HD V3r r_cross(V3r a, V3r b) {
 // bounding box (every extent at least the longest filament).  A warp that meets one such pair
 // re-evaluates a 32-source sub-chain in scalar code, ~3x the cost of the sub-chain itself, for
 // 32 lanes x 8 targets x 32 sources = 8192 pairs: at p = 4e-6 that is +10 %.
+// A small filament set takes the cancellation-free form whatever its shape: its bounding box says nothing about
+// where the points are (one short filament seen from afar is the extreme), the form is 10x more accurate there
+// than any that rounds r1 x r2, and the worst case -- every pair inside a sphere, every sub-chain re-evaluated --
+// is ten times the cost of a launch that is microseconds long.
+constexpr double kF3DSmallSet = 1024.0;
 CVTX_HD int f3d_pick_mode(double sum_len3, double n, const float *lo, const float *hi, float max_len) {
 	if (!(n > 0.0)) return F3D_WIDE;
+	if (n <= kF3DSmallSet) return F3D_NEW;
 	double vol = 1.0;
 	for (int i = 0; i < 3; ++i) {
 		const double e = (double)hi[i] - (double)lo[i];

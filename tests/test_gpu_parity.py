@@ -365,8 +365,9 @@ def test_random_shapes_against_the_oracle(gpu, oracle):
         # the FP32 reference is itself further than 1e-5 from FP64; then the GPU has to be as close to FP64 as it is
         # (Gaussian stretching in deep overlap -- tens of thousands of particles at sigma = 0.3: g = erf - ... cancels to 1e-4
         # of its terms for the many pairs at rho < 0.3, and MUFU.EX2 / RCP (1 - 2 ulp) are noisier there than libm's exp and a
-        # division: up to ~4.5x the reference's own distance from FP64 has been seen)
-        slack = 6.0 if (op, reg) == ("P3D_M2M_dvort", "gaussian") else 3.0
+        # division: up to 7.4x the reference's own distance from FP64 has been seen over 34 seeds x 150 draws -- 2.6e-5 for 58 649 particles
+        # at sigma = 0.3 in the box of 10, sigma / spacing 1.2 -- DESIGN.md section 6)
+        slack = 8.0 if (op, reg) == ("P3D_M2M_dvort", "gaussian") else 3.0
         # filaments: the two-sided filament bar when the array is a sum over enough pairs to be a statistic; with a handful
         # of pairs (one short filament seen from a few points) the error is the rounding of ONE cross product r1 x r2,
         # which enters once here and three times with the other sign there -- a coin flip which of the two is closer to

@@ -283,10 +283,10 @@ def test_long_filaments_take_the_form_that_selects_per_pair(hostcheck, oracle, o
     (F3D_WIDE), only the axis goes to the slow tier, and parity is plain 1e-5."""
     from util import filaments, particles3d
     rng = np.random.default_rng(6)
-    fil, tgt = filaments(rng, 1000), particles3d(rng, 1000)
+    fil, tgt = filaments(rng, 2000), particles3d(rng, 1000)
     tgt = tgt if op.endswith("dvort") else np.ascontiguousarray(tgt[:, :3])
     got, redo, mode = _f3d_run(hostcheck, op, fil, tgt, -1)
-    assert mode == 1 and redo < 50
+    assert mode == 1 and redo < 100
     assert rel_l2(got, oracle.m2m(op, fil, tgt)) <= 1e-5
     # pinned to the cancellation-free form it still answers correctly, through the slow tier
     got0, redo0, _ = _f3d_run(hostcheck, op, fil, tgt, 0)
@@ -351,5 +351,7 @@ def test_filament_mode_is_a_property_of_the_sources_alone(hostcheck):
         _, _, mode = _f3d_run(hostcheck, "F3D_M2M_vel", fil, points(rng, m, 3, box), -1)
         modes.add(mode)
     assert modes == {0}
-    line, _ = vortex_line((0.6, 0.8, 0))           # a straight line of filaments: volume-less cloud -> the per-pair selecting form
-    assert _f3d_run(hostcheck, "F3D_M2M_vel", line, points(rng, 50, 3), -1)[2] == 1
+    long_ones = filaments(rng, 3000)               # both ends anywhere in the box: the per-pair selecting form
+    assert _f3d_run(hostcheck, "F3D_M2M_vel", long_ones, points(rng, 50, 3), -1)[2] == 1
+    few, _ = vortex_line((0.6, 0.8, 0))            # a small set (40 collinear filaments, a volume-less cloud): the
+    assert _f3d_run(hostcheck, "F3D_M2M_vel", few, points(rng, 50, 3), -1)[2] == 0      # cancellation-free form whatever its shape
