@@ -345,13 +345,14 @@ def test_random_shapes_against_the_oracle(gpu, oracle):
     lib, dev = gpu
     rng = np.random.default_rng(int(os.environ.get("CVTX_TEST_SEED", "2026")))      # (other seeds / more draws: stress runs)
     cases = op_cases() + vort_cases()
+    box = float(os.environ.get("CVTX_TEST_BOX", "10"))                                # (stress runs: other length scales)
     for k in range(int(os.environ.get("CVTX_TEST_DRAWS", "60"))):
         op, reg = cases[int(rng.integers(len(cases)))]
         n = int(np.exp(rng.uniform(0, np.log(60_000))))
         m = int(np.exp(rng.uniform(0, np.log(4_000))))
-        sigma = float(rng.choice([0.02, 0.05, 0.3]))
+        sigma = float(rng.choice([0.02, 0.05, 0.3])) * box / 10.0
         base = "P3D_M2M_vel" if op == "P3D_M2M_vort" else op
-        src, tgt = make_case(base, rng, n, m, self_targets=bool(rng.integers(2)) and m <= n)
+        src, tgt = make_case(base, rng, n, m, box=box, self_targets=bool(rng.integers(2)) and m <= n)
         got, f32, f64 = run_all(gpu, oracle, op, reg, src, tgt, sigma)
         if op == "P3D_M2M_vort" and np.linalg.norm(f64) == 0:
             assert np.all(np.asarray(got) == 0), (k, op, reg, n, m)
