@@ -420,3 +420,52 @@ def test_a_page_locked_result_array_is_written_directly(gpu, torch_cuda, m):
     got = lib.P3D_M2M_vel(src, mes, "winckelmans", 0.05, out=pinned[5:5 + m])
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.all(pinned[:5] == -7.0) and np.all(pinned[5 + m:] == -7.0)
+
+
+def test_concurrent_callers_get_their_own_results(gpu, torch_cuda):
+    """Four host threads in the library at once -- two through the cvtx_* ABI (one staging area: they take turns), two
+    through the device-pointer ABI on their own streams (one arena per device: ordered by an event) -- each with its
+    own inputs, many times over: every result is the bits the same call returns alone."""
+    import threading
+    torch = torch_cuda
+    lib, dev = gpu
+    rng = np.random.default_rng(77)
+    jobs = []
+    for k, (op, reg, n, m) in enumerate([("P3D_M2M_vel", "winckelmans", 9_000, 4_000), ("P3D_M2M_dvort", "gaussian", 3_000, 2_500),
+                                         ("P3D_M2M_vel", "gaussian", 20_000, 1_000), ("P2D_M2M_vel", "singular", 6_000, 6_000)]):
+        src, tgt = make_case(op, rng, n, m)
+        jobs.append((k, op, reg, np.ascontiguousarray(src), np.ascontiguousarray(tgt)))
+
+    def host_call(job):
+        _, op, reg, src, tgt = job
+        return np.array(call_abi(lib, op, src, tgt, reg, 0.05, 0.1), copy=True)
+
+    def device_call(job, stream):
+        _, op, reg, src, tgt = job
+        with torch.cuda.stream(stream):
+            s, t = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
+            out = torch.full((tgt.shape[0], SHAPES[op][2]), float("nan"), device="cuda")
+            dev.m2m(op, reg, 0, stream.cuda_stream, s, src.shape[0], t, tgt.shape[0], out, 0.05, 0.1)
+            stream.synchronize()
+            return out.cpu().numpy()
+
+    streams = [torch.cuda.Stream() for _ in jobs]
+    alone = [host_call(j) if j[0] < 2 else device_call(j, streams[j[0]]) for j in jobs]
+    errors = []
+
+    def worker(job):
+        try:
+            for _ in range(25):
+                got = host_call(job) if job[0] < 2 else device_call(job, streams[job[0]])
+                if not np.array_equal(got.view(np.uint32), alone[job[0]].view(np.uint32)):
+                    errors.append((job[0], job[1], float(np.abs(got - alone[job[0]]).max())))
+                    return
+        except Exception as exc:      # noqa: BLE001 - reported below
+            errors.append((job[0], job[1], repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
