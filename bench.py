@@ -503,8 +503,27 @@ class Bench:
             dt = time.perf_counter() - t0
         finally:
             self.api.use_only(self.local_rank)
+        # outside the timed region: the same calls on THIS rank's GPU alone for a stride sample of the targets.  A target's
+        # result does not depend on which other targets share the call or on how many devices took part
+        # (tests/test_gpu_multidevice.py; skipped on one-GPU boxes, so the driver's scaling run carries the check too).
+        idx = np.arange(0, m, max(1, m // 4096))
+        same = True
+        for op, reg in ops:
+            rows = (TP if op in PARTICLE_TARGETS else X)[idx]
+            rows = np.ascontiguousarray(rows)
+            tg = PointerRows(rows, rows.shape[1]) if op in PARTICLE_TARGETS else rows
+            fn = getattr(self.lib, op)
+            if op.startswith("F3D"):
+                one = fn(srcs, tg)
+            elif op.endswith("visc_dvort"):
+                one = fn(srcs, tg, reg, SIGMA, NU)
+            else:
+                one = fn(srcs, tg, reg, SIGMA)
+            same = same and bool(np.array_equal(np.asarray(one).reshape(len(idx), -1).view(np.uint32),
+                                                host_o[op][idx].reshape(len(idx), -1).view(np.uint32)))
         return {"value": float(n) * m * len(ops) * steps / dt / 1e9, "unit": "Gpair/s", "ms_per_step": 1e3 * dt / steps, "steps": steps,
                 "devices_used": used, "exchange": self.be.exchange_backend(),
+                "bits_equal_to_one_gpu": same, "checked_targets": int(len(idx)),
                 "api": "cvtx_*_M2M_* C ABI from ONE process, all accelerators enabled, host arrays of pointers; "
                        "sharded upload + NCCL all-gather of the source rows inside libcvortex.so"}
 
