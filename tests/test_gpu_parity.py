@@ -469,3 +469,21 @@ def test_concurrent_callers_get_their_own_results(gpu, torch_cuda):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("op", ["F3D_M2M_vel", "F3D_M2M_dvort"])
+def test_a_vortex_ring_of_filaments_on_the_gpu(gpu, oracle, op):
+    """tests/test_pair_math_host.py::test_a_vortex_ring_of_filaments through the C ABI: around the core, in the ring's
+    plane (the reference's own rounding decides there) and 100 diameters away (where the reference's t2 is noise)."""
+    from util import vortex_ring_case
+    lib, dev = gpu
+    fil, sets = vortex_ring_case(op)
+    for name, tgt in sets.items():
+        got = call_abi(lib, op, fil, tgt, "singular", 0.3, 0.1)
+        assert dev.last_dispatch() == 1
+        f32, f64 = oracle.m2m(op, fil, tgt), oracle.m2m(op, fil, tgt, f64=True)
+        e_gpu, e_ref = rel_l2(got, f64), rel_l2(f32, f64)
+        print(f"{op} ring, points {name}: gpu-vs-f64 {e_gpu:.2e}, ref-vs-f64 {e_ref:.2e}, gpu-vs-ref {rel_l2(got, f32):.2e}")
+        assert e_gpu <= 1.1 * e_ref + 5e-7, (name, e_gpu, e_ref)
+        if e_ref <= 1e-5:
+            assert e_gpu <= 1e-5, (name, e_gpu, e_ref)

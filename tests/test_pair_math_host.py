@@ -364,19 +364,9 @@ def test_a_vortex_ring_of_filaments(hostcheck, oracle, op):
     No further from FP64 than the reference (whose cancelling t2 loses digits far from the ring), within 1e-5 of FP64 where
     the reference is; in the ring's plane the reference is 6e-5 (velocity) and 6e-2 (stretching) from FP64 and this
     implementation 2e-5 and 6e-2."""
-    n = 3000
-    phi = np.linspace(0.0, 2.0 * np.pi, n + 1)
-    nodes = np.stack([5.0 + 2.0 * np.cos(phi), 5.0 + 2.0 * np.sin(phi), np.full_like(phi, 5.0)], axis=1).astype(np.float32)
-    fil = np.zeros((n, 7), np.float32)
-    fil[:, 0:3], fil[:, 3:6], fil[:, 6] = nodes[:-1], nodes[1:], 1.3
-    rng = np.random.default_rng(3)
-    near = nodes[rng.integers(0, n, 300)] + rng.normal(0.0, 0.05, (300, 3)).astype(np.float32)      # the core's neighbourhood
-    plane = np.stack([rng.uniform(0, 10, 400), rng.uniform(0, 10, 400), np.full(400, 5.0)], axis=1)  # the ring's plane
-    far = rng.uniform(-200, 200, (300, 3))                                                             # 100 diameters away
-    for name, pts in (("near", near), ("plane", plane), ("far", far)):
-        pts = np.ascontiguousarray(pts, np.float32)
-        tgt = np.concatenate([pts, np.tile(np.float32([[0.2, -0.4, 0.9, 0.01]]), (len(pts), 1))], axis=1) if op.endswith("dvort") else pts
-        tgt = np.ascontiguousarray(tgt, np.float32)
+    from util import vortex_ring_case
+    fil, sets = vortex_ring_case(op)
+    for name, tgt in sets.items():
         got, _, mode = _f3d_run(hostcheck, op, fil, tgt, -1)
         f32, f64 = oracle.m2m(op, fil, tgt), oracle.m2m(op, fil, tgt, f64=True)
         e_gpu, e_ref = rel_l2(got, f64), rel_l2(f32, f64)

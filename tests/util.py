@@ -179,6 +179,26 @@ def vortex_line(direction, n=40, as_particles=False):
     return fil, pts
 
 
+def vortex_ring_case(op, n=3000):
+    """A closed ring of n short filaments (radius 2 in the box of 10) and three sets of points: around the core,
+    in the ring's plane, 100 diameters away.  Returns (filaments, {name: targets})."""
+    phi = np.linspace(0.0, 2.0 * np.pi, n + 1)
+    nodes = np.stack([5.0 + 2.0 * np.cos(phi), 5.0 + 2.0 * np.sin(phi), np.full_like(phi, 5.0)], axis=1).astype(np.float32)
+    fil = np.zeros((n, 7), np.float32)
+    fil[:, 0:3], fil[:, 3:6], fil[:, 6] = nodes[:-1], nodes[1:], 1.3
+    rng = np.random.default_rng(3)
+    sets = {"near": nodes[rng.integers(0, n, 300)] + rng.normal(0.0, 0.05, (300, 3)).astype(np.float32),
+            "plane": np.stack([rng.uniform(0, 10, 400), rng.uniform(0, 10, 400), np.full(400, 5.0)], axis=1),
+            "far": rng.uniform(-200, 200, (300, 3))}
+    out = {}
+    for name, pts in sets.items():
+        pts = np.ascontiguousarray(pts, np.float32)
+        if op.endswith("dvort"):
+            pts = np.concatenate([pts, np.tile(np.float32([[0.2, -0.4, 0.9, 0.01]]), (len(pts), 1))], axis=1)
+        out[name] = np.ascontiguousarray(pts, np.float32)
+    return fil, out
+
+
 def op_cases():
     """Every (op, regularisation) the reference accelerates."""
     out = []
